@@ -1,0 +1,183 @@
+/*
+ * mdn_loss.h -- C ABI of the B200-native MDN_SfM loss path (libmdn_loss.so).
+ *
+ * The upstream project (chenluchu/MDN_SfM) has no FFI / plugin layer: its loss path is a set of Python
+ * callables (loss_functions.py, loss_utils.py, networks/layers.py, utils.py) made of ATen ops.  This header
+ * is the boundary a maintainer binds INSTEAD of those ATen compositions; each entry point cites the
+ * upstream lines it replaces.  The binding the reference side would add is a ctypes stub -- see
+ * INTEGRATION.md and mdn_sfm_b200/_cabi.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name says host
+ *   - all tensors are contiguous fp32 NCHW (instance masks / validity are uint8), 16-byte aligned
+ *   - the caller owns every buffer including the workspace; entry points enqueue work on `stream`
+ *     (a cudaStream_t passed as void*), never allocate, never synchronise, and are CUDA-graph capturable
+ *   - return 0 on success, a negative MdnStatus otherwise; mdn_last_error_string() explains (thread local)
+ *   - reductions are deterministic (two-stage, fixed order, no floating-point atomics)
+ */
+#ifndef MDN_LOSS_H_
+#define MDN_LOSS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDN_ABI_VERSION 1
+#define MDN_MAX_SCALES 4
+#define MDN_MAX_PAIRS 2
+
+typedef enum MdnStatus {
+  MDN_OK = 0,
+  MDN_ERR_BAD_SHAPE = -1,      /* batch/height/width/n_scales/n_pairs out of range (h,w >= 2 required)      */
+  MDN_ERR_NULL_POINTER = -2,   /* a tensor the requested terms need is NULL                                 */
+  MDN_ERR_MISALIGNED = -3,     /* a tensor pointer is not 16-byte aligned                                   */
+  MDN_ERR_UNSUPPORTED = -4,    /* unknown mode / mask mode / padding mode                                   */
+  MDN_ERR_WORKSPACE = -5,      /* workspace too small (see mdn_loss_workspace_bytes)                        */
+  MDN_ERR_CUDA = -6            /* a CUDA runtime call failed                                                */
+} MdnStatus;
+
+/* Epipolar post-processing of |e|:
+ *   SN  post_process_epipolar_1        loss_utils.py:92-99   (per-sample max normalise, square)
+ *   T   post_pro_epipolar_weighted     loss_utils.py:81-89   (divide by threshold, square)
+ *   TG  same with the Gaussian distance weight of utils.py:355-379 (threshold, then weight, square) */
+typedef enum MdnPost { MDN_POST_SN = 0, MDN_POST_T = 1, MDN_POST_TG = 2 } MdnPost;
+
+/* Which mobile mask a (target, source) pair is masked with:
+ *   MIN     m = min(mob[0], mob[1]) for both pairs, gradient to the arg-min (first on ties) -- loss_functions.py:176-178,188
+ *   OWN     pair i uses mob[i]                                                             -- --disable_min, loss_functions.py:183-186
+ *   SHARED  both pairs use mob[0] as given (LossModule.forward called directly with a mask) -- loss_functions.py:27            */
+typedef enum MdnMaskMode { MDN_MASK_MIN = 0, MDN_MASK_OWN = 1, MDN_MASK_SHARED = 2 } MdnMaskMode;
+
+enum MdnFlags {
+  MDN_TERM_EPIPOLAR   = 1 << 0,  /* LossModule.epipolar_loss          loss_functions.py:117-138              */
+  MDN_TERM_PHOTO      = 1 << 1,  /* LossModule.photo_metric_loss      loss_functions.py:107-115              */
+  MDN_TERM_SMOOTH     = 1 << 2,  /* smooth_loss                       loss_utils.py:151-168                  */
+  MDN_TERM_CONSIS     = 1 << 3,  /* derivable_consistency_loss        loss_utils.py:171-177                  */
+  MDN_OPT_SSIM        = 1 << 4,  /* photo = 0.15*L1 + 0.85*SSIM (else L1 only)  loss_functions.py:111-112    */
+  MDN_OPT_INST_MASK   = 1 << 5,  /* DS: post *= instance mask         loss_utils.py:127-138                  */
+  MDN_OPT_CROSS_ENT   = 1 << 6,  /* DC: + w_d2_sim * cross entropy    loss_utils.py:72-78, loss_functions.py:132-133 */
+  MDN_OPT_GRADS       = 1 << 7   /* also write d(loss)/d(flow, mob, fmat) for an upstream gradient of 1      */
+};
+
+/* One pyramid level.  h = height, w = width of THIS level. */
+typedef struct MdnScale {
+  int32_t height, width;
+  float flow_sx, flow_sy;   /* pixels = flow * (sx, sy): (w, h) for the nets' normalised flow (layers.py:101-103,
+                               loss_functions.py:44), (1, 1) for a flow map already in pixels                   */
+  float scale_div;          /* 2**scale: every term of this level is divided by it (loss_functions.py:40,55,59,147) */
+  float pad_;
+  const float* tgt;                    /* (B,3,h,w) target image ("color",0,s); PHOTO and SMOOTH              */
+  const float* ref[MDN_MAX_PAIRS];     /* (B,3,h,w) source image ("color",i,s); PHOTO                          */
+  const float* flow[MDN_MAX_PAIRS];    /* (B,2,h,w) optical flow target->source; EPIPOLAR and PHOTO            */
+  const float* mob[MDN_MAX_PAIRS];     /* (B,1,h,w) mobile probability maps; EPIPOLAR, SMOOTH, CONSIS          */
+  const float* fmat[MDN_MAX_PAIRS];    /* (B,3,3) fundamental matrix K^-T [t]x R K^-1 (loss_utils.py:50-62)    */
+  const float* weight;                 /* (h,w) TG weight table (utils.py:355-379) or NULL                     */
+  const uint8_t* inst;                 /* (B,h,w) {0,1} instance mask already resized to (h,w), or NULL        */
+  /* gradient outputs for an upstream gradient of 1 (MDN_OPT_GRADS); each may be NULL to skip it */
+  float* g_flow[MDN_MAX_PAIRS];        /* (B,2,h,w) w.r.t. `flow` as passed (flow_sx/sy chain rule applied)   */
+  float* g_mob[MDN_MAX_PAIRS];         /* (B,1,h,w)                                                            */
+  float* g_fmat[MDN_MAX_PAIRS];        /* (B,3,3)                                                              */
+  /* optional per-pixel maps (the `outputs` dict / tuple returns of the reference); NULL to skip */
+  float* post_map[MDN_MAX_PAIRS];      /* (B,1,h,w) post-processed epipolar map  ("epipolars")                */
+  float* ori_map[MDN_MAX_PAIRS];       /* (B,1,h,w) |e|, or |e|/max in SN (upstream aliasing quirk) ("epipolar_ori") */
+  float* warped[MDN_MAX_PAIRS];        /* (B,3,h,w) flow-warped source image ("warps")                        */
+  float* diff[MDN_MAX_PAIRS];          /* (B,3,h,w) |tgt - warped| * valid ("diffs")                          */
+  uint8_t* valid[MDN_MAX_PAIRS];       /* (B,1,h,w) validity mask, one channel ("valids" is its 3x repeat)    */
+  float* ssim_map[MDN_MAX_PAIRS];      /* (B,3,h,w) SSIM distance map                                         */
+} MdnScale;
+
+typedef struct MdnLossDesc {
+  int32_t batch, n_scales, n_pairs;
+  int32_t post;        /* MdnPost     */
+  int32_t mask_mode;   /* MdnMaskMode */
+  int32_t flags;       /* MdnFlags    */
+  float threshold;     /* T / TG divisor (opt.threshold, options.py:84-87); <= 0 means "None" (no division)  */
+  float alpha;         /* weight of the non-trivial-solution term (opt.alpha)                                 */
+  float w_d2_sim;      /* DC cross-entropy weight (opt.w_d2_sim)                                              */
+  float w_e, w_s, w_c, w_p;  /* loss_functions.py:191-194                                                    */
+  float pad_;
+  MdnScale scale[MDN_MAX_SCALES];
+} MdnLossDesc;
+
+/* loss_out layout (MDN_OUT_COUNT = 8 device floats) written by mdn_loss_fused.  MDN_OUT_APPLIED is the upstream
+ * gradient the gradient buffers currently correspond to (1 after mdn_loss_fused); mdn_loss_scale_grads updates it. */
+enum MdnLossOut { MDN_OUT_LOSS = 0, MDN_OUT_EPIP = 1, MDN_OUT_SMOOTH = 2, MDN_OUT_CONSIS = 3, MDN_OUT_PHOTO = 4,
+                  MDN_OUT_APPLIED = 5, MDN_OUT_COUNT = 8 };
+
+int mdn_version(void);
+const char* mdn_last_error_string(void);
+
+/* Bytes of device workspace mdn_loss_fused needs for this description (tile partial sums, per-sample
+ * sums, SN max keys, a completion ticket). */
+size_t mdn_loss_workspace_bytes(const MdnLossDesc* desc);
+
+/*
+ * The whole loss path in one call: replaces Loss.forward (loss_functions.py:170-205) and everything it
+ * reaches -- LossModule.forward / single_mobile_mask_forward (:27-105), epipolar_loss (:117-138) with
+ * get_epipolar_new (loss_utils.py:39-69) and the SN/T/TG/DS/DC post-processing (:72-138), photo_metric_loss
+ * (:107-115) with inverse_warp (loss_utils.py:12-36) and SSIM (networks/layers.py:148-178), smooth_loss
+ * (loss_utils.py:151-168), consistency_loss (:140-147 / loss_utils.py:171-177), the min mask (:176-178),
+ * create_coords (:150-157) and get_scale_factor (layers.py:101-103) -- for all scales and both source
+ * frames, forward AND (with MDN_OPT_GRADS) the gradients w.r.t. flow, mobile maps and fundamental matrices
+ * for an upstream gradient of 1.  With a single scale / pair and a subset of the MDN_TERM_* flags it is
+ * also what the individual reference functions map to.
+ *
+ *   loss_out[MDN_OUT_EPIP]   = sum_s sum_i (mean(bg*post) + alpha*mean|m log(bg+1e-5)| [+ w_d2_sim*mean(CE)]) / scale_div
+ *   loss_out[MDN_OUT_SMOOTH] = sum_s sum_i smooth_loss / scale_div
+ *   loss_out[MDN_OUT_CONSIS] = sum_s mean((sig(20(m0-.5)) - sig(20(m1-.5)))^2) / scale_div
+ *   loss_out[MDN_OUT_PHOTO]  = sum_s sum_i (0.15*mean(diff) + 0.85*mean(SSIM)  |  mean(diff)) / scale_div
+ *   loss_out[MDN_OUT_LOSS]   = w_e*EPIP + w_s*SMOOTH + w_c*CONSIS + w_p*PHOTO
+ */
+int mdn_loss_fused(const MdnLossDesc* desc, float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Backward of the call above for an arbitrary upstream gradient: multiplies every gradient buffer named in
+ * `desc` by (*g / *applied) and stores *g into *applied.  When *g == *applied (the usual loss.backward(),
+ * g == 1) the kernel exits without touching memory.  `g` and `applied` are device scalars.
+ */
+int mdn_loss_scale_grads(const MdnLossDesc* desc, const float* g, float* applied, void* stream);
+
+/*
+ * get_epipolar_new (loss_utils.py:39-69) for arbitrary homogeneous point sets: p1, p2 are (B,3,N), fmat
+ * (B,3,3); out (B,1,N) is the SIGNED distance.  The backward takes the upstream gradient g_out (B,1,N)
+ * and writes g_p1, g_p2 (B,3,N, either may be NULL) and g_fmat (B,3,3, may be NULL).
+ */
+int mdn_epipolar_points_fwd(const float* p1, const float* p2, const float* fmat, float* out, int32_t batch,
+                            int64_t n, void* stream);
+int mdn_epipolar_points_bwd(const float* p1, const float* p2, const float* fmat, const float* g_out, float* g_p1,
+                            float* g_p2, float* g_fmat, int32_t batch, int64_t n, void* workspace,
+                            size_t workspace_bytes, void* stream);
+size_t mdn_epipolar_points_workspace_bytes(int32_t batch, int64_t n);
+
+/*
+ * inverse_warp (loss_utils.py:12-36) / FlowWarp (utils.py:289-315): bilinear flow warp, zeros padding,
+ * align_corners=True.  flow is in pixels.  warped (B,C,h,w) may be NULL (FlowWarp: grid + validity only);
+ * grid_out (B,h,w,2) normalised grid or NULL; valid (B,h,w) uint8 or NULL.  `flowwarp_norm` selects the
+ * (g-0.5)*2 normalisation of utils.py:311 instead of 2*g-1 (loss_utils.py:31) -- same value, other rounding.
+ * The backward takes g_warped (B,C,h,w) and writes g_flow (B,2,h,w).
+ */
+int mdn_flow_warp_fwd(const float* ref, const float* flow, float* warped, float* grid_out, uint8_t* valid,
+                      int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t flowwarp_norm,
+                      void* stream);
+int mdn_flow_warp_bwd(const float* ref, const float* flow, const float* g_warped, float* g_flow, int32_t batch,
+                      int32_t channels, int32_t height, int32_t width, void* stream);
+
+/*
+ * SSIM module (networks/layers.py:148-178): out = clamp((1 - SSIM(x,y))/2, 0, 1), 3x3 reflect-padded.
+ * x, y, out, g_out, g_x, g_y are (planes,h,w) with planes = B*C.  g_x / g_y may be NULL.
+ */
+int mdn_ssim_fwd(const float* x, const float* y, float* out, int32_t planes, int32_t height, int32_t width,
+                 void* stream);
+int mdn_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* g_y, int32_t planes,
+                 int32_t height, int32_t width, void* stream);
+
+/* binary_image (utils.py:100-103): out = x >= threshold ? 1 : 0 */
+int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDN_LOSS_H_ */

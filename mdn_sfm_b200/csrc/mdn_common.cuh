@@ -1,0 +1,193 @@
+// mdn_common.cuh -- per-pixel math of the MDN_SfM loss path, written once and shared by every kernel.
+//
+// Each helper replays the fp32 operation ORDER of the upstream ATen composition it cites (separate
+// roundings via __f*_rn where the reference rounds separately and a contraction would change a floor(),
+// a validity bit or a cancellation), because parity (fwd 1e-5, grads 1e-4, masks bit exact) is only
+// reachable that way (SURVEY.md section 7 "hard parts").
+#pragma once
+
+#ifdef MDN_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define MDN_DYN_SMEM(name) extern __shared__ __align__(16) float name[]
+#define MDN_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
+#include <stdint.h>
+
+#define MDN_DEV __device__ __forceinline__
+
+namespace mdn {
+
+// ---------------------------------------------------------------------------------------------------
+// Epipolar distance, loss_utils.py:64-67 with p1 = (x, y, 1), p2 = (u, v, 1) (loss_functions.py:120-122).
+// Fully intrinsic so that the SN max pre-pass and the main pass produce bit-identical values.
+struct Epi {
+  float a, b, c;   // F p1
+  float s, den;    // sqrt(a^2+b^2+1e-10), s + 1e-10
+  float d;         // signed distance
+};
+
+MDN_DEV Epi epipolar_distance(const float* F, float x, float y, float u, float v) {
+  Epi e;
+  // bmm row . (x, y, 1): k-ordered FMA chain
+  e.a = __fmaf_rn(F[2], 1.f, __fmaf_rn(F[1], y, __fmul_rn(F[0], x)));
+  e.b = __fmaf_rn(F[5], 1.f, __fmaf_rn(F[4], y, __fmul_rn(F[3], x)));
+  e.c = __fmaf_rn(F[8], 1.f, __fmaf_rn(F[7], y, __fmul_rn(F[6], x)));
+  // (Fp1 * p2).sum(1): three separately rounded products, summed in order
+  float num = __fadd_rn(__fadd_rn(__fmul_rn(e.a, u), __fmul_rn(e.b, v)), e.c);
+  float ss = __fadd_rn(__fadd_rn(__fmul_rn(e.a, e.a), __fmul_rn(e.b, e.b)), 1e-10f);
+  e.s = __fsqrt_rn(ss);
+  e.den = __fadd_rn(e.s, 1e-10f);
+  e.d = __fdiv_rn(num, e.den);
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Flow -> sampling coordinates, loss_utils.py:27-34 followed by grid_sample's un-normalisation
+// (align_corners=True): every op rounded on its own, exactly as the separate ATen kernels do.
+struct WarpCoord {
+  float gx, gy;    // normalised grid in [-1,1]
+  float ix, iy;    // un-normalised source coordinates
+  bool valid;      // max(|gx|,|gy|) <= 1
+};
+
+MDN_DEV WarpCoord warp_coord(float x, float y, float fx, float fy, float wm1, float hm1, bool flowwarp_norm = false) {
+  WarpCoord c;
+  float px = __fadd_rn(x, fx), py = __fadd_rn(y, fy);
+  float gx = __fdiv_rn(px, wm1), gy = __fdiv_rn(py, hm1);
+  if (flowwarp_norm) {  // utils.py:311  (g - 0.5) * 2
+    gx = __fmul_rn(__fsub_rn(gx, 0.5f), 2.f);
+    gy = __fmul_rn(__fsub_rn(gy, 0.5f), 2.f);
+  } else {              // loss_utils.py:31  2 * g - 1
+    gx = __fsub_rn(__fmul_rn(2.f, gx), 1.f);
+    gy = __fsub_rn(__fmul_rn(2.f, gy), 1.f);
+  }
+  c.gx = gx; c.gy = gy;
+  c.valid = (fabsf(gx) <= 1.f) && (fabsf(gy) <= 1.f);
+  c.ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), wm1);
+  c.iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), hm1);
+  return c;
+}
+
+// Bilinear footprint (grid_sample, bilinear, zeros padding): corner offsets + weights + in-bounds bits.
+struct Bilin {
+  int x0, y0;
+  float ax0, ax1, ay0, ay1;   // (x0+1-ix), (ix-x0), (y0+1-iy), (iy-y0)
+  bool xl, xr, yt, yb;        // corner column / row inside the image
+};
+
+MDN_DEV Bilin bilinear_setup(float ix, float iy, int h, int w) {
+  Bilin b;
+  float x0f = floorf(ix), y0f = floorf(iy);
+  b.ax0 = (x0f + 1.f) - ix; b.ax1 = ix - x0f;
+  b.ay0 = (y0f + 1.f) - iy; b.ay1 = iy - y0f;
+  b.x0 = __float2int_rd(ix); b.y0 = __float2int_rd(iy);
+  b.xl = (b.x0 >= 0) & (b.x0 < w);
+  b.xr = (b.x0 >= -1) & (b.x0 < w - 1);
+  b.yt = (b.y0 >= 0) & (b.y0 < h);
+  b.yb = (b.y0 >= -1) & (b.y0 < h - 1);
+  return b;
+}
+
+// One channel: value and d(value)/d(ix), d(value)/d(iy) (GridSampler.cu backward formulas).
+MDN_DEV void bilinear_fetch(const float* __restrict__ plane, int w, const Bilin& b, float& nw, float& ne, float& sw,
+                            float& se) {
+  const float* r0 = plane + (long long)b.y0 * w + b.x0;
+  nw = (b.yt && b.xl) ? __ldg(r0) : 0.f;
+  ne = (b.yt && b.xr) ? __ldg(r0 + 1) : 0.f;
+  sw = (b.yb && b.xl) ? __ldg(r0 + w) : 0.f;
+  se = (b.yb && b.xr) ? __ldg(r0 + w + 1) : 0.f;
+}
+
+MDN_DEV float bilinear_value(const Bilin& b, float nw, float ne, float sw, float se) {
+  float o = nw * (b.ax0 * b.ay0);
+  o += ne * (b.ax1 * b.ay0);
+  o += sw * (b.ax0 * b.ay1);
+  o += se * (b.ax1 * b.ay1);
+  return o;
+}
+
+MDN_DEV void bilinear_deriv(const Bilin& b, float nw, float ne, float sw, float se, float& ddx, float& ddy) {
+  ddx = b.ay0 * (ne - nw) + b.ay1 * (se - sw);
+  ddy = b.ax0 * (sw - nw) + b.ax1 * (se - ne);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SSIM, networks/layers.py:164-178, from the five 3x3 window SUMS (reflect padding applied by the caller).
+struct SsimOut {
+  float J;            // clamp((1 - n/d)/2, 0, 1)
+  float dmu_y, dY2, dXY;   // dz/d(mu_y) (total, incl. through sigma_y, sigma_xy), dz/dE[y^2], dz/dE[xy]; 0 outside the clamp gate
+  float dmu_x, dX2;        // same for x (used by the standalone SSIM backward)
+};
+
+MDN_DEV SsimOut ssim_window(float sx, float sy, float sxx, float syy, float sxy, bool want_grad) {
+  const float C1 = 0.0001f, C2 = 0.0009f;
+  float mu_x = __fdiv_rn(sx, 9.f), mu_y = __fdiv_rn(sy, 9.f);
+  float sig_x = __fsub_rn(__fdiv_rn(sxx, 9.f), __fmul_rn(mu_x, mu_x));
+  float sig_y = __fsub_rn(__fdiv_rn(syy, 9.f), __fmul_rn(mu_y, mu_y));
+  float sig_xy = __fsub_rn(__fdiv_rn(sxy, 9.f), __fmul_rn(mu_x, mu_y));
+  float n1 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, mu_x), mu_y), C1);
+  float n2 = __fadd_rn(__fmul_rn(2.f, sig_xy), C2);
+  float d1 = __fadd_rn(__fadd_rn(__fmul_rn(mu_x, mu_x), __fmul_rn(mu_y, mu_y)), C1);
+  float d2 = __fadd_rn(__fadd_rn(sig_x, sig_y), C2);
+  float n = __fmul_rn(n1, n2), D = __fmul_rn(d1, d2);
+  float z = __fmul_rn(__fsub_rn(1.f, __fdiv_rn(n, D)), 0.5f);
+  SsimOut o;
+  o.J = fminf(fmaxf(z, 0.f), 1.f);
+  o.dmu_y = o.dY2 = o.dXY = o.dmu_x = o.dX2 = 0.f;
+  if (want_grad && z >= 0.f && z <= 1.f) {   // clamp backward gate is inclusive
+    float invD = 1.f / D;
+    float nbar = -0.5f * invD;            // dz/dn
+    float Dbar = 0.5f * n * invD * invD;  // dz/dD
+    float dn1 = nbar * n2, dn2 = nbar * n1, dd1 = Dbar * d2, dd2 = Dbar * d1;
+    o.dmu_y = 2.f * mu_x * (dn1 - dn2) + 2.f * mu_y * (dd1 - dd2);
+    o.dmu_x = 2.f * mu_y * (dn1 - dn2) + 2.f * mu_x * (dd1 - dd2);
+    o.dY2 = dd2;
+    o.dX2 = dd2;
+    o.dXY = 2.f * dn2;
+  }
+  return o;
+}
+
+MDN_DEV int reflect1(int t, int n) {   // ReflectionPad2d(1): -1 -> 1, n -> n-2
+  t = t < 0 ? -t : t;
+  return t >= n ? 2 * n - 2 - t : t;
+}
+
+// multiplicity with which window centre p (in image) touches pixel q along one axis of length n
+MDN_DEV int refl_mult(int p, int q, int n) {
+  int c = 0;
+#pragma unroll
+  for (int d = -1; d <= 1; ++d) c += (reflect1(p + d, n) == q);
+  return c;
+}
+
+MDN_DEV float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+MDN_DEV float signf_(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+// ---------------------------------------------------------------------------------------------------
+// Transposing butterfly: reduces NV per-lane values over the 32 lanes of a warp with NV-ish shuffles
+// instead of 5*NV.  On return lane l holds, in v[0], the warp total of value (l % NV).
+template <int NV>
+MDN_DEV void warp_reduce_transpose(float* v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int m = 16; m >= NV && m >= 1; m >>= 1) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], m);
+  }
+#pragma unroll
+  for (int half = NV / 2; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      float send = up ? v[i] : v[i + half];
+      float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+}
+
+}  // namespace mdn

@@ -1,0 +1,1048 @@
+// mdn_loss.cu -- B200 (sm_100a) kernels + C ABI of the MDN_SfM loss path.  See include/mdn_loss.h.
+//
+// Kernel inventory
+//   sn_max_kernel        per-sample max / first arg-max of |e| (SN post-processing pre-pass, loss_utils.py:96)
+//   fused_tile_kernel    ONE launch over every (scale, sample, 32x16 tile): epipolar map + post-processing +
+//                        masked reductions, bilinear flow warp, SSIM + L1, smoothness, consistency, min mask,
+//                        forward values AND gradients (upstream gradient 1), per-tile partial sums
+//   finish_kernel        deterministic second stage: per-sample sums -> d/dF, SN arg-max fix-up, loss scalars
+//   scale_grads_kernel   backward for an upstream gradient != 1 (exits immediately when it is 1)
+//   small standalone kernels for the individually exported reference functions
+//
+// All of it is bandwidth/latency-bound stencil + gather work: no tensor cores by design.
+#include "mdn_common.cuh"
+#include "../../include/mdn_loss.h"
+
+#include <stdio.h>
+#include <string.h>
+
+namespace mdn {
+
+// ----------------------------------------------------------------------------------------------- geometry
+constexpr int TW = 32, TH = 16;                       // interior tile
+constexpr int R2W = TW + 4, R2H = TH + 4, R2N = R2W * R2H;   // halo 2: target + warped image
+constexpr int R1W = TW + 2, R1H = TH + 2, R1N = R1W * R1H;   // halo 1: SSIM windows, masks
+constexpr int TN = TW * TH;
+constexpr int NTHREADS = 256;
+
+// partial-sum slots per tile
+constexpr int PAIR_SLOTS = 16;   // epi, nt, ce, l1, ssim, gF[9], pad, pad
+constexpr int SL_EPI = 0, SL_NT = 1, SL_CE = 2, SL_L1 = 3, SL_SSIM = 4, SL_GF = 5;
+constexpr int TAIL_BASE = 2 * PAIR_SLOTS;   // consis, smooth_x[0], smooth_y[0], smooth_x[1], smooth_y[1], pad x3
+constexpr int SL_CONSIS = 0, SL_SMX = 1, SL_SMY = 2;
+constexpr int TAIL_SLOTS = 8;
+constexpr int NSLOT = TAIL_BASE + TAIL_SLOTS;   // 40
+
+struct KScale {
+  int h, w, tiles_x, tiles_y;
+  int tile_begin;          // first tile index of this scale
+  float sx, sy;            // flow -> pixels
+  float wm1, hm1;
+  float c_epi, c_nt, c_ce, c_l1, c_ssim, c_smx, c_smy, c_consis;   // gradient coefficients (upstream 1)
+  const float* tgt; const float* ref[2]; const float* flow[2]; const float* mob[2]; const float* fmat[2];
+  const float* weight; const uint8_t* inst;
+  float* g_flow[2]; float* g_mob[2];
+  float* post_map[2]; float* ori_map[2]; float* warped[2]; float* diff[2]; uint8_t* valid[2]; float* ssim_map[2];
+};
+
+struct KParams {
+  int batch, n_scales, n_pairs, post, mask_mode, flags;
+  int n_tiles;
+  float threshold;
+  float* partials;                   // [n_tiles][NSLOT]
+  const unsigned long long* snkey;   // [n_scales][n_pairs][batch] packed (bits(max)<<32 | ~argmax)
+  KScale sc[MDN_MAX_SCALES];
+};
+
+MDN_DEV float post_process(const KParams& P, const KScale& S, float e, float snmax, int pix, float& dpost_de) {
+  // returns post (before the DS mask) and d(post)/d(e)
+  if (P.post == MDN_POST_SN) {
+    float q = __fdiv_rn(e, snmax);            // loss_utils.py:98
+    dpost_de = 2.f * q / snmax;
+    return __fmul_rn(q, q);                   // :99
+  }
+  float r = e, dr = 1.f;
+  if (P.threshold > 0.f) { r = __fdiv_rn(r, P.threshold); dr = dr / P.threshold; }   // loss_utils.py:85-86
+  if (P.post == MDN_POST_TG) { float wgt = __ldg(S.weight + pix); r = __fdiv_rn(r, wgt); dr = dr / wgt; }   // :87-88
+  dpost_de = 2.f * r * dr;
+  return __fmul_rn(r, r);                     // :89
+}
+
+// ----------------------------------------------------------------------------------------------- SN pre-pass
+__global__ void __launch_bounds__(NTHREADS) sn_max_kernel(const KParams P, unsigned long long* keys, int chunks_per_img) {
+  // grid.x = chunk within image, grid.y = (scale * n_pairs + pair) * batch + b
+  int job = blockIdx.y;
+  int b = job % P.batch;
+  int sp = job / P.batch;
+  int pair = sp % P.n_pairs, s = sp / P.n_pairs;
+  const KScale& S = P.sc[s];
+  const int hw = S.h * S.w;
+  const float* F = S.fmat[pair] + b * 9;
+  float Fm[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Fm[k] = __ldg(F + k);
+  const float* fx = S.flow[pair] + (long long)b * 2 * hw;
+  const float* fy = fx + hw;
+  unsigned long long best = 0ull;
+  int per = (hw + chunks_per_img - 1) / chunks_per_img;
+  int beg = blockIdx.x * per, end = min(hw, beg + per);
+  for (int i = beg + (int)threadIdx.x; i < end; i += blockDim.x) {
+    int y = i / S.w, x = i - y * S.w;
+    float u = __fadd_rn((float)x, __fmul_rn(S.sx, __ldg(fx + i)));
+    float v = __fadd_rn((float)y, __fmul_rn(S.sy, __ldg(fy + i)));
+    Epi e = epipolar_distance(Fm, (float)x, (float)y, u, v);
+    float ae = fabsf(e.d);
+    if (ae == ae) {   // NaNs never win (torch.max would propagate; degenerate input)
+      unsigned long long key = ((unsigned long long)__float_as_uint(ae) << 32) | (unsigned)(0xffffffffu - (unsigned)i);
+      best = key > best ? key : best;
+    }
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)(best & 0xffffffffu), m);
+    unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(best >> 32), m);
+    unsigned long long o = ((unsigned long long)hi << 32) | lo;
+    best = o > best ? o : best;
+  }
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(keys + job, best);
+}
+
+// ----------------------------------------------------------------------------------------------- fused tile kernel
+struct Smem {
+  float* T;      // [3][R2N] target image
+  float* W;      // [3][R2N] warped source image (current pair)
+  float* M;      // [2][R1N] mask used by pair 0 / 1 (MIN, SHARED: only [0])
+  float* ABC;    // [9][R1N] SSIM adjoint terms per window: (A,B,C) x 3 channels (current pair)
+  float* D;      // [6][TN]  d(warped_c)/d(ix), d(warped_c)/d(iy) at interior pixels (current pair)
+  float* Mbar;   // [2][TN]  accumulated d(loss)/d(mask slot)
+  float* red;    // [nwarps][NSLOT]
+  uint8_t* V;    // [TN] validity of the current pair at interior pixels
+};
+
+__host__ __device__ inline size_t fused_smem_floats(bool photo, int nwarps) {
+  size_t n = 3 * R2N + 2 * R1N + 2 * TN + (size_t)nwarps * NSLOT + TN / 4;
+  if (photo) n += 3 * R2N + 9 * R1N + 6 * TN;
+  return n;
+}
+
+template <int NV>
+MDN_DEV void flush_acc(float* v, float* red, int slot_base) {
+  warp_reduce_transpose<NV>(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < NV) red[warp * NSLOT + slot_base + lane] = v[0];
+}
+
+__global__ void __launch_bounds__(NTHREADS) fused_tile_kernel(const __grid_constant__ KParams P) {
+  MDN_DYN_SMEM(smem_raw);
+  const int tid = threadIdx.x, nthr = blockDim.x, nwarps = nthr >> 5;
+  const bool photo = (P.flags & MDN_TERM_PHOTO) != 0;
+  const bool use_ssim = photo && (P.flags & MDN_OPT_SSIM);
+  const bool epi_on = (P.flags & MDN_TERM_EPIPOLAR) != 0;
+  const bool smooth_on = (P.flags & MDN_TERM_SMOOTH) != 0;
+  const bool consis_on = (P.flags & MDN_TERM_CONSIS) != 0;
+  const bool grads = (P.flags & MDN_OPT_GRADS) != 0;
+  const bool own = P.mask_mode == MDN_MASK_OWN;
+  const bool need_tgt = photo || smooth_on;
+
+  Smem sm;
+  {
+    float* p = smem_raw;
+    sm.T = p; p += 3 * R2N;
+    sm.M = p; p += 2 * R1N;
+    sm.Mbar = p; p += 2 * TN;
+    sm.red = p; p += nwarps * NSLOT;
+    sm.V = reinterpret_cast<uint8_t*>(p); p += TN / 4;
+    sm.W = p; sm.ABC = p; sm.D = p;
+    if (photo) { sm.W = p; p += 3 * R2N; sm.ABC = p; p += 9 * R1N; sm.D = p; p += 6 * TN; }
+  }
+
+  // ---- which tile
+  int s = 0;
+#pragma unroll
+  for (int k = 1; k < MDN_MAX_SCALES; ++k)
+    if (k < P.n_scales && (int)blockIdx.x >= P.sc[k].tile_begin) s = k;
+  const KScale& S = P.sc[s];
+  int r = blockIdx.x - S.tile_begin;
+  const int tiles_per_img = S.tiles_x * S.tiles_y;
+  const int b = r / tiles_per_img;
+  r -= b * tiles_per_img;
+  const int ty = r / S.tiles_x, tx = r - ty * S.tiles_x;
+  const int x0 = tx * TW, y0 = ty * TH;
+  const int h = S.h, w = S.w, hw = h * w;
+
+  for (int i = tid; i < nwarps * NSLOT; i += nthr) sm.red[i] = 0.f;
+
+  // ---- P0: stage target image (halo 2) and the mask(s) (halo 1)
+  if (need_tgt) {
+    const float* tg = S.tgt + (long long)b * 3 * hw;
+    for (int i = tid; i < R2N; i += nthr) {
+      int ry = i / R2W, rx = i - ry * R2W;
+      int y = y0 - 2 + ry, x = x0 - 2 + rx;
+      bool in = (y >= 0) & (y < h) & (x >= 0) & (x < w);
+      long long o = (long long)y * w + x;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sm.T[c * R2N + i] = in ? __ldg(tg + (long long)c * hw + o) : 0.f;
+    }
+  }
+  const bool need_mask = epi_on || smooth_on || consis_on;
+  if (need_mask) {
+    const float* m0 = S.mob[0] + (long long)b * hw;
+    const float* m1 = (P.mask_mode == MDN_MASK_SHARED) ? m0 : S.mob[1] + (long long)b * hw;
+    for (int i = tid; i < R1N; i += nthr) {
+      int ry = i / R1W, rx = i - ry * R1W;
+      int y = y0 - 1 + ry, x = x0 - 1 + rx;
+      bool in = (y >= 0) & (y < h) & (x >= 0) & (x < w);
+      float a0 = 0.f, a1 = 0.f;
+      if (in) { a0 = __ldg(m0 + (long long)y * w + x); a1 = (P.mask_mode == MDN_MASK_SHARED) ? a0 : __ldg(m1 + (long long)y * w + x); }
+      if (own) { sm.M[i] = a0; sm.M[R1N + i] = a1; }
+      else { sm.M[i] = (a0 <= a1) ? a0 : a1; sm.M[R1N + i] = 0.f; }   // torch.min(dim): first index on ties
+    }
+  }
+  for (int i = tid; i < 2 * TN; i += nthr) sm.Mbar[i] = 0.f;
+  __syncthreads();
+
+  // ---- per (target, source) pair
+  for (int pair = 0; pair < P.n_pairs; ++pair) {
+    float acc[PAIR_SLOTS];
+#pragma unroll
+    for (int k = 0; k < PAIR_SLOTS; ++k) acc[k] = 0.f;
+    const float* flx = S.flow[pair] + (long long)b * 2 * hw;
+    const float* fly = flx + hw;
+    const float* Mp = sm.M + (own ? pair : 0) * R1N;
+    float* Mbar = sm.Mbar + (own ? pair : 0) * TN;
+
+    if (photo) {
+      // -- P1: warp the source image over the halo-2 region
+      const float* rf = S.ref[pair] + (long long)b * 3 * hw;
+      for (int i = tid; i < R2N; i += nthr) {
+        int ry = i / R2W, rx = i - ry * R2W;
+        int y = y0 - 2 + ry, x = x0 - 2 + rx;
+        bool in = (y >= 0) & (y < h) & (x >= 0) & (x < w);
+        float wv[3] = {0.f, 0.f, 0.f};
+        if (in) {
+          long long o = (long long)y * w + x;
+          float fx = __fmul_rn(S.sx, __ldg(flx + o)), fy = __fmul_rn(S.sy, __ldg(fly + o));
+          WarpCoord wc = warp_coord((float)x, (float)y, fx, fy, S.wm1, S.hm1);
+          Bilin bl = bilinear_setup(wc.ix, wc.iy, h, w);
+          int ly = ry - 2, lx = rx - 2;
+          bool interior = (ly >= 0) & (ly < TH) & (lx >= 0) & (lx < TW);
+          int li = ly * TW + lx;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float nw, ne, sw, se;
+            bilinear_fetch(rf + (long long)c * hw, w, bl, nw, ne, sw, se);
+            wv[c] = bilinear_value(bl, nw, ne, sw, se);
+            if (interior) {
+              if (grads) { float ddx, ddy; bilinear_deriv(bl, nw, ne, sw, se, ddx, ddy); sm.D[c * TN + li] = ddx; sm.D[(3 + c) * TN + li] = ddy; }
+              float df = fabsf(sm.T[c * R2N + i] - wv[c]);
+              df = wc.valid ? df : 0.f;
+              acc[SL_L1] += df;
+              if (S.warped[pair]) S.warped[pair][((long long)b * 3 + c) * hw + o] = wv[c];
+              if (S.diff[pair]) S.diff[pair][((long long)b * 3 + c) * hw + o] = df;
+            }
+          }
+          if (interior) {
+            sm.V[li] = wc.valid ? 1 : 0;
+            if (S.valid[pair]) S.valid[pair][(long long)b * hw + o] = wc.valid ? 1 : 0;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sm.W[c * R2N + i] = wv[c];
+      }
+      __syncthreads();
+
+      // -- P2: SSIM per window over the halo-1 region
+      if (use_ssim) {
+        for (int i = tid; i < R1N; i += nthr) {
+          int ry = i / R1W, rx = i - ry * R1W;
+          int py = y0 - 1 + ry, px = x0 - 1 + rx;
+          bool in = (py >= 0) & (py < h) & (px >= 0) & (px < w);
+          bool interior = (ry >= 1) & (ry <= TH) & (rx >= 1) & (rx <= TW);
+          if (in) {
+            int ro[3], co[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              ro[d] = (reflect1(py + d - 1, h) - (y0 - 2)) * R2W;
+              co[d] = reflect1(px + d - 1, w) - (x0 - 2);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                  float xv = sm.T[c * R2N + ro[dy] + co[dx]], yv = sm.W[c * R2N + ro[dy] + co[dx]];
+                  sx += xv; sy += yv; sxx += xv * xv; syy += yv * yv; sxy += xv * yv;
+                }
+              SsimOut so = ssim_window(sx, sy, sxx, syy, sxy, grads);
+              if (interior) {
+                acc[SL_SSIM] += so.J;
+                if (S.ssim_map[pair]) S.ssim_map[pair][((long long)b * 3 + c) * hw + (long long)py * w + px] = so.J;
+              }
+              const float k9 = S.c_ssim * (1.f / 9.f);
+              sm.ABC[(3 * c + 0) * R1N + i] = k9 * so.dmu_y;
+              sm.ABC[(3 * c + 1) * R1N + i] = k9 * 2.f * so.dY2;
+              sm.ABC[(3 * c + 2) * R1N + i] = k9 * so.dXY;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) sm.ABC[k * R1N + i] = 0.f;
+          }
+        }
+        __syncthreads();
+      }
+    }
+
+    // -- P3: interior pixels: photometric adjoint -> d/dflow, epipolar forward + adjoint
+    {
+      float Fm[9];
+      if (epi_on) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Fm[k] = __ldg(S.fmat[pair] + b * 9 + k);
+      }
+      float snmax = 1.f;
+      if (epi_on && P.post == MDN_POST_SN) {
+        unsigned long long key = P.snkey[(s * P.n_pairs + pair) * P.batch + b];
+        snmax = __uint_as_float((unsigned)(key >> 32));
+      }
+      for (int li = tid; li < TN; li += nthr) {
+        int ly = li / TW, lx = li - ly * TW;
+        int y = y0 + ly, x = x0 + lx;
+        if (y >= h || x >= w) continue;
+        long long o = (long long)y * w + x;
+        int i1 = (ly + 1) * R1W + lx + 1, i2 = (ly + 2) * R2W + lx + 2;
+        float gfx = 0.f, gfy = 0.f;
+        if (photo && grads) {
+          float gix = 0.f, giy = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float wb = 0.f;
+            float tv = sm.T[c * R2N + i2], wv = sm.W[c * R2N + i2];
+            if (use_ssim) {
+              float sa = 0.f, sb = 0.f, sc = 0.f;
+#pragma unroll
+              for (int dy = -1; dy <= 1; ++dy) {
+                int py = y + dy;
+                if (py < 0 || py >= h) continue;
+                int my = refl_mult(py, y, h);
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                  int px = x + dx;
+                  if (px < 0 || px >= w) continue;
+                  float mlt = (float)(my * refl_mult(px, x, w));
+                  int j = i1 + dy * R1W + dx;
+                  sa += mlt * sm.ABC[(3 * c + 0) * R1N + j];
+                  sb += mlt * sm.ABC[(3 * c + 1) * R1N + j];
+                  sc += mlt * sm.ABC[(3 * c + 2) * R1N + j];
+                }
+              }
+              wb = sa + wv * sb + tv * sc;
+            }
+            if (sm.V[li]) wb -= S.c_l1 * signf_(tv - wv);
+            gix += wb * sm.D[c * TN + li];
+            giy += wb * sm.D[(3 + c) * TN + li];
+          }
+          gfx = gix * S.sx; gfy = giy * S.sy;   // (w-1)/2 * 2 / (w-1) * sx  (grid_sample, 2g-1, /(w-1), scale factor)
+        }
+        if (epi_on) {
+          float m = Mp[i1];
+          float phx = __ldg(flx + o), phy = __ldg(fly + o);
+          float u = __fadd_rn((float)x, __fmul_rn(S.sx, phx));
+          float v = __fadd_rn((float)y, __fmul_rn(S.sy, phy));
+          Epi e = epipolar_distance(Fm, (float)x, (float)y, u, v);
+          float ae = fabsf(e.d);
+          float dpost;
+          float post = post_process(P, S, ae, snmax, (int)o, dpost);
+          float kmask = 1.f;
+          if ((P.flags & (MDN_OPT_INST_MASK | MDN_OPT_CROSS_ENT)) != 0) kmask = (float)__ldg(S.inst + (long long)b * hw + o);
+          if (P.flags & MDN_OPT_INST_MASK) { post *= kmask; dpost *= kmask; }
+          float bg = 1.f - m;
+          float lg = logf(bg + 1e-5f);
+          float ml = m * lg;
+          acc[SL_EPI] += bg * post;
+          acc[SL_NT] += fabsf(ml);
+          float mb = 0.f;
+          if (P.flags & MDN_OPT_CROSS_ENT) {
+            float l1 = logf(m + 1e-10f), l0 = logf(bg + 1e-10f);
+            acc[SL_CE] += -(kmask * l1 + (1.f - kmask) * l0);
+            mb += S.c_ce * (-kmask / (m + 1e-10f) + (1.f - kmask) / (bg + 1e-10f));
+          }
+          if (S.post_map[pair]) S.post_map[pair][(long long)b * hw + o] = post;
+          if (S.ori_map[pair]) S.ori_map[pair][(long long)b * hw + o] = (P.post == MDN_POST_SN) ? __fdiv_rn(ae, snmax) : ae;
+          if (grads) {
+            mb += -S.c_epi * post + S.c_nt * signf_(ml) * (lg - m / (bg + 1e-5f));
+            Mbar[li] += mb;
+            float ebar = S.c_epi * bg * dpost;
+            float dbar = signf_(e.d) * ebar;
+            float inv_den = 1.f / e.den;
+            float g2 = dbar * inv_den;
+            float das = e.d / e.s;
+            gfx += g2 * e.a * S.sx;
+            gfy += g2 * e.b * S.sy;
+            float g0 = g2 * (u - das * e.a), g1 = g2 * (v - das * e.b);
+            float xf = (float)x, yf = (float)y;
+            acc[SL_GF + 0] += g0 * xf; acc[SL_GF + 1] += g0 * yf; acc[SL_GF + 2] += g0;
+            acc[SL_GF + 3] += g1 * xf; acc[SL_GF + 4] += g1 * yf; acc[SL_GF + 5] += g1;
+            acc[SL_GF + 6] += g2 * xf; acc[SL_GF + 7] += g2 * yf; acc[SL_GF + 8] += g2;
+          }
+        }
+        if (grads && S.g_flow[pair]) {
+          S.g_flow[pair][(long long)b * 2 * hw + o] = gfx;
+          S.g_flow[pair][(long long)b * 2 * hw + hw + o] = gfy;
+        }
+      }
+    }
+    flush_acc<PAIR_SLOTS>(acc, sm.red, pair * PAIR_SLOTS);
+    __syncthreads();   // W / ABC / D / V are reused by the next pair
+  }
+
+  // ---- P4: smoothness + consistency, then route d/dmask to the mobile maps
+  if (need_mask) {
+    float acc[TAIL_SLOTS];
+#pragma unroll
+    for (int k = 0; k < TAIL_SLOTS; ++k) acc[k] = 0.f;
+    const int n_masks = own ? P.n_pairs : 1;
+    // in MIN / SHARED mode the reference evaluates smooth_loss once per source frame with the SAME mask
+    const float rep = own ? 1.f : (float)P.n_pairs;
+    const float* m0g = S.mob[0] + (long long)b * hw;
+    const float* m1g = (P.mask_mode == MDN_MASK_SHARED) ? m0g : S.mob[1] + (long long)b * hw;
+    for (int li = tid; li < TN; li += nthr) {
+      int ly = li / TW, lx = li - ly * TW;
+      int y = y0 + ly, x = x0 + lx;
+      if (y >= h || x >= w) continue;
+      long long o = (long long)y * w + x;
+      int i1 = (ly + 1) * R1W + lx + 1, i2 = (ly + 2) * R2W + lx + 2;
+      float mbar[2] = {sm.Mbar[li], sm.Mbar[TN + li]};
+      if (smooth_on) {
+        // exp(-mean_c |I(x) - I(x+1)|) for the pairs (x-1,x), (x,x+1), (y-1,y), (y,y+1)
+        float ex_r = 0.f, ex_l = 0.f, ey_d = 0.f, ey_u = 0.f;
+        {
+          float gr = 0.f, gl = 0.f, gd = 0.f, gu = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float t0 = sm.T[c * R2N + i2];
+            gr += fabsf(t0 - sm.T[c * R2N + i2 + 1]);
+            gl += fabsf(sm.T[c * R2N + i2 - 1] - t0);
+            gd += fabsf(t0 - sm.T[c * R2N + i2 + R2W]);
+            gu += fabsf(sm.T[c * R2N + i2 - R2W] - t0);
+          }
+          const float third = 1.f / 3.f;
+          if (x + 1 < w) ex_r = expf(-gr * third);
+          if (x > 0) ex_l = expf(-gl * third);
+          if (y + 1 < h) ey_d = expf(-gd * third);
+          if (y > 0) ey_u = expf(-gu * third);
+        }
+        for (int k = 0; k < n_masks; ++k) {
+          const float* Mk = sm.M + k * R1N;
+          float mc = Mk[i1];
+          float dr = mc - Mk[i1 + 1], dl = Mk[i1 - 1] - mc, dd = mc - Mk[i1 + R1W], du = Mk[i1 - R1W] - mc;
+          acc[SL_SMX + 2 * k] += fabsf(dr) * ex_r;   // ex_r == 0 at the last column
+          acc[SL_SMY + 2 * k] += fabsf(dd) * ey_d;
+          mbar[k] += rep * (S.c_smx * (signf_(dr) * ex_r - signf_(dl) * ex_l) + S.c_smy * (signf_(dd) * ey_d - signf_(du) * ey_u));
+        }
+      }
+      float a0 = __ldg(m0g + o), a1 = __ldg(m1g + o);
+      float g0, g1;
+      if (own) { g0 = mbar[0]; g1 = mbar[1]; }
+      else if (P.mask_mode == MDN_MASK_SHARED) { g0 = mbar[0]; g1 = 0.f; }
+      else { bool first = a0 <= a1; g0 = first ? mbar[0] : 0.f; g1 = first ? 0.f : mbar[0]; }
+      if (consis_on) {
+        float p = sigmoidf_(20.f * (a0 - 0.5f)), q = sigmoidf_(20.f * (a1 - 0.5f));
+        float df = p - q;
+        acc[SL_CONSIS] += df * df;
+        g0 += S.c_consis * 2.f * df * 20.f * p * (1.f - p);
+        g1 -= S.c_consis * 2.f * df * 20.f * q * (1.f - q);
+      }
+      if (grads) {
+        if (S.g_mob[0]) S.g_mob[0][(long long)b * hw + o] = g0;
+        if (S.g_mob[1] && P.mask_mode != MDN_MASK_SHARED) S.g_mob[1][(long long)b * hw + o] = g1;
+      }
+    }
+    flush_acc<TAIL_SLOTS>(acc, sm.red, TAIL_BASE);
+  }
+  __syncthreads();
+  for (int k = tid; k < NSLOT; k += nthr) {
+    float t = 0.f;
+    for (int wq = 0; wq < nwarps; ++wq) t += sm.red[wq * NSLOT + k];
+    P.partials[(long long)blockIdx.x * NSLOT + k] = t;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- finish
+struct FParams {
+  KParams K;
+  float* sample_sums;      // [n_scales][batch][NSLOT]
+  unsigned* ticket;
+  float* loss_out;         // MDN_OUT_COUNT
+  float* g_fmat[MDN_MAX_SCALES][2];
+  float alpha, w_d2, w_e, w_s, w_c, w_p, l1_coef, ssim_coef;
+  float scale_div[MDN_MAX_SCALES];
+};
+
+constexpr int FIN_ROWS = 6;   // FIN_ROWS * NSLOT = 240 threads
+
+__global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_constant__ FParams Q) {
+  const KParams& P = Q.K;
+  __shared__ float part[FIN_ROWS][NSLOT];
+  __shared__ bool is_last;
+  const int s = blockIdx.x / P.batch, b = blockIdx.x % P.batch;
+  const KScale& S = P.sc[s];
+  const int slot = threadIdx.x % NSLOT, row = threadIdx.x / NSLOT;
+  const int tiles = S.tiles_x * S.tiles_y;
+  const float* src = P.partials + ((long long)S.tile_begin + (long long)b * tiles) * NSLOT;
+  float t = 0.f;
+  for (int k = row; k < tiles; k += FIN_ROWS) t += src[(long long)k * NSLOT + slot];
+  part[row][slot] = t;
+  __syncthreads();
+  if (row == 0) {
+    float tot = 0.f;
+    for (int k = 0; k < FIN_ROWS; ++k) tot += part[k][slot];
+    part[0][slot] = tot;
+    Q.sample_sums[((long long)s * P.batch + b) * NSLOT + slot] = tot;
+  }
+  __syncthreads();
+  const bool grads = (P.flags & MDN_OPT_GRADS) != 0;
+  if (grads && (P.flags & MDN_TERM_EPIPOLAR) && threadIdx.x < (unsigned)P.n_pairs) {
+    const int pair = threadIdx.x;
+    float gF[9];
+    for (int k = 0; k < 9; ++k) gF[k] = part[0][pair * PAIR_SLOTS + SL_GF + k];
+    if (P.post == MDN_POST_SN) {
+      // d/d(max): -(2/M) * c_epi * sum(bg*post), routed to the first arg-max pixel (loss_utils.py:96-98 backward)
+      unsigned long long key = P.snkey[(s * P.n_pairs + pair) * P.batch + b];
+      float M = __uint_as_float((unsigned)(key >> 32));
+      int idx = (int)(0xffffffffu - (unsigned)(key & 0xffffffffu));
+      if (key != 0ull && M > 0.f) {
+        const int hw = S.h * S.w;
+        int y = idx / S.w, x = idx - y * S.w;
+        const float* flx = S.flow[pair] + (long long)b * 2 * hw;
+        float Fm[9];
+        for (int k = 0; k < 9; ++k) Fm[k] = S.fmat[pair][b * 9 + k];
+        float u = __fadd_rn((float)x, __fmul_rn(S.sx, flx[idx]));
+        float v = __fadd_rn((float)y, __fmul_rn(S.sy, flx[hw + idx]));
+        Epi e = epipolar_distance(Fm, (float)x, (float)y, u, v);
+        float ebar = -2.f * S.c_epi * part[0][pair * PAIR_SLOTS + SL_EPI] / M;
+        float dbar = signf_(e.d) * ebar;
+        float g2 = dbar / e.den, das = e.d / e.s;
+        float g0 = g2 * (u - das * e.a), g1 = g2 * (v - das * e.b);
+        if (S.g_flow[pair]) {
+          S.g_flow[pair][(long long)b * 2 * hw + idx] += g2 * e.a * S.sx;
+          S.g_flow[pair][(long long)b * 2 * hw + hw + idx] += g2 * e.b * S.sy;
+        }
+        float xf = (float)x, yf = (float)y;
+        gF[0] += g0 * xf; gF[1] += g0 * yf; gF[2] += g0;
+        gF[3] += g1 * xf; gF[4] += g1 * yf; gF[5] += g1;
+        gF[6] += g2 * xf; gF[7] += g2 * yf; gF[8] += g2;
+      }
+    }
+    if (Q.g_fmat[s][pair])
+      for (int k = 0; k < 9; ++k) Q.g_fmat[s][pair][b * 9 + k] = gF[k];
+  }
+  // last block to arrive folds the per-sample sums into the loss scalars, in a fixed order
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned prev = atomicInc(Q.ticket, gridDim.x - 1);   // wraps to 0 after the last block: reusable across launches
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    double epip = 0, smooth = 0, consis = 0, photo = 0;
+    const bool own = P.mask_mode == MDN_MASK_OWN;
+    for (int ss = 0; ss < P.n_scales; ++ss) {
+      const KScale& Z = P.sc[ss];
+      double tot[NSLOT];
+      for (int k = 0; k < NSLOT; ++k) tot[k] = 0;
+      for (int bb = 0; bb < P.batch; ++bb)
+        for (int k = 0; k < NSLOT; ++k) tot[k] += (double)Q.sample_sums[((long long)ss * P.batch + bb) * NSLOT + k];
+      const double N = (double)P.batch * Z.h * Z.w, div = Q.scale_div[ss];
+      const double cx = (double)P.batch * Z.h * (Z.w - 1), cy = (double)P.batch * (Z.h - 1) * Z.w;
+      for (int p = 0; p < P.n_pairs; ++p) {
+        const double* tp = tot + p * PAIR_SLOTS;
+        if (P.flags & MDN_TERM_EPIPOLAR) {
+          double e = tp[SL_EPI] / N + (double)Q.alpha * (tp[SL_NT] / N);
+          if (P.flags & MDN_OPT_CROSS_ENT) e += (double)Q.w_d2 * (tp[SL_CE] / N);
+          epip += e / div;
+        }
+        if (P.flags & MDN_TERM_PHOTO)
+          photo += ((double)Q.l1_coef * (tp[SL_L1] / (3 * N)) + (double)Q.ssim_coef * (tp[SL_SSIM] / (3 * N))) / div;
+        if (P.flags & MDN_TERM_SMOOTH) {
+          const int k = own ? p : 0;
+          smooth += (tot[TAIL_BASE + SL_SMX + 2 * k] / cx + tot[TAIL_BASE + SL_SMY + 2 * k] / cy) / div;
+        }
+      }
+      if (P.flags & MDN_TERM_CONSIS) consis += tot[TAIL_BASE + SL_CONSIS] / N / div;
+    }
+    Q.loss_out[MDN_OUT_EPIP] = (float)epip;
+    Q.loss_out[MDN_OUT_SMOOTH] = (float)smooth;
+    Q.loss_out[MDN_OUT_CONSIS] = (float)consis;
+    Q.loss_out[MDN_OUT_PHOTO] = (float)photo;
+    Q.loss_out[MDN_OUT_APPLIED] = 1.f;
+    Q.loss_out[MDN_OUT_APPLIED + 1] = 0.f;
+    Q.loss_out[MDN_OUT_APPLIED + 2] = 0.f;
+    Q.loss_out[MDN_OUT_LOSS] = (float)((double)Q.w_e * epip + (double)Q.w_s * smooth + (double)Q.w_c * consis + (double)Q.w_p * photo);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- scale grads
+struct GradList {
+  int n;
+  float* ptr[MDN_MAX_SCALES * 6];
+  long long count[MDN_MAX_SCALES * 6];
+};
+
+__global__ void __launch_bounds__(NTHREADS) scale_grads_kernel(const __grid_constant__ GradList L, const float* g, float* applied) {
+  const float gv = __ldg(g), ap = *applied;
+  if (gv == ap) return;                      // loss.backward() with the implicit upstream gradient of 1
+  const float ratio = gv / ap;
+  for (int k = 0; k < L.n; ++k) {
+    float* p = L.ptr[k];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < L.count[k]; i += (long long)gridDim.x * blockDim.x)
+      p[i] *= ratio;
+  }
+}
+__global__ void set_applied_kernel(const float* g, float* applied) { *applied = *g; }
+
+// ----------------------------------------------------------------------------------------------- standalone kernels
+__global__ void __launch_bounds__(NTHREADS) epipolar_points_fwd_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                                                                       const float* __restrict__ fmat, float* __restrict__ out, long long n) {
+  const int b = blockIdx.y;
+  const float* F = fmat + b * 9;
+  const float* a = p1 + (long long)b * 3 * n;
+  const float* c = p2 + (long long)b * 3 * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float x = a[i], y = a[n + i], z = a[2 * n + i];
+    float fa = __fmaf_rn(F[2], z, __fmaf_rn(F[1], y, __fmul_rn(F[0], x)));
+    float fb = __fmaf_rn(F[5], z, __fmaf_rn(F[4], y, __fmul_rn(F[3], x)));
+    float fc = __fmaf_rn(F[8], z, __fmaf_rn(F[7], y, __fmul_rn(F[6], x)));
+    float num = __fadd_rn(__fadd_rn(__fmul_rn(fa, c[i]), __fmul_rn(fb, c[n + i])), __fmul_rn(fc, c[2 * n + i]));
+    float s = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(fa, fa), __fmul_rn(fb, fb)), 1e-10f));
+    out[(long long)b * n + i] = __fdiv_rn(num, __fadd_rn(s, 1e-10f));
+  }
+}
+
+constexpr int EPB_SLOTS = 16;
+__global__ void __launch_bounds__(NTHREADS) epipolar_points_bwd_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                                                                       const float* __restrict__ fmat, const float* __restrict__ g_out,
+                                                                       float* __restrict__ g_p1, float* __restrict__ g_p2,
+                                                                       float* __restrict__ partials, long long n) {
+  __shared__ float red[NTHREADS / 32][EPB_SLOTS];
+  const int b = blockIdx.y;
+  const float* F = fmat + b * 9;
+  const float* a = p1 + (long long)b * 3 * n;
+  const float* c = p2 + (long long)b * 3 * n;
+  float acc[EPB_SLOTS];
+#pragma unroll
+  for (int k = 0; k < EPB_SLOTS; ++k) acc[k] = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float x = a[i], y = a[n + i], z = a[2 * n + i];
+    float u = c[i], v = c[n + i], t = c[2 * n + i];
+    float fa = __fmaf_rn(F[2], z, __fmaf_rn(F[1], y, __fmul_rn(F[0], x)));
+    float fb = __fmaf_rn(F[5], z, __fmaf_rn(F[4], y, __fmul_rn(F[3], x)));
+    float fc = __fmaf_rn(F[8], z, __fmaf_rn(F[7], y, __fmul_rn(F[6], x)));
+    float num = fa * u + fb * v + fc * t;
+    float s = sqrtf(fa * fa + fb * fb + 1e-10f);
+    float den = s + 1e-10f;
+    float d = num / den;
+    float g = g_out[(long long)b * n + i];
+    float g2 = g / den, das = d / s;
+    float ga = g2 * (u - das * fa), gb = g2 * (v - das * fb), gc = g2 * t;   // d/d(Fp1)
+    if (g_p2) {
+      g_p2[(long long)b * 3 * n + i] = g2 * fa; g_p2[(long long)b * 3 * n + n + i] = g2 * fb; g_p2[(long long)b * 3 * n + 2 * n + i] = g2 * fc;
+    }
+    if (g_p1) {
+      g_p1[(long long)b * 3 * n + i] = F[0] * ga + F[3] * gb + F[6] * gc;
+      g_p1[(long long)b * 3 * n + n + i] = F[1] * ga + F[4] * gb + F[7] * gc;
+      g_p1[(long long)b * 3 * n + 2 * n + i] = F[2] * ga + F[5] * gb + F[8] * gc;
+    }
+    acc[0] += ga * x; acc[1] += ga * y; acc[2] += ga * z;
+    acc[3] += gb * x; acc[4] += gb * y; acc[5] += gb * z;
+    acc[6] += gc * x; acc[7] += gc * y; acc[8] += gc * z;
+  }
+  warp_reduce_transpose<EPB_SLOTS>(acc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < EPB_SLOTS) red[warp][lane] = acc[0];
+  __syncthreads();
+  if (threadIdx.x < EPB_SLOTS) {
+    float t = 0.f;
+    for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) t += red[wq][threadIdx.x];
+    partials[((long long)b * gridDim.x + blockIdx.x) * EPB_SLOTS + threadIdx.x] = t;
+  }
+}
+
+__global__ void epipolar_points_bwd_finish_kernel(const float* __restrict__ partials, float* __restrict__ g_fmat, int nblk) {
+  const int b = blockIdx.x, k = threadIdx.x;
+  if (k >= 9) return;
+  float t = 0.f;
+  for (int j = 0; j < nblk; ++j) t += partials[((long long)b * nblk + j) * EPB_SLOTS + k];
+  g_fmat[b * 9 + k] = t;
+}
+
+__global__ void __launch_bounds__(NTHREADS) flow_warp_fwd_kernel(const float* __restrict__ ref, const float* __restrict__ flow,
+                                                                 float* __restrict__ warped, float* __restrict__ grid_out,
+                                                                 uint8_t* __restrict__ valid, int C, int h, int w, int fw_norm) {
+  const int b = blockIdx.y;
+  const int hw = h * w;
+  const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    int y = i / w, x = i - y * w;
+    float fx = flow[(long long)b * 2 * hw + i], fy = flow[(long long)b * 2 * hw + hw + i];
+    WarpCoord wc = warp_coord((float)x, (float)y, fx, fy, wm1, hm1, fw_norm != 0);
+    if (grid_out) { grid_out[((long long)b * hw + i) * 2] = wc.gx; grid_out[((long long)b * hw + i) * 2 + 1] = wc.gy; }
+    if (valid) valid[(long long)b * hw + i] = wc.valid ? 1 : 0;
+    if (warped) {
+      Bilin bl = bilinear_setup(wc.ix, wc.iy, h, w);
+      for (int c = 0; c < C; ++c) {
+        float nw, ne, sw, se;
+        bilinear_fetch(ref + ((long long)b * C + c) * hw, w, bl, nw, ne, sw, se);
+        warped[((long long)b * C + c) * hw + i] = bilinear_value(bl, nw, ne, sw, se);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS) flow_warp_bwd_kernel(const float* __restrict__ ref, const float* __restrict__ flow,
+                                                                 const float* __restrict__ g_warped, float* __restrict__ g_flow,
+                                                                 int C, int h, int w) {
+  const int b = blockIdx.y;
+  const int hw = h * w;
+  const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    int y = i / w, x = i - y * w;
+    float fx = flow[(long long)b * 2 * hw + i], fy = flow[(long long)b * 2 * hw + hw + i];
+    WarpCoord wc = warp_coord((float)x, (float)y, fx, fy, wm1, hm1);
+    Bilin bl = bilinear_setup(wc.ix, wc.iy, h, w);
+    float gix = 0.f, giy = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float nw, ne, sw, se, ddx, ddy;
+      bilinear_fetch(ref + ((long long)b * C + c) * hw, w, bl, nw, ne, sw, se);
+      bilinear_deriv(bl, nw, ne, sw, se, ddx, ddy);
+      float g = g_warped[((long long)b * C + c) * hw + i];
+      gix += g * ddx; giy += g * ddy;
+    }
+    // grid_sample: * (size-1)/2 ; "2*g-1": * 2 ; "/= (size-1)": / (size-1)
+    g_flow[(long long)b * 2 * hw + i] = __fdiv_rn(__fmul_rn(__fmul_rn(gix, __fmul_rn(wm1, 0.5f)), 2.f), wm1);
+    g_flow[(long long)b * 2 * hw + hw + i] = __fdiv_rn(__fmul_rn(__fmul_rn(giy, __fmul_rn(hm1, 0.5f)), 2.f), hm1);
+  }
+}
+
+MDN_DEV void ssim_sums(const float* __restrict__ xp, const float* __restrict__ yp, int py, int px, int h, int w, float& sx,
+                       float& sy, float& sxx, float& syy, float& sxy) {
+  sx = sy = sxx = syy = sxy = 0.f;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    int ry = reflect1(py + dy, h);
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      int rx = reflect1(px + dx, w);
+      float xv = __ldg(xp + (long long)ry * w + rx), yv = __ldg(yp + (long long)ry * w + rx);
+      sx += xv; sy += yv; sxx += xv * xv; syy += yv * yv; sxy += xv * yv;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS) ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+                                                            int h, int w) {
+  const long long plane = (long long)blockIdx.y * h * w;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h * w; i += gridDim.x * blockDim.x) {
+    int py = i / w, px = i - py * w;
+    float sx, sy, sxx, syy, sxy;
+    ssim_sums(x + plane, y + plane, py, px, h, w, sx, sy, sxx, syy, sxy);
+    out[plane + i] = ssim_window(sx, sy, sxx, syy, sxy, false).J;
+  }
+}
+
+// gather-form adjoint of (reflect pad -> 3x3 mean pools -> SSIM): every pixel q visits the <= 9 windows that touch it
+__global__ void __launch_bounds__(NTHREADS) ssim_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            const float* __restrict__ g_out, float* __restrict__ g_x, float* __restrict__ g_y,
+                                                            int h, int w) {
+  const long long plane = (long long)blockIdx.y * h * w;
+  const float* xp = x + plane; const float* yp = y + plane;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h * w; i += gridDim.x * blockDim.x) {
+    int qy = i / w, qx = i - qy * w;
+    float xq = xp[i], yq = yp[i];
+    float gx = 0.f, gy = 0.f;
+    for (int dy = -1; dy <= 1; ++dy) {
+      int py = qy + dy;
+      if (py < 0 || py >= h) continue;
+      int my = refl_mult(py, qy, h);
+      for (int dx = -1; dx <= 1; ++dx) {
+        int px = qx + dx;
+        if (px < 0 || px >= w) continue;
+        float mlt = (float)(my * refl_mult(px, qx, w));
+        if (mlt == 0.f) continue;
+        float sx, sy, sxx, syy, sxy;
+        ssim_sums(xp, yp, py, px, h, w, sx, sy, sxx, syy, sxy);
+        SsimOut so = ssim_window(sx, sy, sxx, syy, sxy, true);
+        float g = mlt * g_out[plane + (long long)py * w + px] * (1.f / 9.f);
+        gy += g * (so.dmu_y + 2.f * yq * so.dY2 + xq * so.dXY);
+        gx += g * (so.dmu_x + 2.f * xq * so.dX2 + yq * so.dXY);
+      }
+    }
+    if (g_x) g_x[plane + i] = gx;
+    if (g_y) g_y[plane + i] = gy;
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS) binary_image_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, float thr) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (x[i] >= thr) ? 1.f : 0.f;
+}
+
+}  // namespace mdn
+
+// =================================================================================================== C ABI
+using namespace mdn;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, const char* what = "") {
+  snprintf(g_err, sizeof(g_err), fmt, what);
+  return code;
+}
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" int mdn_version(void) { return MDN_ABI_VERSION; }
+extern "C" const char* mdn_last_error_string(void) { return g_err; }
+
+struct WsLayout { size_t partials, sample_sums, snkeys, ticket, total; int n_tiles; };
+
+static int plan_tiles(const MdnLossDesc* d, KParams& K) {
+  int t = 0;
+  for (int s = 0; s < d->n_scales; ++s) {
+    KScale& Z = K.sc[s];
+    Z.h = d->scale[s].height; Z.w = d->scale[s].width;
+    Z.tiles_x = (Z.w + TW - 1) / TW; Z.tiles_y = (Z.h + TH - 1) / TH;
+    Z.tile_begin = t;
+    t += Z.tiles_x * Z.tiles_y * d->batch;
+  }
+  K.n_tiles = t;
+  return t;
+}
+
+static int check_desc(const MdnLossDesc* d) {
+  if (!d) return fail(MDN_ERR_NULL_POINTER, "desc is NULL");
+  if (d->batch < 1 || d->n_scales < 1 || d->n_scales > MDN_MAX_SCALES || d->n_pairs < 1 || d->n_pairs > MDN_MAX_PAIRS)
+    return fail(MDN_ERR_BAD_SHAPE, "batch / n_scales / n_pairs out of range");
+  if (d->post < MDN_POST_SN || d->post > MDN_POST_TG) return fail(MDN_ERR_UNSUPPORTED, "unknown post-processing mode");
+  if (d->mask_mode < MDN_MASK_MIN || d->mask_mode > MDN_MASK_SHARED) return fail(MDN_ERR_UNSUPPORTED, "unknown mask mode");
+  if ((d->flags & MDN_TERM_CONSIS) && d->mask_mode == MDN_MASK_SHARED)
+    return fail(MDN_ERR_UNSUPPORTED, "consistency term needs two mobile maps (not MDN_MASK_SHARED)");
+  const int f = d->flags;
+  for (int s = 0; s < d->n_scales; ++s) {
+    const MdnScale& S = d->scale[s];
+    if (S.height < 2 || S.width < 2 || (long long)S.height * S.width > (1ll << 30)) return fail(MDN_ERR_BAD_SHAPE, "height/width must be >= 2");
+#define NEED(p, what) do { if (!(p)) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", what); if (!aligned16(p)) return fail(MDN_ERR_MISALIGNED, "%s is not 16-byte aligned", what); } while (0)
+#define OPT(p, what) do { if ((p) && !aligned16(p)) return fail(MDN_ERR_MISALIGNED, "%s is not 16-byte aligned", what); } while (0)
+    if (f & (MDN_TERM_PHOTO | MDN_TERM_SMOOTH)) NEED(S.tgt, "tgt");
+    if (f & (MDN_TERM_EPIPOLAR | MDN_TERM_SMOOTH | MDN_TERM_CONSIS)) {
+      NEED(S.mob[0], "mob[0]");
+      if (d->mask_mode != MDN_MASK_SHARED) NEED(S.mob[1], "mob[1]");   // MIN / OWN / consistency read both maps
+    }
+    for (int p = 0; p < d->n_pairs; ++p) {
+      if (f & MDN_TERM_PHOTO) NEED(S.ref[p], "ref");
+      if (f & (MDN_TERM_PHOTO | MDN_TERM_EPIPOLAR)) NEED(S.flow[p], "flow");
+      if (f & MDN_TERM_EPIPOLAR) { if (!S.fmat[p]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "fmat"); }
+      OPT(S.g_flow[p], "g_flow"); OPT(S.g_mob[p], "g_mob"); OPT(S.post_map[p], "post_map"); OPT(S.ori_map[p], "ori_map");
+      OPT(S.warped[p], "warped"); OPT(S.diff[p], "diff"); OPT(S.ssim_map[p], "ssim_map");
+    }
+    if ((f & MDN_TERM_EPIPOLAR) && d->post == MDN_POST_TG) NEED(S.weight, "weight");
+    if ((f & MDN_TERM_EPIPOLAR) && (f & (MDN_OPT_INST_MASK | MDN_OPT_CROSS_ENT)) && !S.inst) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "inst");
+#undef NEED
+#undef OPT
+  }
+  return MDN_OK;
+}
+
+static WsLayout ws_layout(const MdnLossDesc* d, int n_tiles) {
+  WsLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+  L.partials = take((size_t)n_tiles * NSLOT * sizeof(float));
+  L.sample_sums = take((size_t)d->n_scales * d->batch * NSLOT * sizeof(float));
+  L.snkeys = take((size_t)d->n_scales * d->n_pairs * d->batch * sizeof(unsigned long long));
+  L.ticket = take(256);
+  L.total = off;
+  L.n_tiles = n_tiles;
+  return L;
+}
+
+extern "C" size_t mdn_loss_workspace_bytes(const MdnLossDesc* d) {
+  if (check_desc(d) != MDN_OK) return 0;
+  KParams K;
+  memset(&K, 0, sizeof(K));
+  return ws_layout(d, plan_tiles(d, K)).total;
+}
+
+extern "C" int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, void* workspace, size_t workspace_bytes, void* stream_) {
+  int rc = check_desc(d);
+  if (rc != MDN_OK) return rc;
+  if (!loss_out) return fail(MDN_ERR_NULL_POINTER, "loss_out is NULL");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FParams Q;
+  memset(&Q, 0, sizeof(Q));
+  KParams& K = Q.K;
+  WsLayout L = ws_layout(d, plan_tiles(d, K));
+  if (!workspace || workspace_bytes < L.total) return fail(MDN_ERR_WORKSPACE, "workspace too small");
+  if (!aligned16(workspace)) return fail(MDN_ERR_MISALIGNED, "%s is not 16-byte aligned", "workspace");
+  char* ws = (char*)workspace;
+  K.batch = d->batch; K.n_scales = d->n_scales; K.n_pairs = d->n_pairs; K.post = d->post; K.mask_mode = d->mask_mode;
+  K.flags = d->flags; K.threshold = d->threshold;
+  K.partials = (float*)(ws + L.partials);
+  unsigned long long* keys = (unsigned long long*)(ws + L.snkeys);
+  K.snkey = keys;
+  Q.sample_sums = (float*)(ws + L.sample_sums);
+  Q.ticket = (unsigned*)(ws + L.ticket);
+  Q.loss_out = loss_out;
+  const bool use_ssim = (d->flags & MDN_OPT_SSIM) != 0;
+  Q.alpha = d->alpha; Q.w_d2 = d->w_d2_sim; Q.w_e = d->w_e; Q.w_s = d->w_s; Q.w_c = d->w_c; Q.w_p = d->w_p;
+  Q.l1_coef = use_ssim ? 0.15f : 1.f; Q.ssim_coef = use_ssim ? 0.85f : 0.f;
+  for (int s = 0; s < d->n_scales; ++s) {
+    const MdnScale& S = d->scale[s];
+    KScale& Z = K.sc[s];
+    Z.sx = S.flow_sx; Z.sy = S.flow_sy; Z.wm1 = (float)(Z.w - 1); Z.hm1 = (float)(Z.h - 1);
+    const double div = S.scale_div > 0.f ? (double)S.scale_div : 1.0;
+    Q.scale_div[s] = (float)div;
+    const double N = (double)d->batch * Z.h * Z.w;
+    Z.c_epi = (float)(d->w_e / (div * N));
+    Z.c_nt = (float)((double)d->w_e * d->alpha / (div * N));
+    Z.c_ce = (float)((double)d->w_e * d->w_d2_sim / (div * N));
+    Z.c_l1 = (float)((double)d->w_p * Q.l1_coef / (div * 3.0 * N));
+    Z.c_ssim = (float)((double)d->w_p * Q.ssim_coef / (div * 3.0 * N));
+    Z.c_smx = (float)(d->w_s / (div * (double)d->batch * Z.h * (Z.w - 1)));
+    Z.c_smy = (float)(d->w_s / (div * (double)d->batch * (Z.h - 1) * Z.w));
+    Z.c_consis = (float)(d->w_c / (div * N));
+    Z.tgt = S.tgt; Z.weight = S.weight; Z.inst = S.inst;
+    for (int p = 0; p < 2; ++p) {
+      Z.ref[p] = S.ref[p]; Z.flow[p] = S.flow[p]; Z.mob[p] = S.mob[p]; Z.fmat[p] = S.fmat[p];
+      Z.g_flow[p] = S.g_flow[p]; Z.g_mob[p] = S.g_mob[p]; Q.g_fmat[s][p] = S.g_fmat[p];
+      Z.post_map[p] = S.post_map[p]; Z.ori_map[p] = S.ori_map[p]; Z.warped[p] = S.warped[p]; Z.diff[p] = S.diff[p];
+      Z.valid[p] = S.valid[p]; Z.ssim_map[p] = S.ssim_map[p];
+    }
+  }
+  // SN keys and the completion ticket are adjacent in the workspace: one memset node zeroes both
+  if (cudaMemsetAsync(keys, 0, L.total - L.snkeys, stream) != cudaSuccess) return fail(MDN_ERR_CUDA, "memset failed");
+  if ((d->flags & MDN_TERM_EPIPOLAR) && d->post == MDN_POST_SN) {
+    size_t nkeys = (size_t)d->n_scales * d->n_pairs * d->batch;
+    const int chunks = 16;
+    dim3 grid(chunks, (unsigned)nkeys);
+    MDN_LAUNCH(sn_max_kernel, grid, dim3(NTHREADS), 0, stream, K, keys, chunks);
+  }
+  const bool photo = (d->flags & MDN_TERM_PHOTO) != 0;
+  const size_t smem = fused_smem_floats(photo, NTHREADS / 32) * sizeof(float);
+#ifndef MDN_EMU
+  static bool attr_set = false;   // idempotent; a benign race sets it twice
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(fused_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fused_smem_floats(true, NTHREADS / 32) * sizeof(float))) != cudaSuccess)
+      return fail(MDN_ERR_CUDA, "cudaFuncSetAttribute failed");
+    attr_set = true;
+  }
+#endif
+  MDN_LAUNCH(fused_tile_kernel, dim3(K.n_tiles), dim3(NTHREADS), smem, stream, K);
+  MDN_LAUNCH(finish_kernel, dim3(d->n_scales * d->batch), dim3(FIN_ROWS * NSLOT), 0, stream, Q);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return MDN_OK;
+}
+
+extern "C" int mdn_loss_scale_grads(const MdnLossDesc* d, const float* g, float* applied, void* stream_) {
+  if (!d || !g || !applied) return fail(MDN_ERR_NULL_POINTER, "desc / g / applied is NULL");
+  if (d->batch < 1 || d->n_scales < 1 || d->n_scales > MDN_MAX_SCALES) return fail(MDN_ERR_BAD_SHAPE, "batch / n_scales out of range");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GradList L;
+  memset(&L, 0, sizeof(L));
+  for (int s = 0; s < d->n_scales; ++s) {
+    const MdnScale& S = d->scale[s];
+    const long long hw = (long long)S.height * S.width;
+    for (int p = 0; p < MDN_MAX_PAIRS; ++p) {
+      if (S.g_flow[p]) { L.ptr[L.n] = S.g_flow[p]; L.count[L.n++] = 2 * hw * d->batch; }
+      if (S.g_mob[p]) { L.ptr[L.n] = S.g_mob[p]; L.count[L.n++] = hw * d->batch; }
+      if (S.g_fmat[p]) { L.ptr[L.n] = S.g_fmat[p]; L.count[L.n++] = 9ll * d->batch; }
+    }
+  }
+  if (L.n == 0) return MDN_OK;
+  MDN_LAUNCH(scale_grads_kernel, dim3(592), dim3(NTHREADS), 0, stream, L, g, applied);
+  MDN_LAUNCH(set_applied_kernel, dim3(1), dim3(1), 0, stream, g, applied);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return MDN_OK;
+}
+
+static inline unsigned blocks_for(long long n, int cap = 148 * 8) {
+  long long b = (n + NTHREADS - 1) / NTHREADS;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+extern "C" int mdn_epipolar_points_fwd(const float* p1, const float* p2, const float* fmat, float* out, int32_t batch,
+                                       int64_t n, void* stream) {
+  if (!p1 || !p2 || !fmat || !out) return fail(MDN_ERR_NULL_POINTER, "p1 / p2 / fmat / out is NULL");
+  if (batch < 1 || n < 1) return fail(MDN_ERR_BAD_SHAPE, "batch and n must be >= 1");
+  MDN_LAUNCH(epipolar_points_fwd_kernel, dim3(blocks_for(n), batch), dim3(NTHREADS), 0, (cudaStream_t)stream, p1, p2, fmat, out, (long long)n);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+static const int EPB_BLOCKS = 64;
+extern "C" size_t mdn_epipolar_points_workspace_bytes(int32_t batch, int64_t) {
+  return (size_t)(batch < 1 ? 0 : batch) * EPB_BLOCKS * EPB_SLOTS * sizeof(float);
+}
+
+extern "C" int mdn_epipolar_points_bwd(const float* p1, const float* p2, const float* fmat, const float* g_out, float* g_p1,
+                                       float* g_p2, float* g_fmat, int32_t batch, int64_t n, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  if (!p1 || !p2 || !fmat || !g_out) return fail(MDN_ERR_NULL_POINTER, "p1 / p2 / fmat / g_out is NULL");
+  if (batch < 1 || n < 1) return fail(MDN_ERR_BAD_SHAPE, "batch and n must be >= 1");
+  if (!workspace || workspace_bytes < mdn_epipolar_points_workspace_bytes(batch, n)) return fail(MDN_ERR_WORKSPACE, "workspace too small");
+  MDN_LAUNCH(epipolar_points_bwd_kernel, dim3(EPB_BLOCKS, batch), dim3(NTHREADS), 0, (cudaStream_t)stream, p1, p2, fmat, g_out, g_p1, g_p2,
+             (float*)workspace, (long long)n);
+  if (g_fmat) MDN_LAUNCH(epipolar_points_bwd_finish_kernel, dim3(batch), dim3(32), 0, (cudaStream_t)stream, (const float*)workspace, g_fmat, EPB_BLOCKS);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" int mdn_flow_warp_fwd(const float* ref, const float* flow, float* warped, float* grid_out, uint8_t* valid,
+                                 int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t flowwarp_norm, void* stream) {
+  if (!flow || (warped && !ref)) return fail(MDN_ERR_NULL_POINTER, "flow / ref is NULL");
+  if (batch < 1 || channels < 0 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad warp shape (h,w >= 2)");
+  MDN_LAUNCH(flow_warp_fwd_kernel, dim3(blocks_for((long long)height * width), batch), dim3(NTHREADS), 0, (cudaStream_t)stream, ref, flow, warped,
+             grid_out, valid, (int)channels, (int)height, (int)width, (int)flowwarp_norm);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" int mdn_flow_warp_bwd(const float* ref, const float* flow, const float* g_warped, float* g_flow, int32_t batch,
+                                 int32_t channels, int32_t height, int32_t width, void* stream) {
+  if (!ref || !flow || !g_warped || !g_flow) return fail(MDN_ERR_NULL_POINTER, "ref / flow / g_warped / g_flow is NULL");
+  if (batch < 1 || channels < 1 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad warp shape (h,w >= 2)");
+  MDN_LAUNCH(flow_warp_bwd_kernel, dim3(blocks_for((long long)height * width), batch), dim3(NTHREADS), 0, (cudaStream_t)stream, ref, flow, g_warped,
+             g_flow, (int)channels, (int)height, (int)width);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" int mdn_ssim_fwd(const float* x, const float* y, float* out, int32_t planes, int32_t height, int32_t width, void* stream) {
+  if (!x || !y || !out) return fail(MDN_ERR_NULL_POINTER, "x / y / out is NULL");
+  if (planes < 1 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad SSIM shape (h,w >= 2)");
+  MDN_LAUNCH(ssim_fwd_kernel, dim3(blocks_for((long long)height * width), planes), dim3(NTHREADS), 0, (cudaStream_t)stream, x, y, out, (int)height, (int)width);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" int mdn_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* g_y, int32_t planes,
+                            int32_t height, int32_t width, void* stream) {
+  if (!x || !y || !g_out) return fail(MDN_ERR_NULL_POINTER, "x / y / g_out is NULL");
+  if (planes < 1 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad SSIM shape (h,w >= 2)");
+  MDN_LAUNCH(ssim_bwd_kernel, dim3(blocks_for((long long)height * width), planes), dim3(NTHREADS), 0, (cudaStream_t)stream, x, y, g_out, g_x, g_y,
+             (int)height, (int)width);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream) {
+  if (!x || !out) return fail(MDN_ERR_NULL_POINTER, "x / out is NULL");
+  if (n < 1) return MDN_OK;
+  MDN_LAUNCH(binary_image_kernel, dim3(blocks_for(n)), dim3(NTHREADS), 0, (cudaStream_t)stream, x, out, (long long)n, threshold);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}

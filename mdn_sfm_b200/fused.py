@@ -1,0 +1,183 @@
+"""Host side of the fused loss call: tensor marshalling + the autograd node.
+
+One ``mdn_loss_fused`` call evaluates every requested term for all scales and both source frames and, when any
+input requires grad, also writes the gradients for an upstream gradient of 1 (the loss is a scalar, so the
+backward pass is a rescale -- ``mdn_loss_scale_grads`` -- that returns immediately for ``loss.backward()``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import _cabi
+from ._cabi import (MASK_MIN, MASK_OWN, MASK_SHARED, OPT_CROSS_ENT, OPT_GRADS, OPT_INST_MASK, OPT_SSIM, OUT_APPLIED,
+                    OUT_COUNT, POST_SN, POST_T, POST_TG, TERM_CONSIS, TERM_EPIPOLAR, TERM_PHOTO, TERM_SMOOTH)
+
+POST_OF_MODE = {"SN": POST_SN, "T": POST_T, "TG": POST_TG}
+
+
+def fundamental_matrix(inv_K, rotation, translation):
+    """F = K^-T ((t_x R) K^-1), the three small matmuls of loss_utils.py:50-62 in the reference's association order.
+
+    Stays in torch on the host side of the boundary: parity of F is then exact by
+    construction and autograd carries the kernel's d(loss)/dF back to rotation / translation / PoseNet.
+    Broadcasts: inv_K (..., B, 3, 3), rotation (..., B, 3, 3), translation (..., B, 3).
+    """
+    t0, t1, t2 = translation[..., 0], translation[..., 1], translation[..., 2]
+    z = torch.zeros_like(t0)
+    t_x = torch.stack([z, -t2, t1, t2, z, -t0, -t1, t0, z], dim=-1).reshape(translation.shape[:-1] + (3, 3))
+    return torch.matmul(inv_K.transpose(-2, -1), torch.matmul(torch.matmul(t_x, rotation), inv_K))
+
+
+@dataclass
+class ScaleData:
+    """Tensors of one pyramid level, in the order the C ABI wants them."""
+    height: int
+    width: int
+    flow_sx: float
+    flow_sy: float
+    scale_div: float
+    tgt: Optional[torch.Tensor] = None
+    ref: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
+    flow: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
+    mob: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
+    fmat: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
+    weight: Optional[torch.Tensor] = None
+    inst: Optional[torch.Tensor] = None
+
+
+@dataclass
+class FusedConfig:
+    batch: int
+    n_pairs: int
+    post: int
+    mask_mode: int
+    flags: int
+    threshold: Optional[float] = None
+    alpha: float = 0.0
+    w_d2_sim: float = 0.0
+    w_e: float = 1.0
+    w_s: float = 1.0
+    w_c: float = 1.0
+    w_p: float = 1.0
+    want_maps: tuple = ()   # subset of ("post_map", "ori_map", "warped", "diff", "valid", "ssim_map"), scale 0 only
+
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None):
+    """Launches the fused kernel.
+
+    need_grad: per scale a dict {"flow": [bool,bool], "mob": [bool,bool], "fmat": [bool,bool]}.
+    Returns (loss_out (8,), grads (same structure, tensors or None), maps (dict name -> [pair tensors]), call).
+    """
+    library = library or _cabi.lib()
+    dev = None
+    any_grad = any(any(v) for ng in need_grad for v in ng.values())
+    flags = cfg.flags | (OPT_GRADS if any_grad else 0)
+    call = _cabi.FusedCall(batch=cfg.batch, n_pairs=cfg.n_pairs, post=cfg.post, mask_mode=cfg.mask_mode, flags=flags,
+                           threshold=cfg.threshold, alpha=cfg.alpha, w_d2_sim=cfg.w_d2_sim, w_e=cfg.w_e, w_s=cfg.w_s,
+                           w_c=cfg.w_c, w_p=cfg.w_p)
+    grads, maps = [], {}
+    B = cfg.batch
+    for k, (S, ng) in enumerate(zip(scales, need_grad)):
+        some = S.flow[0] if S.flow[0] is not None else (S.mob[0] if S.mob[0] is not None else S.tgt)
+        dev = some.device
+        h, w = S.height, S.width
+        g = {"flow": [None, None], "mob": [None, None], "fmat": [None, None]}
+        for p in range(2):
+            if ng["flow"][p]:
+                g["flow"][p] = torch.empty((B, 2, h, w), dtype=torch.float32, device=dev)
+            if ng["mob"][p]:
+                g["mob"][p] = torch.empty((B, 1, h, w), dtype=torch.float32, device=dev)
+            if ng["fmat"][p]:
+                g["fmat"][p] = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+        if any_grad and cfg.mask_mode == MASK_MIN and (g["mob"][0] is None) != (g["mob"][1] is None):
+            # the arg-min routing writes both maps; give the kernel a scratch target for the unused one
+            for p in range(2):
+                if g["mob"][p] is None:
+                    g["mob"][p] = torch.empty((B, 1, h, w), dtype=torch.float32, device=dev)
+        extra = {}
+        if k == 0:
+            for name in cfg.want_maps:
+                if name == "valid":
+                    bufs = [torch.empty((B, 1, h, w), dtype=torch.uint8, device=dev) for _ in range(cfg.n_pairs)]
+                elif name in ("post_map", "ori_map"):
+                    bufs = [torch.empty((B, 1, h, w), dtype=torch.float32, device=dev) for _ in range(cfg.n_pairs)]
+                else:
+                    bufs = [torch.empty((B, 3, h, w), dtype=torch.float32, device=dev) for _ in range(cfg.n_pairs)]
+                maps[name] = bufs
+                extra[name] = bufs
+        call.add_scale(h, w, S.flow_sx, S.flow_sy, S.scale_div, tgt=S.tgt, ref=S.ref, flow=S.flow, mob=S.mob,
+                       fmat=S.fmat, weight=S.weight, inst=S.inst, g_flow=g["flow"], g_mob=g["mob"], g_fmat=g["fmat"],
+                       **extra)
+        grads.append(g)
+    loss_out = torch.empty(OUT_COUNT, dtype=torch.float32, device=dev)
+    ws = _workspace(dev, call.workspace_bytes(library))
+    call.run(library, loss_out, ws, _cabi.stream_ptr(loss_out))
+    return loss_out, grads, maps, call
+
+
+class _FusedLossFn(torch.autograd.Function):
+    """total = fused(flows, mobs, fmats); the gradients were produced by the forward launch."""
+
+    @staticmethod
+    def forward(ctx, cfg, scales, slots, library, *diff_inputs):
+        # slots[i] = (scale index, kind, pair) for diff_inputs[i]
+        need = [{"flow": [False, False], "mob": [False, False], "fmat": [False, False]} for _ in scales]
+        for (k, kind, p), t in zip(slots, diff_inputs):
+            if t.requires_grad:
+                need[k][kind][p] = True
+        loss_out, grads, maps, call = run_fused(cfg, scales, need, library)
+        ctx.call, ctx.library, ctx.slots, ctx.grads, ctx.loss_out = call, library, slots, grads, loss_out
+        ctx.maps = maps
+        total = loss_out[0]
+        terms = loss_out[1:5]
+        ctx.mark_non_differentiable(terms)
+        return total, terms
+
+    @staticmethod
+    def backward(ctx, g_total, _g_terms):
+        g = g_total.contiguous()
+        if g.dtype != torch.float32:
+            g = g.float()
+        ctx.call.scale_grads(ctx.library, g, ctx.loss_out[OUT_APPLIED:], _cabi.stream_ptr(g))
+        out = [None, None, None, None]
+        for (k, kind, p) in ctx.slots:
+            out.append(ctx.grads[k][kind][p])
+        return tuple(out)
+
+
+def fused_loss(cfg: FusedConfig, scales: List[ScaleData], library=None):
+    """-> (total 0-d tensor with grad_fn, terms (4,) = [epip, smooth, consis, photo] detached, maps dict)."""
+    library = library or _cabi.lib()
+    slots, diff = [], []
+    for k, S in enumerate(scales):
+        for kind in ("flow", "mob", "fmat"):
+            for p, t in enumerate(getattr(S, kind)):
+                if t is not None and t.requires_grad and torch.is_grad_enabled():
+                    if kind == "mob" and cfg.mask_mode == MASK_SHARED and p == 1:
+                        continue
+                    slots.append((k, kind, p))
+                    diff.append(t)
+    holder = {}
+    if diff:
+        total, terms = _FusedLossFn.apply(cfg, scales, slots, library, *diff)
+        maps = total.grad_fn.maps if total.grad_fn is not None and hasattr(total.grad_fn, "maps") else holder
+    else:
+        need = [{"flow": [False, False], "mob": [False, False], "fmat": [False, False]} for _ in scales]
+        loss_out, _, maps, _ = run_fused(cfg, scales, need, library)
+        total, terms = loss_out[0], loss_out[1:5]
+    return total, terms, maps

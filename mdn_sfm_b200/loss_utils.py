@@ -1,0 +1,121 @@
+"""Drop-in for the reference ``loss_utils.py``: same free functions, same signatures.
+
+The heavy ones (`inverse_warp`, `get_epipolar_new`, `smooth_loss`) call the CUDA kernels through the C ABI;
+the per-pixel one-liners that the reference applies to maps it has already materialised
+(`post_process_epipolar_*`, `derivable_consistency_loss`, `detectron2_similarity_loss`) are thin torch
+expressions on CUDA tensors -- inside ``Loss.forward`` none of them runs, the fused kernel does that work.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi, fused
+from .ops import EpipolarPointsFn, FlowWarpFn, _c
+
+__all__ = ["inverse_warp", "get_epipolar_new", "detectron2_similarity_loss", "post_pro_epipolar_weighted",
+           "post_process_epipolar_1", "get_batch_instance_mask", "post_process_epipolar_2", "create_coords",
+           "smooth_loss", "derivable_consistency_loss", "compute_quantiles"]
+
+
+def inverse_warp(ref_img, flow_map, pix_coords, padding_mode, library=None):
+    """loss_utils.py:12-36 -> (warped (B,3,H,W), valid_points bool (B,3,H,W)).
+
+    `pix_coords` is accepted for signature compatibility; the kernel derives the grid from the thread index
+    (it must be the regular pixel grid, which is what every caller passes).
+    """
+    if padding_mode != "zeros":
+        raise NotImplementedError("mdn_sfm_b200: only padding_mode='zeros' is implemented")
+    ref_img, flow_map = _c(ref_img, "ref_img"), _c(flow_map, "flow_map")
+    warped, _, valid = FlowWarpFn.apply(ref_img, flow_map, False, True, library)
+    return warped, valid.bool().unsqueeze(1).expand(-1, ref_img.shape[1], -1, -1)
+
+
+def get_epipolar_new(p1, p2, inv_K, rotation, translation, library=None):
+    """loss_utils.py:39-69 -> signed epipolar distance (B,1,N)."""
+    F = fused.fundamental_matrix(inv_K, rotation, translation).contiguous()
+    return EpipolarPointsFn.apply(_c(p1, "p1"), _c(p2, "p2"), _c(F, "F"), library)
+
+
+def get_batch_instance_mask(instances_info):
+    """loss_utils.py:102-124 -> int64 {0,1} (B,3,H,W) / (1,3,H,W)."""
+    if isinstance(instances_info, list):
+        m = torch.stack([(info["instances"].pred_masks.sum(0, keepdim=True) != 0) for info in instances_info], 0)
+    else:
+        m = (instances_info.pred_masks.sum(0, keepdim=True) != 0).unsqueeze(0)
+    return m.to(torch.int64).repeat(1, 3, 1, 1)
+
+
+def instance_mask_u8(instances_info, size, device):
+    """One-channel uint8 {0,1} instance mask at `size`, resized exactly as loss_utils.py:73-75 / :135-137 do
+    (torchvision Resize on the int64 mask, bilinear + antialias, rounded back to integers); the three
+    channels the reference carries are identical, so one is kept."""
+    from torchvision.transforms import Resize
+    if isinstance(instances_info, list):
+        m = torch.stack([(info["instances"].pred_masks.sum(0, keepdim=True) != 0) for info in instances_info], 0)
+    else:
+        m = (instances_info.pred_masks.sum(0, keepdim=True) != 0).unsqueeze(0)
+    m = Resize(tuple(size))(m.to(device=device, dtype=torch.int64))
+    return m[:, 0].to(torch.uint8).contiguous()
+
+
+def detectron2_similarity_loss(mobile_mask, instances_info):
+    """loss_utils.py:72-78 -> cross-entropy map (B,3,h,w)."""
+    from torchvision.transforms import Resize
+    mask = Resize(tuple(mobile_mask.size()[2:]))(get_batch_instance_mask(instances_info).to(mobile_mask.device))
+    return -(mask * torch.log(mobile_mask + 1e-10) + (1 - mask) * torch.log(1 - mobile_mask + 1e-10))
+
+
+def post_pro_epipolar_weighted(epipolar_map, weight=None, threshold=None):
+    """loss_utils.py:81-89 (T / TG)."""
+    post = epipolar_map.clone()
+    if threshold is not None:
+        post /= threshold
+    if weight is not None:
+        post /= weight
+    return post ** 2
+
+
+def post_process_epipolar_1(epipolar_map):
+    """loss_utils.py:92-99 (SN).  Divides its argument IN PLACE like the reference."""
+    b = epipolar_map.size(0)
+    norms = torch.max(epipolar_map.view(b, -1), dim=1, keepdim=True)[0]
+    epipolar_map /= norms[..., None, None]
+    return epipolar_map ** 2
+
+
+def post_process_epipolar_2(epipolar_map, instances_info):
+    """loss_utils.py:127-138 (DS)."""
+    from torchvision.transforms import Resize
+    mask = Resize(tuple(epipolar_map.size()[2:]))(get_batch_instance_mask(instances_info).to(epipolar_map.device))
+    return mask * epipolar_map
+
+
+def create_coords(batch_size=64, height=128, width=416):
+    """loss_utils.py:141-148 -> (B,2,H,W) CPU tensor (ch0 = column, ch1 = row), like the reference."""
+    xs = torch.arange(width, dtype=torch.float32).view(1, 1, 1, width).expand(1, 1, height, width)
+    ys = torch.arange(height, dtype=torch.float32).view(1, 1, height, 1).expand(1, 1, height, width)
+    return torch.cat([xs, ys], 1).repeat(batch_size, 1, 1, 1)
+
+
+def smooth_loss(target, mobile, library=None):
+    """loss_utils.py:151-168 -> scalar."""
+    target, mobile = _c(target, "target"), _c(mobile, "mobile")
+    b, _, h, w = target.shape
+    S = fused.ScaleData(h, w, 1.0, 1.0, 1.0, tgt=target)
+    S.mob[0] = mobile
+    cfg = fused.FusedConfig(batch=b, n_pairs=1, post=fused.POST_T, mask_mode=_cabi.MASK_SHARED, flags=_cabi.TERM_SMOOTH)
+    total, _, _ = fused.fused_loss(cfg, [S], library)
+    return total
+
+
+def derivable_consistency_loss(mobile1, mobile2, threshold=0.5):
+    """loss_utils.py:171-177 -> per-pixel map."""
+    return (torch.sigmoid(20 * (mobile1 - threshold)) - torch.sigmoid(20 * (mobile2 - threshold))) ** 2
+
+
+def compute_quantiles(flow, cam_T_cam, inv_K, p1, pix_coords, ones, scale_factor, percentage, i, b):
+    """loss_utils.py:197-202."""
+    flow_map = scale_factor * flow[("flow", i, 0)]
+    p2 = torch.cat([pix_coords + flow_map, ones], 1).view(b, 3, -1)
+    e = get_epipolar_new(p1, p2, inv_K[:, :3, :3], cam_T_cam[:, :3, :3], cam_T_cam[:, :3, -1]).view(b, -1).abs()
+    return torch.quantile(e, percentage, dim=1)
