@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- loss-path frames/s, forward + backward, @192x640 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape 192x640|375x1242] [--mode T]
+
+A *step* is one pass of the whole configured loss path over one batch: `Loss.forward` (all scales, both
+source frames: epipolar map + post-processing, flow warp, SSIM + L1, smoothness, consistency, min mask) followed
+by `losses["loss"].backward()` down to d/dflow, d/dmobile and d/dpose.  Workload at every N: BASELINE configs[1],
+T mode + photometric, batch 12 per GPU (weak scaling), 3x192x640, 4 scales, synthetic KITTI-shaped inputs.
+
+`value`   whole-job frames/s with inputs resident in HBM, the step replayed from a CUDA graph, `--sets` input
+          sets rotated so the working set (inputs + gradients) is several times the 126 MB L2.
+`e2e`     the same step through the public Python API with HOST inputs: pinned host -> device copies of every
+          input tensor and a device -> host read of the loss inside the timed region.
+`roofline` algorithmic bytes of one fused launch / its measured duration (CUDA events) vs MEASURED_PEAKS.json.
+`cpu_baseline` the oracle port (oracle/restate.py, eager torch, the reference's own op sequence) on the host cores.
+`--impl reference` prints the reference arm: the same oracle port timed on the host CPU with all threads.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "loss-path frames/s fwd+bwd @192x640"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="192x640")
+    ap.add_argument("--mode", default="T", choices=["SN", "T", "TG", "DS", "DC"])
+    ap.add_argument("--batch", type=int, default=12)
+    ap.add_argument("--sets", type=int, default=4, help="rotating input sets (defeats L2 reuse between steps)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 100)")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    H, W = map(int, args.shape.split("x"))
+    scales = (0, 1, 2, 3) if (H % 8 == 0 and W % 8 == 0) else (0,)
+    return H, W, scales
+
+
+def algorithmic_bytes_per_frame(H, W, scales, with_inst=False):
+    """One-pass variant A1 of SURVEY.md section 8d: every input read once, every gradient written once.
+    per scale-pixel: tgt 12 + mob 4+4 + 2 x (flow 8 + ref 12) = 60 read, g_flow 2x8 + g_mob 2x4 = 24 written."""
+    px = sum((H >> s) * (W >> s) for s in scales)
+    return px * (84 + (1 if with_inst else 0))
+
+
+def config_dict(args, H, W, scales, n_gpus):
+    return {"workload": "BASELINE configs[1]: %s-mode epipolar map + flow-warp SSIM/L1 photometric + smooth + consistency, "
+                        "fwd+bwd, batch %d/GPU x %d GPU, 3x%dx%d, %d scales, 2 source frames" % (
+                            args.mode, args.batch, n_gpus, H, W, len(scales)),
+            "mode": args.mode, "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus, "height": H, "width": W,
+            "scales": list(scales), "frame_ids": [0, -1, 1], "photometric": True, "ssim": True}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the GPU is under load."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.stop_flag = index, period, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step_fn(args, H, W, scales, seed=42):
+    """The oracle port on the host CPU: same workload, fwd + backward, all host threads."""
+    from mdn_sfm_b200 import synthetic
+    from oracle import restate
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    opt = synthetic.default_opt(args.batch, H, W)
+    inputs, flows, mobiles, cams, inst = synthetic.make_batch(args.batch, H, W, scales=scales, seed=seed, flow_std=0.05,
+                                                              with_instances=args.mode in ("DS", "DC"))
+    weights = restate.gauss_distance_weight(4, H, W) if args.mode == "TG" else None
+
+    def step():
+        f = {k: v.clone().requires_grad_(True) for k, v in flows.items()}
+        m = {k: v.clone().requires_grad_(True) for k, v in mobiles.items()}
+        c = {k: v.clone().requires_grad_(True) for k, v in cams.items()}
+        _, losses = restate.loss_forward(opt, inputs, [-1, 1], f, m, inst, list(scales), c, mode=args.mode,
+                                         weights=weights, photometric=True, ssim_on=True)
+        losses["loss"].backward()
+        return float(losses["loss"].detach())
+
+    return step, threads
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    H, W, scales = workload(args)
+    step, threads = cpu_reference_step_fn(args, H, W, scales)
+    warm = min(args.warmup, 2)
+    steps = max(1, min(args.steps, 20))     # bounded sample: ~1-2 s of CPU work per step
+    for _ in range(max(1, warm)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    fps = args.batch * steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": max(1, warm), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, H, W, scales, args.gpus),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": "%d steps of one batch of %d frames (the N=1 workload) on the host CPU, torch %d threads; "
+                                       "requested steps=%d were capped at 20" % (steps, args.batch, threads, args.steps)},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from mdn_sfm_b200 import _cabi, synthetic
+    from mdn_sfm_b200.loss_functions import Loss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.lib()   # fail loudly right here if the extension is missing
+
+    H, W, scales = workload(args)
+    B = args.batch
+    opt = synthetic.default_opt(B, H, W)
+    with_inst = args.mode in ("DS", "DC")
+    loss_mod = Loss(opt, no_ssim=False, mode=args.mode, photometric=True)
+    ids = [-1, 1]
+
+    # ---- input sets: pinned host masters + device-resident copies
+    host_sets, dev_sets = [], []
+    for k in range(args.sets):
+        inputs, flows, mobiles, cams, inst = synthetic.make_batch(B, H, W, scales=scales, seed=42 + rank + 1000 * k,
+                                                                  flow_std=0.05, with_instances=with_inst)
+        pin = lambda d: {kk: v.pin_memory() for kk, v in d.items()}
+        host_sets.append((pin(inputs), pin(flows), pin(mobiles), pin(cams), inst))
+        to = lambda d, g=False: {kk: v.to(dev).requires_grad_(g) for kk, v in d.items()}
+        inst_d = [{"instances": d["instances"].to(dev)} for d in inst] if inst is not None else None
+        dev_sets.append((to(inputs), to(flows, True), to(mobiles, True), to(cams, True), inst_d))
+
+    def step_on(s):
+        inputs, flows, mobiles, cams, inst = s
+        for d in (flows, mobiles, cams):
+            for v in d.values():
+                v.grad = None
+        _, losses = loss_mod(inputs, ids, flows, mobiles, inst, list(scales), cams)
+        losses["loss"].backward()
+        return losses["loss"]
+
+    # ---- eager warm-up (also sets the kernel attributes outside any capture) + optional graph capture
+    for s in dev_sets:
+        step_on(s)
+    torch.cuda.synchronize()
+    graphs, graph_ok = [], not args.no_graph
+    if graph_ok:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for s in dev_sets:
+                    step_on(s)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for s in dev_sets:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    out = step_on(s)
+                graphs.append((g, out))
+            torch.cuda.synchronize()
+        except Exception as e:   # keep measuring, but say so
+            graph_ok, graphs = False, []
+            print("bench: CUDA graph capture failed (%r); timing eager launches" % (e,), file=sys.stderr)
+            torch.cuda.synchronize()
+
+    def run_step(i):
+        if graph_ok:
+            graphs[i % len(graphs)][0].replay()
+        else:
+            step_on(dev_sets[i % len(dev_sets)])
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # clock ramp (untimed) so a short timed region does not run at idle clocks
+    t_end = time.perf_counter() + 1.0
+    i = 0
+    while time.perf_counter() < t_end:
+        run_step(i)
+        i += 1
+    for i in range(args.warmup):
+        run_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- dominant kernel alone: the fused launch (memset + fused_tile_kernel + finish_kernel nodes), eager, rotating sets
+    from mdn_sfm_b200 import fused as fz
+    post, bits = 1, 0
+    calls = []
+    from mdn_sfm_b200.loss_functions import _mode_bits
+    post, bits = _mode_bits(args.mode, "SN")
+    flags = bits | _cabi.TERM_SMOOTH | _cabi.TERM_CONSIS | _cabi.TERM_PHOTO | _cabi.OPT_SSIM
+    lib = _cabi.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    for s in dev_sets:
+        inputs, flows, mobiles, cams, inst = s
+        with torch.no_grad():
+            data = loss_mod._scale_data(inputs, ids, flows, mobiles, inst, list(scales), cams, post, bits)
+        cfg = fz.FusedConfig(batch=B, n_pairs=2, post=post, mask_mode=_cabi.MASK_MIN, flags=flags,
+                             threshold=opt.threshold if post != 0 else None, alpha=opt.alpha, w_d2_sim=opt.w_d2_sim,
+                             w_e=opt.w_e, w_s=opt.w_s, w_c=opt.w_c, w_p=opt.w_p)
+        need = [{"flow": [True, True], "mob": [True, True], "fmat": [True, True]} for _ in data]
+        loss_out, grads, _, call = fz.run_fused(cfg, data, need, lib)
+        ws = fz._workspace(dev, call.workspace_bytes(lib))
+        calls.append((call, loss_out, ws, grads))
+    torch.cuda.synchronize()
+    n_k = max(200, min(args.steps, 2000))
+    for i in range(50):
+        c = calls[i % len(calls)]
+        c[0].run(lib, c[1], c[2], stream)
+        c[0].keep = c[0].keep[:-2]
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(n_k):
+        c = calls[i % len(calls)]
+        c[0].run(lib, c[1], c[2], stream)
+        c[0].keep = c[0].keep[:-2]
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / n_k
+    alg_bytes = algorithmic_bytes_per_frame(H, W, scales, with_inst) * B
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.shape)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "mdn::fused_tile_kernel (+ memset and finish_kernel nodes of the same mdn_loss_fused call)",
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
+
+    # ---- e2e: public API, host buffers in, loss out, every step
+    n_e2e = args.e2e_steps or min(args.steps, 100)
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    h2d_bytes = sum(v.numel() * v.element_size() for d in host_sets[0][:4] for v in d.values())
+
+    def e2e_step(i):
+        hs = host_sets[i % len(host_sets)]
+        up = lambda d, g=False: {kk: v.to(dev, non_blocking=True).requires_grad_(g) for kk, v in d.items()}
+        s = (up(hs[0]), up(hs[1], True), up(hs[2], True), up(hs[3], True), dev_sets[i % len(dev_sets)][4])
+        loss = step_on(s)
+        host_loss.copy_(loss.detach(), non_blocking=True)
+
+    for i in range(5):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(n_e2e):
+        e2e_step(i)
+    f1.record()
+    torch.cuda.synchronize()
+    e2e_ms = f0.elapsed_time(f1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * n_e2e / (e2e_ms * 1e-3)
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        step, threads = cpu_reference_step_fn(args, H, W, scales)
+        step()
+        best = 1e30
+        for _ in range(args.cpu_steps):
+            t0 = time.perf_counter()
+            step()
+            best = min(best, time.perf_counter() - t0)
+        cpu_base = {"value": B / best, "unit": "frames/s", "cores": threads, "kind": "port",
+                    "sample": "best of %d steps of the same batch of %d frames (oracle/restate.py, eager torch on the host CPU, "
+                              "%d threads, anomaly detection off)" % (args.cpu_steps, B, threads)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": dict(config_dict(args, H, W, scales, world), cuda_graph=graph_ok,
+                                                    l2="%d rotating input sets (%.0f MB inputs+grads per set vs 126 MB L2)" % (
+                                                        args.sets, (alg_bytes) / 1e6)),
+                "clocks": sampler.summary(),
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                        "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
+                        "path": "mdn_sfm_b200.loss_functions.Loss.forward + backward (eager public API), pinned host inputs"},
+                "gpu_launches": 3 * args.steps,
+                "launches_per_step": "mdn::fused_tile_kernel, mdn::finish_kernel, mdn::scale_grads_kernel (+1 memset node, "
+                                     "+ torch's tiny F-matrix ops)",
+                "roofline": roofline, "cpu_baseline": cpu_base}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)

@@ -25,6 +25,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define MDN_API __attribute__((visibility("default")))
+#else
+#define MDN_API
+#endif
+
 #define MDN_ABI_VERSION 1
 #define MDN_MAX_SCALES 4
 #define MDN_MAX_PAIRS 2
@@ -107,12 +113,12 @@ typedef struct MdnLossDesc {
 enum MdnLossOut { MDN_OUT_LOSS = 0, MDN_OUT_EPIP = 1, MDN_OUT_SMOOTH = 2, MDN_OUT_CONSIS = 3, MDN_OUT_PHOTO = 4,
                   MDN_OUT_APPLIED = 5, MDN_OUT_COUNT = 8 };
 
-int mdn_version(void);
-const char* mdn_last_error_string(void);
+MDN_API int mdn_version(void);
+MDN_API const char* mdn_last_error_string(void);
 
 /* Bytes of device workspace mdn_loss_fused needs for this description (tile partial sums, per-sample
  * sums, SN max keys, a completion ticket). */
-size_t mdn_loss_workspace_bytes(const MdnLossDesc* desc);
+MDN_API size_t mdn_loss_workspace_bytes(const MdnLossDesc* desc);
 
 /*
  * The whole loss path in one call: replaces Loss.forward (loss_functions.py:170-205) and everything it
@@ -131,26 +137,27 @@ size_t mdn_loss_workspace_bytes(const MdnLossDesc* desc);
  *   loss_out[MDN_OUT_PHOTO]  = sum_s sum_i (0.15*mean(diff) + 0.85*mean(SSIM)  |  mean(diff)) / scale_div
  *   loss_out[MDN_OUT_LOSS]   = w_e*EPIP + w_s*SMOOTH + w_c*CONSIS + w_p*PHOTO
  */
-int mdn_loss_fused(const MdnLossDesc* desc, float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
+MDN_API int mdn_loss_fused(const MdnLossDesc* desc, float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Backward of the call above for an arbitrary upstream gradient: multiplies every gradient buffer named in
- * `desc` by (*g / *applied) and stores *g into *applied.  When *g == *applied (the usual loss.backward(),
+ * `desc` by (*g / *applied) and stores *g into *applied (`applied` = loss_out + MDN_OUT_APPLIED of the forward
+ * call: two floats, the value and a completion ticket).  When *g == *applied (the usual loss.backward(),
  * g == 1) the kernel exits without touching memory.  `g` and `applied` are device scalars.
  */
-int mdn_loss_scale_grads(const MdnLossDesc* desc, const float* g, float* applied, void* stream);
+MDN_API int mdn_loss_scale_grads(const MdnLossDesc* desc, const float* g, float* applied, void* stream);
 
 /*
  * get_epipolar_new (loss_utils.py:39-69) for arbitrary homogeneous point sets: p1, p2 are (B,3,N), fmat
  * (B,3,3); out (B,1,N) is the SIGNED distance.  The backward takes the upstream gradient g_out (B,1,N)
  * and writes g_p1, g_p2 (B,3,N, either may be NULL) and g_fmat (B,3,3, may be NULL).
  */
-int mdn_epipolar_points_fwd(const float* p1, const float* p2, const float* fmat, float* out, int32_t batch,
+MDN_API int mdn_epipolar_points_fwd(const float* p1, const float* p2, const float* fmat, float* out, int32_t batch,
                             int64_t n, void* stream);
-int mdn_epipolar_points_bwd(const float* p1, const float* p2, const float* fmat, const float* g_out, float* g_p1,
+MDN_API int mdn_epipolar_points_bwd(const float* p1, const float* p2, const float* fmat, const float* g_out, float* g_p1,
                             float* g_p2, float* g_fmat, int32_t batch, int64_t n, void* workspace,
                             size_t workspace_bytes, void* stream);
-size_t mdn_epipolar_points_workspace_bytes(int32_t batch, int64_t n);
+MDN_API size_t mdn_epipolar_points_workspace_bytes(int32_t batch, int64_t n);
 
 /*
  * inverse_warp (loss_utils.py:12-36) / FlowWarp (utils.py:289-315): bilinear flow warp, zeros padding,
@@ -159,23 +166,23 @@ size_t mdn_epipolar_points_workspace_bytes(int32_t batch, int64_t n);
  * (g-0.5)*2 normalisation of utils.py:311 instead of 2*g-1 (loss_utils.py:31) -- same value, other rounding.
  * The backward takes g_warped (B,C,h,w) and writes g_flow (B,2,h,w).
  */
-int mdn_flow_warp_fwd(const float* ref, const float* flow, float* warped, float* grid_out, uint8_t* valid,
+MDN_API int mdn_flow_warp_fwd(const float* ref, const float* flow, float* warped, float* grid_out, uint8_t* valid,
                       int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t flowwarp_norm,
                       void* stream);
-int mdn_flow_warp_bwd(const float* ref, const float* flow, const float* g_warped, float* g_flow, int32_t batch,
+MDN_API int mdn_flow_warp_bwd(const float* ref, const float* flow, const float* g_warped, float* g_flow, int32_t batch,
                       int32_t channels, int32_t height, int32_t width, void* stream);
 
 /*
  * SSIM module (networks/layers.py:148-178): out = clamp((1 - SSIM(x,y))/2, 0, 1), 3x3 reflect-padded.
  * x, y, out, g_out, g_x, g_y are (planes,h,w) with planes = B*C.  g_x / g_y may be NULL.
  */
-int mdn_ssim_fwd(const float* x, const float* y, float* out, int32_t planes, int32_t height, int32_t width,
+MDN_API int mdn_ssim_fwd(const float* x, const float* y, float* out, int32_t planes, int32_t height, int32_t width,
                  void* stream);
-int mdn_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* g_y, int32_t planes,
+MDN_API int mdn_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* g_y, int32_t planes,
                  int32_t height, int32_t width, void* stream);
 
 /* binary_image (utils.py:100-103): out = x >= threshold ? 1 : 0 */
-int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream);
+MDN_API int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream);
 
 #ifdef __cplusplus
 }

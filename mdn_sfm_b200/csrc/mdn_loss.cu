@@ -593,17 +593,24 @@ struct GradList {
   long long count[MDN_MAX_SCALES * 6];
 };
 
-__global__ void __launch_bounds__(NTHREADS) scale_grads_kernel(const __grid_constant__ GradList L, const float* g, float* applied) {
+__global__ void __launch_bounds__(NTHREADS) scale_grads_kernel(const __grid_constant__ GradList L, const float* g, float* applied,
+                                                               unsigned* ticket) {
+  __shared__ bool is_last;
   const float gv = __ldg(g), ap = *applied;
-  if (gv == ap) return;                      // loss.backward() with the implicit upstream gradient of 1
+  if (gv == ap) return;                      // loss.backward() with the implicit upstream gradient of 1: nothing to do
   const float ratio = gv / ap;
   for (int k = 0; k < L.n; ++k) {
     float* p = L.ptr[k];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < L.count[k]; i += (long long)gridDim.x * blockDim.x)
       p[i] *= ratio;
   }
+  // every block has read *applied before the last one to finish overwrites it
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) *applied = gv;
 }
-__global__ void set_applied_kernel(const float* g, float* applied) { *applied = *g; }
 
 // ----------------------------------------------------------------------------------------------- standalone kernels
 __global__ void __launch_bounds__(NTHREADS) epipolar_points_fwd_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
@@ -803,8 +810,8 @@ static int fail(int code, const char* fmt, const char* what = "") {
 }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-extern "C" int mdn_version(void) { return MDN_ABI_VERSION; }
-extern "C" const char* mdn_last_error_string(void) { return g_err; }
+extern "C" MDN_API int mdn_version(void) { return MDN_ABI_VERSION; }
+extern "C" MDN_API const char* mdn_last_error_string(void) { return g_err; }
 
 struct WsLayout { size_t partials, sample_sums, snkeys, ticket, total; int n_tiles; };
 
@@ -868,14 +875,14 @@ static WsLayout ws_layout(const MdnLossDesc* d, int n_tiles) {
   return L;
 }
 
-extern "C" size_t mdn_loss_workspace_bytes(const MdnLossDesc* d) {
+extern "C" MDN_API size_t mdn_loss_workspace_bytes(const MdnLossDesc* d) {
   if (check_desc(d) != MDN_OK) return 0;
   KParams K;
   memset(&K, 0, sizeof(K));
   return ws_layout(d, plan_tiles(d, K)).total;
 }
 
-extern "C" int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, void* workspace, size_t workspace_bytes, void* stream_) {
+extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, void* workspace, size_t workspace_bytes, void* stream_) {
   int rc = check_desc(d);
   if (rc != MDN_OK) return rc;
   if (!loss_out) return fail(MDN_ERR_NULL_POINTER, "loss_out is NULL");
@@ -946,7 +953,7 @@ extern "C" int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, void* works
   return MDN_OK;
 }
 
-extern "C" int mdn_loss_scale_grads(const MdnLossDesc* d, const float* g, float* applied, void* stream_) {
+extern "C" MDN_API int mdn_loss_scale_grads(const MdnLossDesc* d, const float* g, float* applied, void* stream_) {
   if (!d || !g || !applied) return fail(MDN_ERR_NULL_POINTER, "desc / g / applied is NULL");
   if (d->batch < 1 || d->n_scales < 1 || d->n_scales > MDN_MAX_SCALES) return fail(MDN_ERR_BAD_SHAPE, "batch / n_scales out of range");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -962,8 +969,8 @@ extern "C" int mdn_loss_scale_grads(const MdnLossDesc* d, const float* g, float*
     }
   }
   if (L.n == 0) return MDN_OK;
-  MDN_LAUNCH(scale_grads_kernel, dim3(592), dim3(NTHREADS), 0, stream, L, g, applied);
-  MDN_LAUNCH(set_applied_kernel, dim3(1), dim3(1), 0, stream, g, applied);
+  // applied[1] (MDN_OUT_APPLIED + 1) is the completion ticket, zeroed by mdn_loss_fused
+  MDN_LAUNCH(scale_grads_kernel, dim3(296), dim3(NTHREADS), 0, stream, L, g, applied, reinterpret_cast<unsigned*>(applied + 1));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return MDN_OK;
@@ -974,7 +981,7 @@ static inline unsigned blocks_for(long long n, int cap = 148 * 8) {
   return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-extern "C" int mdn_epipolar_points_fwd(const float* p1, const float* p2, const float* fmat, float* out, int32_t batch,
+extern "C" MDN_API int mdn_epipolar_points_fwd(const float* p1, const float* p2, const float* fmat, float* out, int32_t batch,
                                        int64_t n, void* stream) {
   if (!p1 || !p2 || !fmat || !out) return fail(MDN_ERR_NULL_POINTER, "p1 / p2 / fmat / out is NULL");
   if (batch < 1 || n < 1) return fail(MDN_ERR_BAD_SHAPE, "batch and n must be >= 1");
@@ -984,11 +991,11 @@ extern "C" int mdn_epipolar_points_fwd(const float* p1, const float* p2, const f
 }
 
 static const int EPB_BLOCKS = 64;
-extern "C" size_t mdn_epipolar_points_workspace_bytes(int32_t batch, int64_t) {
+extern "C" MDN_API size_t mdn_epipolar_points_workspace_bytes(int32_t batch, int64_t) {
   return (size_t)(batch < 1 ? 0 : batch) * EPB_BLOCKS * EPB_SLOTS * sizeof(float);
 }
 
-extern "C" int mdn_epipolar_points_bwd(const float* p1, const float* p2, const float* fmat, const float* g_out, float* g_p1,
+extern "C" MDN_API int mdn_epipolar_points_bwd(const float* p1, const float* p2, const float* fmat, const float* g_out, float* g_p1,
                                        float* g_p2, float* g_fmat, int32_t batch, int64_t n, void* workspace,
                                        size_t workspace_bytes, void* stream) {
   if (!p1 || !p2 || !fmat || !g_out) return fail(MDN_ERR_NULL_POINTER, "p1 / p2 / fmat / g_out is NULL");
@@ -1001,7 +1008,7 @@ extern "C" int mdn_epipolar_points_bwd(const float* p1, const float* p2, const f
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }
 
-extern "C" int mdn_flow_warp_fwd(const float* ref, const float* flow, float* warped, float* grid_out, uint8_t* valid,
+extern "C" MDN_API int mdn_flow_warp_fwd(const float* ref, const float* flow, float* warped, float* grid_out, uint8_t* valid,
                                  int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t flowwarp_norm, void* stream) {
   if (!flow || (warped && !ref)) return fail(MDN_ERR_NULL_POINTER, "flow / ref is NULL");
   if (batch < 1 || channels < 0 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad warp shape (h,w >= 2)");
@@ -1011,7 +1018,7 @@ extern "C" int mdn_flow_warp_fwd(const float* ref, const float* flow, float* war
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }
 
-extern "C" int mdn_flow_warp_bwd(const float* ref, const float* flow, const float* g_warped, float* g_flow, int32_t batch,
+extern "C" MDN_API int mdn_flow_warp_bwd(const float* ref, const float* flow, const float* g_warped, float* g_flow, int32_t batch,
                                  int32_t channels, int32_t height, int32_t width, void* stream) {
   if (!ref || !flow || !g_warped || !g_flow) return fail(MDN_ERR_NULL_POINTER, "ref / flow / g_warped / g_flow is NULL");
   if (batch < 1 || channels < 1 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad warp shape (h,w >= 2)");
@@ -1021,7 +1028,7 @@ extern "C" int mdn_flow_warp_bwd(const float* ref, const float* flow, const floa
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }
 
-extern "C" int mdn_ssim_fwd(const float* x, const float* y, float* out, int32_t planes, int32_t height, int32_t width, void* stream) {
+extern "C" MDN_API int mdn_ssim_fwd(const float* x, const float* y, float* out, int32_t planes, int32_t height, int32_t width, void* stream) {
   if (!x || !y || !out) return fail(MDN_ERR_NULL_POINTER, "x / y / out is NULL");
   if (planes < 1 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad SSIM shape (h,w >= 2)");
   MDN_LAUNCH(ssim_fwd_kernel, dim3(blocks_for((long long)height * width), planes), dim3(NTHREADS), 0, (cudaStream_t)stream, x, y, out, (int)height, (int)width);
@@ -1029,7 +1036,7 @@ extern "C" int mdn_ssim_fwd(const float* x, const float* y, float* out, int32_t 
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }
 
-extern "C" int mdn_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* g_y, int32_t planes,
+extern "C" MDN_API int mdn_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* g_y, int32_t planes,
                             int32_t height, int32_t width, void* stream) {
   if (!x || !y || !g_out) return fail(MDN_ERR_NULL_POINTER, "x / y / g_out is NULL");
   if (planes < 1 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad SSIM shape (h,w >= 2)");
@@ -1039,7 +1046,7 @@ extern "C" int mdn_ssim_bwd(const float* x, const float* y, const float* g_out, 
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }
 
-extern "C" int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream) {
+extern "C" MDN_API int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream) {
   if (!x || !out) return fail(MDN_ERR_NULL_POINTER, "x / out is NULL");
   if (n < 1) return MDN_OK;
   MDN_LAUNCH(binary_image_kernel, dim3(blocks_for(n)), dim3(NTHREADS), 0, (cudaStream_t)stream, x, out, (long long)n, threshold);

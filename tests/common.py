@@ -1,0 +1,101 @@
+"""Shared parity machinery: run the product and the oracle on the same seeded inputs and compare.
+
+Tolerances (BASELINE.json north star): forward values 1e-5 relative, gradients 1e-4, binary masks bit exact.
+Per-pixel tensors are compared in the max norm relative to the tensor's own max.
+"""
+import torch
+
+from mdn_sfm_b200 import synthetic
+from oracle import restate
+
+FWD_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+CASES = [
+    # mode, photometric, ssim, disable_min
+    ("T", True, True, False),      # BASELINE configs[1]
+    ("SN", True, True, False),     # configs[0]
+    ("TG", True, True, False),     # configs[2]
+    ("DC", False, False, False),   # HEAD
+    ("DS", False, False, True),
+    ("DC", True, True, True),
+    ("TG", True, False, True),
+]
+
+
+def leaf(d):
+    return {k: v.clone().requires_grad_(True) for k, v in d.items()}
+
+
+def rel_max(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / a.abs().max().clamp_min(1e-30)).item()
+
+
+def oracle_run(opt, batch, mode, photo, ssim_on, device="cpu", pose_grad=False):
+    inputs, flows, mobiles, cams, inst = batch
+    mv = lambda d: {k: v.to(device) for k, v in d.items()}
+    inputs, cams = mv(inputs), mv(cams)
+    if inst is not None:
+        inst = [{"instances": d["instances"].to(device)} for d in inst]
+    f, m = leaf(mv(flows)), leaf(mv(mobiles))
+    if pose_grad:
+        cams = leaf(cams)
+    H, W = inputs[("color", 0, 0)].shape[-2:]
+    scales = sorted({k[2] for k in flows})
+    weights = restate.gauss_distance_weight(4, H, W) if mode == "TG" else None
+    out, losses = restate.loss_forward(opt, inputs, [-1, 1], f, m, inst, scales, cams, mode=mode, weights=weights,
+                                       photometric=photo, ssim_on=ssim_on)
+    losses["loss"].backward()
+    return out, losses, f, m, cams
+
+
+def product_run(opt, batch, mode, photo, ssim_on, device, pose_grad=False, library=None):
+    from mdn_sfm_b200.loss_functions import Loss
+    inputs, flows, mobiles, cams, inst = batch
+    mv = lambda d: {k: v.to(device) for k, v in d.items()}
+    inputs, cams = mv(inputs), mv(cams)
+    if inst is not None:
+        inst = [{"instances": d["instances"].to(device)} for d in inst]
+    f, m = leaf(mv(flows)), leaf(mv(mobiles))
+    if pose_grad:
+        cams = leaf(cams)
+    scales = sorted({k[2] for k in flows})
+    loss = Loss(opt, no_ssim=not ssim_on, mode=mode, photometric=photo, library=library)
+    out, losses = loss(inputs, [-1, 1], f, m, inst, scales, cams)
+    losses["loss"].backward()
+    return out, losses, f, m, cams
+
+
+def compare(ref, got, photo, check_maps=True, fwd_tol=FWD_TOL, grad_tol=GRAD_TOL):
+    o_r, l_r, f_r, m_r, c_r = ref
+    o_g, l_g, f_g, m_g, c_g = got
+    for k in ("loss", "epip", "smooth", "consis") + (("photo",) if photo else ()):
+        a, b = float(l_r[k]), float(l_g[k])
+        assert abs(a - b) <= fwd_tol * max(abs(a), 1e-12), (k, a, b)
+    for k in f_r:
+        assert rel_max(f_r[k].grad, f_g[k].grad) <= grad_tol, ("d/dflow", k, rel_max(f_r[k].grad, f_g[k].grad))
+    for k in m_r:
+        assert rel_max(m_r[k].grad, m_g[k].grad) <= grad_tol, ("d/dmobile", k, rel_max(m_r[k].grad, m_g[k].grad))
+    for k in c_r:
+        if c_r[k].grad is not None:
+            assert rel_max(c_r[k].grad, c_g[k].grad) <= grad_tol, ("d/dpose", k, rel_max(c_r[k].grad, c_g[k].grad))
+    if check_maps:
+        names = ["epipolars", "epipolar_ori", "flows"] + (["warps", "diffs"] if photo else [])
+        for name in names:
+            assert set(o_r[name].keys()) == set(o_g[name].keys()), name
+            for key in o_r[name]:
+                assert o_r[name][key].shape == o_g[name][key].shape, (name, key)
+                assert rel_max(o_r[name][key], o_g[name][key]) <= fwd_tol, (name, key, rel_max(o_r[name][key], o_g[name][key]))
+        if photo:
+            for key in o_r["valids"]:
+                assert o_g["valids"][key].dtype == torch.bool
+                assert torch.equal(o_r["valids"][key].cpu(), o_g["valids"][key].cpu()), ("valids", key)
+        for s in o_r["min_mobiles"]:
+            assert torch.equal(o_r["min_mobiles"][s].cpu(), o_g["min_mobiles"][s].cpu())
+
+
+def make(B, H, W, scales=(0, 1, 2, 3), seed=11, flow_std=0.05, **opt_over):
+    opt = synthetic.default_opt(B, H, W, **opt_over)
+    batch = synthetic.make_batch(B, H, W, scales=scales, seed=seed, flow_std=flow_std)
+    return opt, batch

@@ -1,0 +1,67 @@
+"""The C-ABI library builds for sm_100a, loads without a GPU, and exports exactly what include/mdn_loss.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mdn_loss.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    from mdn_sfm_b200 import _cabi
+    assert declared_symbols() == sorted(_cabi.EXPORTS)
+
+
+def test_library_loads_and_exports_every_symbol():
+    from mdn_sfm_b200 import _cabi, build
+    path = build.build()
+    dll = ctypes.CDLL(path)
+    for name in declared_symbols():
+        assert hasattr(dll, name), name
+    lib = _cabi.Library(path)
+    assert lib.cdll.mdn_version() == 1
+
+
+def test_struct_layout_matches_header():
+    """sizeof(MdnLossDesc) computed by a C compiler equals the ctypes mirror."""
+    import subprocess
+    import tempfile
+    from mdn_sfm_b200 import _cabi
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "sz.c")
+        open(c, "w").write('#include <stdio.h>\n#include <stddef.h>\n#include "mdn_loss.h"\nint main(){printf("%zu %zu %zu %zu",'
+                           'sizeof(MdnScale),sizeof(MdnLossDesc),offsetof(MdnScale,g_flow),offsetof(MdnLossDesc,scale));return 0;}')
+        exe = os.path.join(d, "sz")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        a, b, c_, d_ = map(int, subprocess.check_output([exe]).split())
+    assert a == ctypes.sizeof(_cabi.MdnScale) and b == ctypes.sizeof(_cabi.MdnLossDesc)
+    assert c_ == _cabi.MdnScale.g_flow.offset and d_ == _cabi.MdnLossDesc.scale.offset
+
+
+def test_product_refuses_cpu_tensors():
+    import torch
+    from mdn_sfm_b200 import synthetic
+    from mdn_sfm_b200.loss_functions import Loss
+    opt = synthetic.default_opt(1, 16, 32)
+    inputs, flows, mobiles, cams, inst = synthetic.make_batch(1, 16, 32, scales=(0,))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        Loss(opt, mode="T")(inputs, [-1, 1], flows, mobiles, inst, [0], cams)
+
+
+def test_error_codes():
+    from mdn_sfm_b200 import _cabi, build
+    lib = _cabi.Library(build.build())
+    call = _cabi.FusedCall(batch=0, n_pairs=2, post=0, mask_mode=0, flags=1)
+    assert lib.cdll.mdn_loss_workspace_bytes(ctypes.byref(call.desc)) == 0
+    assert b"out of range" in lib.cdll.mdn_last_error_string()
+    with pytest.raises(RuntimeError, match="NULL"):
+        lib.call("mdn_ssim_fwd", None, None, None, 1, 4, 4, None)
+    with pytest.raises(RuntimeError, match="shape"):
+        lib.call("mdn_flow_warp_bwd", 16, 16, 16, 16, 1, 3, 1, 8, None)

@@ -1,0 +1,164 @@
+"""CPU-side execution of the UNMODIFIED kernel source under the SIMT emulator (tests/emu) vs the oracle.
+
+This is what catches tile / halo / reflection / adjoint bugs without a GPU.  It says nothing about speed and
+the product never takes this route (see tests/emu/cuda_emu.h).
+"""
+import pytest
+import torch
+
+import common
+from emu_harness import emulated
+from mdn_sfm_b200 import synthetic
+from oracle import restate
+
+
+@pytest.mark.parametrize("mode,photo,ssim_on,disable_min", common.CASES)
+def test_fused_loss_matches_oracle(mode, photo, ssim_on, disable_min):
+    opt, batch = common.make(2, 32, 64, disable_min=disable_min)
+    ref = common.oracle_run(opt, batch, mode, photo, ssim_on)
+    with emulated():
+        got = common.product_run(opt, batch, mode, photo, ssim_on, "cpu")
+        common.compare(ref, got, photo)
+
+
+def test_ragged_tiles_and_pose_gradient():
+    # 23x45: not a multiple of the 32x16 tile in either direction, odd sizes; single scale like config 5 (375x1242)
+    opt, batch = common.make(2, 23, 45, scales=(0,), seed=5, flow_std=0.08)
+    for mode in ("SN", "T"):
+        ref = common.oracle_run(opt, batch, mode, True, True, pose_grad=True)
+        with emulated():
+            got = common.product_run(opt, batch, mode, True, True, "cpu", pose_grad=True)
+            common.compare(ref, got, True)
+
+
+def test_large_flow_out_of_bounds_and_disabled_terms():
+    opt, batch = common.make(1, 32, 64, scales=(0, 1), seed=9, flow_std=0.6, disable_smoothloss=True,
+                             disable_consisloss=True)
+    ref = common.oracle_run(opt, batch, "T", True, True)
+    with emulated():
+        got = common.product_run(opt, batch, "T", True, True, "cpu")
+        common.compare(ref, got, True)
+    assert float(got[1]["loss"]) == pytest.approx(float(ref[1]["loss"]), rel=1e-5)
+    assert got[1]["smooth"] == 0 and got[1]["consis"] == 0
+
+
+def test_upstream_gradient_scaling():
+    opt, batch = common.make(1, 16, 32, scales=(0,), seed=3)
+    inputs, flows, mobiles, cams, inst = batch
+    from mdn_sfm_b200.loss_functions import Loss
+    with emulated():
+        f1, m1 = common.leaf(flows), common.leaf(mobiles)
+        _, l1 = Loss(opt, no_ssim=False, mode="T", photometric=True)(inputs, [-1, 1], f1, m1, inst, [0], cams)
+        l1["loss"].backward()
+        f2, m2 = common.leaf(flows), common.leaf(mobiles)
+        _, l2 = Loss(opt, no_ssim=False, mode="T", photometric=True)(inputs, [-1, 1], f2, m2, inst, [0], cams)
+        (l2["loss"] * 3.5).backward()
+    for k in f1:
+        assert torch.allclose(f1[k].grad * 3.5, f2[k].grad, rtol=1e-6, atol=0)
+    for k in m1:
+        assert torch.allclose(m1[k].grad * 3.5, m2[k].grad, rtol=1e-6, atol=0)
+
+
+def test_loss_module_methods():
+    opt, batch = common.make(2, 32, 64, seed=13)
+    inputs, flows, mobiles, cams, inst = batch
+    from mdn_sfm_b200.loss_functions import LossModule
+    from mdn_sfm_b200.layers import SSIM
+    pix = restate.create_coords(2, 32, 64)
+    f = (restate.get_scale_factor(2, 32, 64) * flows[("flow", 1, 0)]).contiguous()
+    m = mobiles[("mobile", 1, 0)]
+    R, t = cams[1][:, :3, :3], cams[1][:, :3, -1]
+    with emulated():
+        for mode in ("SN", "T", "TG", "DS", "DC"):
+            fo, mo = f.clone().requires_grad_(True), m.clone().requires_grad_(True)
+            weights = restate.gauss_distance_weight(4, 32, 64)
+            lo, po, eo = restate.epipolar_loss(fo, mo, inst, inputs[("inv_K", 0)], R, t, pix, mode=mode, alpha=opt.alpha,
+                                               w_d2_sim=opt.w_d2_sim, threshold=opt.threshold,
+                                               weight=weights[0] if mode == "TG" else None)
+            lo.backward()
+            fg, mg = f.clone().requires_grad_(True), m.clone().requires_grad_(True)
+            lm = LossModule(opt, batch=2, ssim=SSIM(), mode=mode)
+            lg, pg, eg = lm.epipolar_loss(fg, mg, inst, inputs[("inv_K", 0)], R, t)
+            lg.backward()
+            assert float(lg) == pytest.approx(float(lo), rel=1e-5), mode
+            assert pg.shape == po.shape and eg.shape == eo.shape
+            assert common.rel_max(po, pg) < 1e-5 and common.rel_max(eo, eg) < 1e-5, mode
+            assert common.rel_max(fo.grad, fg.grad) < 1e-4 and common.rel_max(mo.grad, mg.grad) < 1e-4, mode
+        # photometric
+        fo = f.clone().requires_grad_(True)
+        lo, wo, do, vo = restate.photo_metric_loss(inputs[("color", 0, 0)], inputs[("color", 1, 0)], fo, pix, True)
+        lo.backward()
+        fg = f.clone().requires_grad_(True)
+        lm = LossModule(opt, batch=2, ssim=SSIM())
+        lg, wg, dg, vg = lm.photo_metric_loss(inputs[("color", 0, 0)], inputs[("color", 1, 0)], fg)
+        lg.backward()
+        assert float(lg) == pytest.approx(float(lo), rel=1e-5)
+        assert common.rel_max(wo, wg) < 1e-5 and common.rel_max(do, dg) < 1e-5 and torch.equal(vo, vg)
+        assert common.rel_max(fo.grad, fg.grad) < 1e-4
+        # forward()/consistency accumulate like the reference
+        lm = LossModule(opt, batch=2, mode="DC")
+        lm.consistency_loss(mobiles[("mobile", -1, 1)], mobiles[("mobile", 1, 1)], 1)
+        lm(inputs, [-1, 1], flows, mobiles[("mobile", 1, 1)], inst, cams, 1)
+        olm = restate.LossModule(opt, mode="DC")
+        olm.consistency_loss(mobiles[("mobile", -1, 1)], mobiles[("mobile", 1, 1)], 1)
+        for i in (-1, 1):
+            olm.frame_terms(inputs, i, flows, mobiles[("mobile", 1, 1)], inst, cams, 1)
+        for k in ("consis", "epip", "smooth"):
+            assert float(lm.losses[k]) == pytest.approx(float(olm.losses[k]), rel=1e-5), k
+
+
+def test_free_functions():
+    from mdn_sfm_b200 import layers, loss_utils, utils
+    g = torch.Generator().manual_seed(21)
+    B, h, w = 2, 19, 37
+    ref = torch.rand(B, 3, h, w, generator=g)
+    x = torch.rand(B, 3, h, w, generator=g)
+    flow = torch.randn(B, 2, h, w, generator=g) * 6
+    pix = restate.create_coords(B, h, w)
+    with emulated():
+        # inverse_warp fwd + bwd, valid mask bit exact
+        fo = flow.clone().requires_grad_(True)
+        wo, vo = restate.inverse_warp(ref, fo, pix)
+        (wo * x).sum().backward()
+        fg = flow.clone().requires_grad_(True)
+        wg, vg = loss_utils.inverse_warp(ref, fg, pix, "zeros")
+        (wg * x).sum().backward()
+        assert common.rel_max(wo, wg) < 1e-5 and torch.equal(vo, vg)
+        assert common.rel_max(fo.grad, fg.grad) < 1e-4
+        # SSIM module fwd + bwd to both arguments
+        xo, yo = x.clone().requires_grad_(True), ref.clone().requires_grad_(True)
+        (restate.ssim(xo, yo) * flow[:, :1].abs()).sum().backward()
+        xg, yg = x.clone().requires_grad_(True), ref.clone().requires_grad_(True)
+        sg = layers.SSIM()(xg, yg)
+        (sg * flow[:, :1].abs()).sum().backward()
+        assert common.rel_max(restate.ssim(x, ref), sg) < 1e-5
+        assert common.rel_max(xo.grad, xg.grad) < 1e-4 and common.rel_max(yo.grad, yg.grad) < 1e-4
+        # get_epipolar_new on arbitrary point sets, with gradients to p2 and pose
+        p1 = torch.cat([pix, torch.ones(B, 1, h, w)], 1).view(B, 3, -1)
+        p2 = torch.cat([pix + flow, torch.ones(B, 1, h, w)], 1).view(B, 3, -1)
+        K = torch.tensor([[0.58 * w, 0, 0.5 * w], [0, 1.92 * h, 0.5 * h], [0, 0, 1]])
+        invK = torch.linalg.inv(K).unsqueeze(0).repeat(B, 1, 1)
+        M = synthetic.make_pose(torch.randn(B, 1, 1, 3, generator=g) * 0.02, torch.randn(B, 1, 1, 3, generator=g) * 0.1)
+        R, t = M[:, :3, :3].contiguous(), M[:, :3, 3].contiguous()
+        p2o, to = p2.clone().requires_grad_(True), t.clone().requires_grad_(True)
+        eo = restate.get_epipolar_new(p1, p2o, invK, R, to)
+        eo.abs().sum().backward()
+        p2g, tg = p2.clone().requires_grad_(True), t.clone().requires_grad_(True)
+        eg = loss_utils.get_epipolar_new(p1, p2g, invK, R, tg)
+        eg.abs().sum().backward()
+        assert eg.shape == eo.shape and common.rel_max(eo, eg) < 1e-5
+        assert common.rel_max(p2o.grad, p2g.grad) < 1e-4 and common.rel_max(to.grad, tg.grad) < 1e-4
+        # smooth_loss, binary_image, FlowWarp
+        m = torch.rand(B, 1, h, w, generator=g)
+        assert float(loss_utils.smooth_loss(x, m)) == pytest.approx(float(restate.smooth_loss(x, m)), rel=1e-5)
+        assert torch.equal(utils.binary_image(m, 0.4), restate.binary_image(m, 0.4))
+        a, b = utils.FlowWarp(B, h, w)(flow), restate.flow_warp_grid(flow)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    # pure host helpers
+    for wa, wb in zip(utils.gauss_distance_weight(4, 64, 96), restate.gauss_distance_weight(4, 64, 96)):
+        assert torch.equal(wa, wb)
+    aa, tt = torch.randn(3, 1, 1, 3, generator=g) * 0.3, torch.randn(3, 1, 1, 3, generator=g)
+    for inv in (False, True):
+        assert torch.equal(layers.transformation_from_parameters(aa, tt, inv), restate.transformation_from_parameters(aa, tt, inv))
+    assert torch.equal(layers.get_scale_factor(2, 5, 7).contiguous(), restate.get_scale_factor(2, 5, 7).contiguous())
+    assert torch.equal(loss_utils.create_coords(2, 5, 7), restate.create_coords(2, 5, 7))

@@ -1,0 +1,123 @@
+"""-m gpu: the CUDA path, called through the C ABI, against the oracle on identical seeded inputs.
+
+Comparators: the oracle run eagerly on the same GPU (the reference's own CUDA-eager arithmetic) and on the host CPU.
+"""
+import pytest
+import torch
+
+import common
+from mdn_sfm_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("mode,photo,ssim_on,disable_min", common.CASES)
+def test_fused_vs_oracle_small(mode, photo, ssim_on, disable_min):
+    opt, batch = common.make(2, 64, 96, disable_min=disable_min)
+    got = common.product_run(opt, batch, mode, photo, ssim_on, DEV)
+    common.compare(common.oracle_run(opt, batch, mode, photo, ssim_on, DEV), got, photo)
+    common.compare(common.oracle_run(opt, batch, mode, photo, ssim_on, "cpu"), got, photo)
+
+
+@pytest.mark.parametrize("mode", ["SN", "T", "TG", "DC"])
+def test_fused_vs_oracle_config1_shape(mode):
+    # BASELINE configs[0]: B=4, 3x192x640, 4 scales
+    opt, batch = common.make(4, 192, 640, seed=42, flow_std=0.01)
+    got = common.product_run(opt, batch, mode, True, True, DEV)
+    common.compare(common.oracle_run(opt, batch, mode, True, True, DEV), got, True)
+
+
+def test_fused_vs_oracle_headline_shape():
+    # BASELINE configs[1]: T mode + photometric, B=12, 192x640, 4 scales
+    opt, batch = common.make(12, 192, 640, seed=42, flow_std=0.05)
+    got = common.product_run(opt, batch, "T", True, True, DEV, pose_grad=True)
+    common.compare(common.oracle_run(opt, batch, "T", True, True, DEV, pose_grad=True), got, True)
+
+
+def test_fused_vs_oracle_full_res_kitti():
+    # BASELINE configs[4]: 375x1242, scale 0 only (ragged tiles)
+    opt, batch = common.make(2, 375, 1242, scales=(0,), seed=42, flow_std=0.02)
+    for mode in ("SN", "TG"):
+        got = common.product_run(opt, batch, mode, True, True, DEV)
+        common.compare(common.oracle_run(opt, batch, mode, True, True, DEV), got, True)
+
+
+def test_deterministic_and_repeatable():
+    opt, batch = common.make(3, 96, 160, seed=1)
+    a = common.product_run(opt, batch, "SN", True, True, DEV)
+    b = common.product_run(opt, batch, "SN", True, True, DEV)
+    assert torch.equal(a[1]["loss"], b[1]["loss"])
+    for k in a[2]:
+        assert torch.equal(a[2][k].grad, b[2][k].grad)
+    for k in a[3]:
+        assert torch.equal(a[3][k].grad, b[3][k].grad)
+
+
+def test_batch_linearity_property():
+    """Size-independent property: every term is a mean over the batch, so the loss of a batch made of the same
+    sample repeated equals the loss of that sample (T mode has no cross-pixel coupling) and gradients scale by 1/B."""
+    opt1, b1 = common.make(1, 192, 640, seed=8)
+    opt6 = synthetic.default_opt(6, 192, 640)
+    rep = lambda d: {k: v.repeat(6, *([1] * (v.dim() - 1))) for k, v in d.items()}
+    b6 = (rep(b1[0]), rep(b1[1]), rep(b1[2]), rep(b1[3]), None)
+    b1 = b1[:4] + (None,)
+    g1 = common.product_run(opt1, b1, "T", True, True, DEV)
+    g6 = common.product_run(opt6, b6, "T", True, True, DEV)
+    assert float(g6[1]["loss"]) == pytest.approx(float(g1[1]["loss"]), rel=1e-5)
+    for k in g1[2]:
+        assert common.rel_max(g1[2][k].grad / 6, g6[2][k].grad[2:3]) < 1e-5
+
+
+def test_zero_flow_valid_mask_and_identity_quirk():
+    """valid mask is all-true for zero flow and the warp is NOT the identity: both must match."""
+    from mdn_sfm_b200.loss_functions import LossModule
+    from mdn_sfm_b200.layers import SSIM
+    from oracle import restate
+    opt = synthetic.default_opt(2, 192, 640)
+    g = torch.Generator().manual_seed(0)
+    tgt = torch.rand(2, 3, 192, 640, generator=g).to(DEV)
+    flow = torch.zeros(2, 2, 192, 640, device=DEV)
+    lo, wo, do, vo = restate.photo_metric_loss(tgt, tgt, flow, restate.create_coords(2, 192, 640, DEV), True)
+    lg, wg, dg, vg = LossModule(opt, ssim=SSIM()).photo_metric_loss(tgt, tgt, flow)
+    assert torch.equal(vo, vg) and bool(vg.all())
+    assert common.rel_max(wo, wg) < 1e-6
+    assert float(lg) == pytest.approx(float(lo), rel=1e-5, abs=1e-9)
+
+
+def test_standalone_ops_on_gpu():
+    from mdn_sfm_b200 import layers, loss_utils, utils
+    from oracle import restate
+    g = torch.Generator().manual_seed(21)
+    B, h, w = 3, 75, 131
+    ref = torch.rand(B, 3, h, w, generator=g).to(DEV)
+    x = torch.rand(B, 3, h, w, generator=g).to(DEV)
+    flow = (torch.randn(B, 2, h, w, generator=g) * 9).to(DEV)
+    pix = restate.create_coords(B, h, w, DEV)
+    fo = flow.clone().requires_grad_(True)
+    wo, vo = restate.inverse_warp(ref, fo, pix)
+    (wo * x).sum().backward()
+    fg = flow.clone().requires_grad_(True)
+    wg, vg = loss_utils.inverse_warp(ref, fg, pix, "zeros")
+    (wg * x).sum().backward()
+    assert common.rel_max(wo, wg) < 1e-5 and torch.equal(vo, vg) and common.rel_max(fo.grad, fg.grad) < 1e-4
+    xo, yo = x.clone().requires_grad_(True), ref.clone().requires_grad_(True)
+    (restate.ssim(xo, yo) * flow[:, :1].abs()).sum().backward()
+    xg, yg = x.clone().requires_grad_(True), ref.clone().requires_grad_(True)
+    sg = layers.SSIM()(xg, yg)
+    (sg * flow[:, :1].abs()).sum().backward()
+    assert common.rel_max(restate.ssim(x, ref), sg) < 1e-5
+    assert common.rel_max(xo.grad, xg.grad) < 1e-4 and common.rel_max(yo.grad, yg.grad) < 1e-4
+    m = torch.rand(B, 1, h, w, generator=g).to(DEV)
+    assert float(loss_utils.smooth_loss(x, m)) == pytest.approx(float(restate.smooth_loss(x, m)), rel=1e-5)
+    assert torch.equal(utils.binary_image(m, 0.4), restate.binary_image(m, 0.4))
+    a, b = utils.FlowWarp(B, h, w)(flow), restate.flow_warp_grid(flow)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+
+
+def test_native_library_is_what_ran():
+    """Guards against a silent fallback: the in-tree .so must be mapped into this process."""
+    from mdn_sfm_b200 import _cabi
+    _cabi.lib()
+    maps = open("/proc/self/maps").read()
+    assert "libmdn_loss.so" in maps
