@@ -65,7 +65,12 @@ enum MdnFlags {
   MDN_OPT_SSIM        = 1 << 4,  /* photo = 0.15*L1 + 0.85*SSIM (else L1 only)  loss_functions.py:111-112    */
   MDN_OPT_INST_MASK   = 1 << 5,  /* DS: post *= instance mask         loss_utils.py:127-138                  */
   MDN_OPT_CROSS_ENT   = 1 << 6,  /* DC: + w_d2_sim * cross entropy    loss_utils.py:72-78, loss_functions.py:132-133 */
-  MDN_OPT_GRADS       = 1 << 7   /* also write d(loss)/d(flow, mob, fmat) for an upstream gradient of 1      */
+  MDN_OPT_GRADS       = 1 << 7,  /* also write d(loss)/d(flow, mob, fmat) for an upstream gradient of 1      */
+  MDN_OPT_CUDA_ARITH  = 1 << 8   /* replay the rounding of the reference's CUDA-EAGER path where it differs from its
+                                    CPU path: `tensor /= python_scalar` is a multiplication by the fp32-rounded
+                                    reciprocal on CUDA (ATen BinaryDivTrueKernel.cu) but a true division on the CPU.
+                                    Affects grid /= (w-1), (h-1) (loss_utils.py:29-30, utils.py:309-310) and
+                                    post /= threshold (loss_utils.py:86).  Without the flag: CPU rounding.          */
 };
 
 /* One pyramid level.  h = height, w = width of THIS level. */
@@ -100,11 +105,10 @@ typedef struct MdnLossDesc {
   int32_t post;        /* MdnPost     */
   int32_t mask_mode;   /* MdnMaskMode */
   int32_t flags;       /* MdnFlags    */
-  float threshold;     /* T / TG divisor (opt.threshold, options.py:84-87); <= 0 means "None" (no division)  */
+  double threshold;    /* T / TG divisor (opt.threshold, options.py:84-87); <= 0 means "None" (no division)  */
   float alpha;         /* weight of the non-trivial-solution term (opt.alpha)                                 */
   float w_d2_sim;      /* DC cross-entropy weight (opt.w_d2_sim)                                              */
   float w_e, w_s, w_c, w_p;  /* loss_functions.py:191-194                                                    */
-  float pad_;
   MdnScale scale[MDN_MAX_SCALES];
 } MdnLossDesc;
 
@@ -162,15 +166,16 @@ MDN_API size_t mdn_epipolar_points_workspace_bytes(int32_t batch, int64_t n);
 /*
  * inverse_warp (loss_utils.py:12-36) / FlowWarp (utils.py:289-315): bilinear flow warp, zeros padding,
  * align_corners=True.  flow is in pixels.  warped (B,C,h,w) may be NULL (FlowWarp: grid + validity only);
- * grid_out (B,h,w,2) normalised grid or NULL; valid (B,h,w) uint8 or NULL.  `flowwarp_norm` selects the
- * (g-0.5)*2 normalisation of utils.py:311 instead of 2*g-1 (loss_utils.py:31) -- same value, other rounding.
+ * grid_out (B,h,w,2) normalised grid or NULL; valid (B,h,w) uint8 or NULL.  `warp_flags` bit 0 selects the
+ * (g-0.5)*2 normalisation of utils.py:311 instead of 2*g-1 (loss_utils.py:31) -- same value, other rounding;
+ * bit 1 selects the CUDA-eager rounding of `/= (w-1)` (see MDN_OPT_CUDA_ARITH).
  * The backward takes g_warped (B,C,h,w) and writes g_flow (B,2,h,w).
  */
 MDN_API int mdn_flow_warp_fwd(const float* ref, const float* flow, float* warped, float* grid_out, uint8_t* valid,
-                      int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t flowwarp_norm,
+                      int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t warp_flags,
                       void* stream);
 MDN_API int mdn_flow_warp_bwd(const float* ref, const float* flow, const float* g_warped, float* g_flow, int32_t batch,
-                      int32_t channels, int32_t height, int32_t width, void* stream);
+                      int32_t channels, int32_t height, int32_t width, int32_t warp_flags, void* stream);
 
 /*
  * SSIM module (networks/layers.py:148-178): out = clamp((1 - SSIM(x,y))/2, 0, 1), 3x3 reflect-padded.

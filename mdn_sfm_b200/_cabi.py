@@ -13,7 +13,8 @@ MAX_SCALES, MAX_PAIRS = 4, 2
 POST_SN, POST_T, POST_TG = 0, 1, 2
 MASK_MIN, MASK_OWN, MASK_SHARED = 0, 1, 2
 TERM_EPIPOLAR, TERM_PHOTO, TERM_SMOOTH, TERM_CONSIS = 1, 2, 4, 8
-OPT_SSIM, OPT_INST_MASK, OPT_CROSS_ENT, OPT_GRADS = 16, 32, 64, 128
+OPT_SSIM, OPT_INST_MASK, OPT_CROSS_ENT, OPT_GRADS, OPT_CUDA_ARITH = 16, 32, 64, 128, 256
+WARP_FLOWWARP_NORM, WARP_CUDA_ARITH = 1, 2
 OUT_LOSS, OUT_EPIP, OUT_SMOOTH, OUT_CONSIS, OUT_PHOTO, OUT_APPLIED, OUT_COUNT = 0, 1, 2, 3, 4, 5, 8
 
 _P = C.c_void_p
@@ -32,9 +33,9 @@ class MdnScale(C.Structure):
 
 class MdnLossDesc(C.Structure):
     _fields_ = [("batch", C.c_int32), ("n_scales", C.c_int32), ("n_pairs", C.c_int32), ("post", C.c_int32),
-                ("mask_mode", C.c_int32), ("flags", C.c_int32), ("threshold", C.c_float), ("alpha", C.c_float),
+                ("mask_mode", C.c_int32), ("flags", C.c_int32), ("threshold", C.c_double), ("alpha", C.c_float),
                 ("w_d2_sim", C.c_float), ("w_e", C.c_float), ("w_s", C.c_float), ("w_c", C.c_float),
-                ("w_p", C.c_float), ("pad_", C.c_float), ("scale", MdnScale * MAX_SCALES)]
+                ("w_p", C.c_float), ("scale", MdnScale * MAX_SCALES)]
 
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmdn_loss.so")
@@ -65,7 +66,7 @@ class Library:
             "mdn_epipolar_points_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, i32, i64, _P, sz, _P]),
             "mdn_epipolar_points_workspace_bytes": (sz, [i32, i64]),
             "mdn_flow_warp_fwd": (C.c_int, [_P, _P, _P, _P, _P, i32, i32, i32, i32, i32, _P]),
-            "mdn_flow_warp_bwd": (C.c_int, [_P, _P, _P, _P, i32, i32, i32, i32, _P]),
+            "mdn_flow_warp_bwd": (C.c_int, [_P, _P, _P, _P, i32, i32, i32, i32, i32, _P]),
             "mdn_ssim_fwd": (C.c_int, [_P, _P, _P, i32, i32, i32, _P]),
             "mdn_ssim_bwd": (C.c_int, [_P, _P, _P, _P, _P, i32, i32, i32, _P]),
             "mdn_binary_image": (C.c_int, [_P, _P, i64, f32, _P]),

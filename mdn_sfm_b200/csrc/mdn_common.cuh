@@ -53,10 +53,21 @@ struct WarpCoord {
   bool valid;      // max(|gx|,|gy|) <= 1
 };
 
-MDN_DEV WarpCoord warp_coord(float x, float y, float fx, float fy, float wm1, float hm1, bool flowwarp_norm = false) {
+struct WarpGeom {
+  float wm1, hm1;          // w-1, h-1
+  float inv_wm1, inv_hm1;  // (float)(1.0 / (double)(w-1)): what ATen's CUDA `tensor /= scalar` multiplies by
+  bool cuda_arith;         // MDN_OPT_CUDA_ARITH
+  bool flowwarp_norm;      // utils.py:311 normalisation
+};
+
+MDN_DEV WarpCoord warp_coord(float x, float y, float fx, float fy, const WarpGeom& G) {
   WarpCoord c;
+  const float wm1 = G.wm1, hm1 = G.hm1;
+  const bool flowwarp_norm = G.flowwarp_norm;
   float px = __fadd_rn(x, fx), py = __fadd_rn(y, fy);
-  float gx = __fdiv_rn(px, wm1), gy = __fdiv_rn(py, hm1);
+  float gx, gy;
+  if (G.cuda_arith) { gx = __fmul_rn(px, G.inv_wm1); gy = __fmul_rn(py, G.inv_hm1); }
+  else { gx = __fdiv_rn(px, wm1); gy = __fdiv_rn(py, hm1); }
   if (flowwarp_norm) {  // utils.py:311  (g - 0.5) * 2
     gx = __fmul_rn(__fsub_rn(gx, 0.5f), 2.f);
     gy = __fmul_rn(__fsub_rn(gy, 0.5f), 2.f);

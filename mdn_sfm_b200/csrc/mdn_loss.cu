@@ -37,7 +37,7 @@ struct KScale {
   int h, w, tiles_x, tiles_y;
   int tile_begin;          // first tile index of this scale
   float sx, sy;            // flow -> pixels
-  float wm1, hm1;
+  WarpGeom geom;
   float c_epi, c_nt, c_ce, c_l1, c_ssim, c_smx, c_smy, c_consis;   // gradient coefficients (upstream 1)
   const float* tgt; const float* ref[2]; const float* flow[2]; const float* mob[2]; const float* fmat[2];
   const float* weight; const uint8_t* inst;
@@ -48,7 +48,7 @@ struct KScale {
 struct KParams {
   int batch, n_scales, n_pairs, post, mask_mode, flags;
   int n_tiles;
-  float threshold;
+  float threshold, inv_threshold;
   float* partials;                   // [n_tiles][NSLOT]
   const unsigned long long* snkey;   // [n_scales][n_pairs][batch] packed (bits(max)<<32 | ~argmax)
   KScale sc[MDN_MAX_SCALES];
@@ -62,7 +62,10 @@ MDN_DEV float post_process(const KParams& P, const KScale& S, float e, float snm
     return __fmul_rn(q, q);                   // :99
   }
   float r = e, dr = 1.f;
-  if (P.threshold > 0.f) { r = __fdiv_rn(r, P.threshold); dr = dr / P.threshold; }   // loss_utils.py:85-86
+  if (P.threshold > 0.f) {                                                             // loss_utils.py:85-86
+    r = (P.flags & MDN_OPT_CUDA_ARITH) ? __fmul_rn(r, P.inv_threshold) : __fdiv_rn(r, P.threshold);
+    dr = dr * P.inv_threshold;
+  }
   if (P.post == MDN_POST_TG) { float wgt = __ldg(S.weight + pix); r = __fdiv_rn(r, wgt); dr = dr / wgt; }   // :87-88
   dpost_de = 2.f * r * dr;
   return __fmul_rn(r, r);                     // :89
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(NTHREADS) fused_tile_kernel(const __grid_const
         if (in) {
           long long o = (long long)y * w + x;
           float fx = __fmul_rn(S.sx, __ldg(flx + o)), fy = __fmul_rn(S.sy, __ldg(fly + o));
-          WarpCoord wc = warp_coord((float)x, (float)y, fx, fy, S.wm1, S.hm1);
+          WarpCoord wc = warp_coord((float)x, (float)y, fx, fy, S.geom);
           Bilin bl = bilinear_setup(wc.ix, wc.iy, h, w);
           int ly = ry - 2, lx = rx - 2;
           bool interior = (ly >= 0) & (ly < TH) & (lx >= 0) & (lx < TW);
@@ -689,14 +692,13 @@ __global__ void epipolar_points_bwd_finish_kernel(const float* __restrict__ part
 
 __global__ void __launch_bounds__(NTHREADS) flow_warp_fwd_kernel(const float* __restrict__ ref, const float* __restrict__ flow,
                                                                  float* __restrict__ warped, float* __restrict__ grid_out,
-                                                                 uint8_t* __restrict__ valid, int C, int h, int w, int fw_norm) {
+                                                                 uint8_t* __restrict__ valid, int C, int h, int w, const WarpGeom G) {
   const int b = blockIdx.y;
   const int hw = h * w;
-  const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
     int y = i / w, x = i - y * w;
     float fx = flow[(long long)b * 2 * hw + i], fy = flow[(long long)b * 2 * hw + hw + i];
-    WarpCoord wc = warp_coord((float)x, (float)y, fx, fy, wm1, hm1, fw_norm != 0);
+    WarpCoord wc = warp_coord((float)x, (float)y, fx, fy, G);
     if (grid_out) { grid_out[((long long)b * hw + i) * 2] = wc.gx; grid_out[((long long)b * hw + i) * 2 + 1] = wc.gy; }
     if (valid) valid[(long long)b * hw + i] = wc.valid ? 1 : 0;
     if (warped) {
@@ -712,14 +714,14 @@ __global__ void __launch_bounds__(NTHREADS) flow_warp_fwd_kernel(const float* __
 
 __global__ void __launch_bounds__(NTHREADS) flow_warp_bwd_kernel(const float* __restrict__ ref, const float* __restrict__ flow,
                                                                  const float* __restrict__ g_warped, float* __restrict__ g_flow,
-                                                                 int C, int h, int w) {
+                                                                 int C, int h, int w, const WarpGeom G) {
   const int b = blockIdx.y;
   const int hw = h * w;
-  const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
+  const float wm1 = G.wm1, hm1 = G.hm1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
     int y = i / w, x = i - y * w;
     float fx = flow[(long long)b * 2 * hw + i], fy = flow[(long long)b * 2 * hw + hw + i];
-    WarpCoord wc = warp_coord((float)x, (float)y, fx, fy, wm1, hm1);
+    WarpCoord wc = warp_coord((float)x, (float)y, fx, fy, G);
     Bilin bl = bilinear_setup(wc.ix, wc.iy, h, w);
     float gix = 0.f, giy = 0.f;
     for (int c = 0; c < C; ++c) {
@@ -730,8 +732,9 @@ __global__ void __launch_bounds__(NTHREADS) flow_warp_bwd_kernel(const float* __
       gix += g * ddx; giy += g * ddy;
     }
     // grid_sample: * (size-1)/2 ; "2*g-1": * 2 ; "/= (size-1)": / (size-1)
-    g_flow[(long long)b * 2 * hw + i] = __fdiv_rn(__fmul_rn(__fmul_rn(gix, __fmul_rn(wm1, 0.5f)), 2.f), wm1);
-    g_flow[(long long)b * 2 * hw + hw + i] = __fdiv_rn(__fmul_rn(__fmul_rn(giy, __fmul_rn(hm1, 0.5f)), 2.f), hm1);
+    float tx = __fmul_rn(__fmul_rn(gix, __fmul_rn(wm1, 0.5f)), 2.f), ty = __fmul_rn(__fmul_rn(giy, __fmul_rn(hm1, 0.5f)), 2.f);
+    g_flow[(long long)b * 2 * hw + i] = G.cuda_arith ? __fmul_rn(tx, G.inv_wm1) : __fdiv_rn(tx, wm1);
+    g_flow[(long long)b * 2 * hw + hw + i] = G.cuda_arith ? __fmul_rn(ty, G.inv_hm1) : __fdiv_rn(ty, hm1);
   }
 }
 
@@ -862,6 +865,14 @@ static int check_desc(const MdnLossDesc* d) {
   return MDN_OK;
 }
 
+static WarpGeom make_geom(int h, int w, bool cuda_arith, bool flowwarp_norm) {
+  WarpGeom G;
+  G.wm1 = (float)(w - 1); G.hm1 = (float)(h - 1);
+  G.inv_wm1 = (float)(1.0 / (double)(w - 1)); G.inv_hm1 = (float)(1.0 / (double)(h - 1));
+  G.cuda_arith = cuda_arith; G.flowwarp_norm = flowwarp_norm;
+  return G;
+}
+
 static WsLayout ws_layout(const MdnLossDesc* d, int n_tiles) {
   WsLayout L;
   size_t off = 0;
@@ -895,7 +906,8 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
   if (!aligned16(workspace)) return fail(MDN_ERR_MISALIGNED, "%s is not 16-byte aligned", "workspace");
   char* ws = (char*)workspace;
   K.batch = d->batch; K.n_scales = d->n_scales; K.n_pairs = d->n_pairs; K.post = d->post; K.mask_mode = d->mask_mode;
-  K.flags = d->flags; K.threshold = d->threshold;
+  K.flags = d->flags; K.threshold = (float)d->threshold;
+  K.inv_threshold = d->threshold > 0 ? (float)(1.0 / d->threshold) : 0.f;
   K.partials = (float*)(ws + L.partials);
   unsigned long long* keys = (unsigned long long*)(ws + L.snkeys);
   K.snkey = keys;
@@ -908,7 +920,8 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
   for (int s = 0; s < d->n_scales; ++s) {
     const MdnScale& S = d->scale[s];
     KScale& Z = K.sc[s];
-    Z.sx = S.flow_sx; Z.sy = S.flow_sy; Z.wm1 = (float)(Z.w - 1); Z.hm1 = (float)(Z.h - 1);
+    Z.sx = S.flow_sx; Z.sy = S.flow_sy;
+    Z.geom = make_geom(Z.h, Z.w, (d->flags & MDN_OPT_CUDA_ARITH) != 0, false);
     const double div = S.scale_div > 0.f ? (double)S.scale_div : 1.0;
     Q.scale_div[s] = (float)div;
     const double N = (double)d->batch * Z.h * Z.w;
@@ -1009,21 +1022,21 @@ extern "C" MDN_API int mdn_epipolar_points_bwd(const float* p1, const float* p2,
 }
 
 extern "C" MDN_API int mdn_flow_warp_fwd(const float* ref, const float* flow, float* warped, float* grid_out, uint8_t* valid,
-                                 int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t flowwarp_norm, void* stream) {
+                                 int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t warp_flags, void* stream) {
   if (!flow || (warped && !ref)) return fail(MDN_ERR_NULL_POINTER, "flow / ref is NULL");
   if (batch < 1 || channels < 0 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad warp shape (h,w >= 2)");
   MDN_LAUNCH(flow_warp_fwd_kernel, dim3(blocks_for((long long)height * width), batch), dim3(NTHREADS), 0, (cudaStream_t)stream, ref, flow, warped,
-             grid_out, valid, (int)channels, (int)height, (int)width, (int)flowwarp_norm);
+             grid_out, valid, (int)channels, (int)height, (int)width, make_geom(height, width, (warp_flags & 2) != 0, (warp_flags & 1) != 0));
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }
 
 extern "C" MDN_API int mdn_flow_warp_bwd(const float* ref, const float* flow, const float* g_warped, float* g_flow, int32_t batch,
-                                 int32_t channels, int32_t height, int32_t width, void* stream) {
+                                 int32_t channels, int32_t height, int32_t width, int32_t warp_flags, void* stream) {
   if (!ref || !flow || !g_warped || !g_flow) return fail(MDN_ERR_NULL_POINTER, "ref / flow / g_warped / g_flow is NULL");
   if (batch < 1 || channels < 1 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad warp shape (h,w >= 2)");
   MDN_LAUNCH(flow_warp_bwd_kernel, dim3(blocks_for((long long)height * width), batch), dim3(NTHREADS), 0, (cudaStream_t)stream, ref, flow, g_warped,
-             g_flow, (int)channels, (int)height, (int)width);
+             g_flow, (int)channels, (int)height, (int)width, make_geom(height, width, (warp_flags & 2) != 0, false));
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }

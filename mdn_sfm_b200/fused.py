@@ -12,7 +12,7 @@ from typing import List, Optional
 import torch
 
 from . import _cabi
-from ._cabi import (MASK_MIN, MASK_OWN, MASK_SHARED, OPT_CROSS_ENT, OPT_GRADS, OPT_INST_MASK, OPT_SSIM, OUT_APPLIED,
+from ._cabi import (MASK_MIN, MASK_OWN, MASK_SHARED, OPT_CROSS_ENT, OPT_CUDA_ARITH, OPT_GRADS, OPT_INST_MASK, OPT_SSIM, OUT_APPLIED,
                     OUT_COUNT, POST_SN, POST_T, POST_TG, TERM_CONSIS, TERM_EPIPOLAR, TERM_PHOTO, TERM_SMOOTH)
 
 POST_OF_MODE = {"SN": POST_SN, "T": POST_T, "TG": POST_TG}
@@ -62,6 +62,7 @@ class FusedConfig:
     w_s: float = 1.0
     w_c: float = 1.0
     w_p: float = 1.0
+    cuda_arith: bool = True   # replay the reference's CUDA-eager rounding (MDN_OPT_CUDA_ARITH); False = its CPU rounding
     want_maps: tuple = ()   # subset of ("post_map", "ori_map", "warped", "diff", "valid", "ssim_map"), scale 0 only
 
 
@@ -86,7 +87,7 @@ def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None
     library = library or _cabi.lib()
     dev = None
     any_grad = any(any(v) for ng in need_grad for v in ng.values())
-    flags = cfg.flags | (OPT_GRADS if any_grad else 0)
+    flags = cfg.flags | (OPT_GRADS if any_grad else 0) | (OPT_CUDA_ARITH if cfg.cuda_arith else 0)
     call = _cabi.FusedCall(batch=cfg.batch, n_pairs=cfg.n_pairs, post=cfg.post, mask_mode=cfg.mask_mode, flags=flags,
                            threshold=cfg.threshold, alpha=cfg.alpha, w_d2_sim=cfg.w_d2_sim, w_e=cfg.w_e, w_s=cfg.w_s,
                            w_c=cfg.w_c, w_p=cfg.w_p)

@@ -15,6 +15,9 @@ Same constructor / method signatures, same returned structures and the same numb
   differentiable, nobody differentiates them).  The per-pixel ``outputs`` maps are computed lazily on first
   access (they are read every 50 batches for TensorBoard, trainer.py:248-250), and are not differentiable.
 * ``padding_mode`` other than "zeros" is rejected (the reference only ever passes "zeros").
+* ``arith="cuda"`` (default) replays the rounding of the reference's CUDA-eager path, ``arith="cpu"`` that of its
+  CPU path; they differ where ATen divides a tensor by a Python scalar (a reciprocal multiply on CUDA), which
+  moves warp coordinates by an ulp and can flip a bilinear cell (MDN_OPT_CUDA_ARITH in include/mdn_loss.h).
 """
 from __future__ import annotations
 
@@ -29,7 +32,7 @@ from ._cabi import (MASK_MIN, MASK_OWN, MASK_SHARED, OPT_CROSS_ENT, OPT_INST_MAS
 from .layers import SSIM, get_scale_factor  # noqa: F401  (re-exported like the reference module does)
 from .loss_utils import *  # noqa: F401,F403  (the reference does `from loss_utils import *`)
 from .loss_utils import create_coords as _create_coords
-from .loss_utils import instance_mask_u8
+from .loss_utils import _arith_flag, instance_mask_u8
 from .utils import gauss_distance_weight
 
 MODES = ("SN", "T", "TG", "DS", "DC")
@@ -75,7 +78,7 @@ class LossModule(nn.Module):
     """loss_functions.py:11-157."""
 
     def __init__(self, opt, batch=None, ssim=None, padding_mode="zeros", cuda=True, *, mode=None, weights=None,
-                 ds_base="SN", library=None):
+                 ds_base="SN", library=None, arith="cuda"):
         super().__init__()
         if padding_mode != "zeros":
             raise NotImplementedError("mdn_sfm_b200: only padding_mode='zeros' is implemented")
@@ -90,6 +93,7 @@ class LossModule(nn.Module):
         self.ds_base = ds_base
         self.weights = weights
         self._library = library
+        self._cuda_arith = _arith_flag(arith)
         self.losses = {"consis": 0, "epip": 0, "smooth": 0}
         self.outputs = {"warps": {}, "diffs": {}, "valids": {}, "epipolars": {}, "flows": {}, "epipolar_ori": {}}
         self._pix_shape = (batch if batch is not None else opt.batch_size, opt.height, opt.width)
@@ -148,13 +152,13 @@ class LossModule(nn.Module):
         thr = getattr(o, "threshold", None) if post != fused.POST_SN else None
         # two launches so that losses["epip"] and losses["smooth"] each own their gradient (the reference
         # keeps them as separate differentiable accumulators); Loss.forward uses a single launch instead
-        cfg = fused.FusedConfig(batch=b, n_pairs=len(frame_ids), post=post, mask_mode=mask_mode, flags=bits,
+        cfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=len(frame_ids), post=post, mask_mode=mask_mode, flags=bits,
                                 threshold=thr, alpha=o.alpha, w_d2_sim=o.w_d2_sim,
                                 want_maps=("post_map", "ori_map") if scale == 0 else ())
         epip, _, maps = fused.fused_loss(cfg, [S], self._library)
         self.losses["epip"] = self.losses["epip"] + epip
         if not o.disable_smoothloss:
-            scfg = fused.FusedConfig(batch=b, n_pairs=len(frame_ids), post=post, mask_mode=mask_mode, flags=TERM_SMOOTH)
+            scfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=len(frame_ids), post=post, mask_mode=mask_mode, flags=TERM_SMOOTH)
             smooth, _, _ = fused.fused_loss(scfg, [S], self._library)
             self.losses["smooth"] = self.losses["smooth"] + smooth
         if scale == 0:
@@ -180,7 +184,7 @@ class LossModule(nn.Module):
         b, _, h, w = flow_map.size()
         S = fused.ScaleData(h, w, 1.0, 1.0, 1.0, tgt=target)
         S.ref[0], S.flow[0] = reference, flow_map
-        cfg = fused.FusedConfig(batch=b, n_pairs=1, post=fused.POST_T, mask_mode=MASK_SHARED,
+        cfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=1, post=fused.POST_T, mask_mode=MASK_SHARED,
                                 flags=TERM_PHOTO | (OPT_SSIM if self.ssim is not None else 0),
                                 want_maps=("warped", "diff", "valid"))
         total, _, maps = fused.fused_loss(cfg, [S], self._library)
@@ -197,7 +201,7 @@ class LossModule(nn.Module):
         S.fmat[0] = fused.fundamental_matrix(inv_K[:, :3, :3], ro, tran).contiguous()
         S.weight, S.inst = self._epi_extras(post, bits, h, w, flow_map.device, instances_info)
         o = self.options
-        cfg = fused.FusedConfig(batch=b, n_pairs=1, post=post, mask_mode=MASK_SHARED, flags=bits,
+        cfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=1, post=post, mask_mode=MASK_SHARED, flags=bits,
                                 threshold=getattr(o, "threshold", None) if post != fused.POST_SN else None,
                                 alpha=self.alpha, w_d2_sim=o.w_d2_sim, want_maps=("post_map", "ori_map"))
         total, _, maps = fused.fused_loss(cfg, [S], self._library)
@@ -209,7 +213,7 @@ class LossModule(nn.Module):
         b, _, h, w = m1.size()
         S = fused.ScaleData(h, w, 1.0, 1.0, float(2 ** scale))
         S.mob[0], S.mob[1] = m1, m2
-        cfg = fused.FusedConfig(batch=b, n_pairs=1, post=fused.POST_T, mask_mode=MASK_OWN, flags=TERM_CONSIS)
+        cfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=1, post=fused.POST_T, mask_mode=MASK_OWN, flags=TERM_CONSIS)
         total, _, _ = fused.fused_loss(cfg, [S], self._library)
         self.losses["consis"] = self.losses["consis"] + total
 
@@ -218,7 +222,7 @@ class Loss(nn.Module):
     """loss_functions.py:160-205."""
 
     def __init__(self, opt, no_ssim=True, padding_mode="zeros", alpha=1, *, mode=None, photometric=None, weights=None,
-                 ds_base="SN", library=None):
+                 ds_base="SN", library=None, arith="cuda"):
         super().__init__()
         if padding_mode != "zeros":
             raise NotImplementedError("mdn_sfm_b200: only padding_mode='zeros' is implemented")
@@ -231,12 +235,14 @@ class Loss(nn.Module):
         self.ds_base = ds_base
         self.weights = weights
         self._library = library
+        self._arith = arith
+        self._cuda_arith = _arith_flag(arith)
         self._helper = None
 
     def _lm(self):
         if self._helper is None:
             self._helper = LossModule(self.opt, ssim=self.ssim, mode=self.mode, weights=self.weights,
-                                      ds_base=self.ds_base, library=self._library)
+                                      ds_base=self.ds_base, library=self._library, arith=self._arith)
         return self._helper
 
     def _scale_data(self, inputs, frame_id, flow, mobile, instances_info, scales, cam_T_cam, post, bits):
@@ -281,7 +287,7 @@ class Loss(nn.Module):
             flags |= TERM_PHOTO | (OPT_SSIM if self.ssim is not None else 0)
         data = self._scale_data(inputs, ids, flow, mobile, instances_info, scales, cam_T_cam, post, bits)
         b = data[0].tgt.shape[0]
-        cfg = fused.FusedConfig(batch=b, n_pairs=len(ids), post=post, mask_mode=MASK_OWN if o.disable_min else MASK_MIN,
+        cfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=len(ids), post=post, mask_mode=MASK_OWN if o.disable_min else MASK_MIN,
                                 flags=flags, threshold=getattr(o, "threshold", None) if post != fused.POST_SN else None,
                                 alpha=o.alpha, w_d2_sim=o.w_d2_sim, w_e=o.w_e, w_s=o.w_s, w_c=o.w_c,
                                 w_p=getattr(o, "w_p", 1.0) if self.photometric else 0.0)
@@ -305,7 +311,7 @@ class Loss(nn.Module):
                                     fmat=[None if f is None else f.detach() for f in S0.fmat],
                                     weight=S0.weight, inst=S0.inst)
                 want = ("post_map", "ori_map") + (("warped", "diff", "valid") if self.photometric else ())
-                mcfg = fused.FusedConfig(batch=b, n_pairs=len(ids), post=post, mask_mode=cfg.mask_mode,
+                mcfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=len(ids), post=post, mask_mode=cfg.mask_mode,
                                          flags=flags & ~(TERM_SMOOTH | TERM_CONSIS), threshold=cfg.threshold,
                                          alpha=o.alpha, w_d2_sim=o.w_d2_sim, want_maps=want)
                 _, _, maps = fused.fused_loss(mcfg, [S], self._library)

@@ -17,16 +17,23 @@ __all__ = ["inverse_warp", "get_epipolar_new", "detectron2_similarity_loss", "po
            "smooth_loss", "derivable_consistency_loss", "compute_quantiles"]
 
 
-def inverse_warp(ref_img, flow_map, pix_coords, padding_mode, library=None):
+def _arith_flag(arith):
+    if arith not in ("cuda", "cpu"):
+        raise ValueError("arith must be 'cuda' (the reference's CUDA-eager rounding) or 'cpu'")
+    return arith == "cuda"
+
+
+def inverse_warp(ref_img, flow_map, pix_coords, padding_mode, library=None, arith="cuda"):
     """loss_utils.py:12-36 -> (warped (B,3,H,W), valid_points bool (B,3,H,W)).
 
     `pix_coords` is accepted for signature compatibility; the kernel derives the grid from the thread index
-    (it must be the regular pixel grid, which is what every caller passes).
+    (it must be the regular pixel grid, which is what every caller passes).  `arith` picks which of the
+    reference's two roundings of `grid /= (w-1)` is replayed: its CUDA-eager one (default) or its CPU one.
     """
     if padding_mode != "zeros":
         raise NotImplementedError("mdn_sfm_b200: only padding_mode='zeros' is implemented")
     ref_img, flow_map = _c(ref_img, "ref_img"), _c(flow_map, "flow_map")
-    warped, _, valid = FlowWarpFn.apply(ref_img, flow_map, False, True, library)
+    warped, _, valid = FlowWarpFn.apply(ref_img, flow_map, _cabi.WARP_CUDA_ARITH if _arith_flag(arith) else 0, True, library)
     return warped, valid.bool().unsqueeze(1).expand(-1, ref_img.shape[1], -1, -1)
 
 

@@ -14,7 +14,7 @@ class FlowWarpFn(torch.autograd.Function):
     """inverse_warp's sampling (loss_utils.py:27-34): flow in pixels -> (warped, grid, valid)."""
 
     @staticmethod
-    def forward(ctx, ref, flow, flowwarp_norm, want_warp, library):
+    def forward(ctx, ref, flow, warp_flags, want_warp, library):
         library = library or _cabi.lib()
         B, _, h, w = flow.shape
         C = ref.shape[1] if want_warp else 0
@@ -22,8 +22,8 @@ class FlowWarpFn(torch.autograd.Function):
         grid = torch.empty((B, h, w, 2), dtype=torch.float32, device=flow.device)
         valid = torch.empty((B, h, w), dtype=torch.uint8, device=flow.device)
         library.call("mdn_flow_warp_fwd", _cabi.ptr(ref) if want_warp else None, flow.data_ptr(), _cabi.ptr(warped),
-                     grid.data_ptr(), valid.data_ptr(), B, C, h, w, 1 if flowwarp_norm else 0, _cabi.stream_ptr(flow))
-        ctx.library = library
+                     grid.data_ptr(), valid.data_ptr(), B, C, h, w, int(warp_flags), _cabi.stream_ptr(flow))
+        ctx.library, ctx.warp_flags = library, int(warp_flags)
         ctx.save_for_backward(ref, flow)
         ctx.mark_non_differentiable(grid, valid)
         if not want_warp:
@@ -40,7 +40,7 @@ class FlowWarpFn(torch.autograd.Function):
         B, C, h, w = ref.shape
         g_flow = torch.empty_like(flow)
         ctx.library.call("mdn_flow_warp_bwd", ref.data_ptr(), flow.data_ptr(), g_warped.contiguous().data_ptr(),
-                         g_flow.data_ptr(), B, C, h, w, _cabi.stream_ptr(flow))
+                         g_flow.data_ptr(), B, C, h, w, ctx.warp_flags, _cabi.stream_ptr(flow))
         return None, g_flow, None, None, None
 
 

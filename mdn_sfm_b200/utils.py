@@ -21,15 +21,16 @@ def binary_image(x, threshold=0.5, library=None):
 class FlowWarp(nn.Module):
     """utils.py:289-315: forward(flow) -> (pix_coords, pix_coords_norm, valid_points), no sampling."""
 
-    def __init__(self, batch_size, height, width, library=None):
+    def __init__(self, batch_size, height, width, library=None, arith="cuda"):
         super().__init__()
         self.batch_size, self.height, self.width = batch_size, height, width
         self._library = library
+        self._flags = _cabi.WARP_FLOWWARP_NORM | (_cabi.WARP_CUDA_ARITH if arith == "cuda" else 0)
 
     def forward(self, flow):
         flow = _c(flow, "flow")
         B, _, h, w = flow.shape
-        _, grid, valid = FlowWarpFn.apply(flow, flow, True, False, self._library)
+        _, grid, valid = FlowWarpFn.apply(flow, flow, self._flags, False, self._library)
         xs = torch.arange(w, dtype=torch.float32, device=flow.device).view(1, 1, 1, w)
         ys = torch.arange(h, dtype=torch.float32, device=flow.device).view(1, 1, h, 1)
         pix = torch.cat([xs + flow[:, 0:1], ys + flow[:, 1:2]], 1)

@@ -50,7 +50,8 @@ def oracle_run(opt, batch, mode, photo, ssim_on, device="cpu", pose_grad=False):
     return out, losses, f, m, cams
 
 
-def product_run(opt, batch, mode, photo, ssim_on, device, pose_grad=False, library=None):
+def product_run(opt, batch, mode, photo, ssim_on, device, pose_grad=False, library=None, arith=None):
+    arith = arith or ("cuda" if str(device).startswith("cuda") else "cpu")
     from mdn_sfm_b200.loss_functions import Loss
     inputs, flows, mobiles, cams, inst = batch
     mv = lambda d: {k: v.to(device) for k, v in d.items()}
@@ -61,7 +62,7 @@ def product_run(opt, batch, mode, photo, ssim_on, device, pose_grad=False, libra
     if pose_grad:
         cams = leaf(cams)
     scales = sorted({k[2] for k in flows})
-    loss = Loss(opt, no_ssim=not ssim_on, mode=mode, photometric=photo, library=library)
+    loss = Loss(opt, no_ssim=not ssim_on, mode=mode, photometric=photo, library=library, arith=arith)
     out, losses = loss(inputs, [-1, 1], f, m, inst, scales, cams)
     losses["loss"].backward()
     return out, losses, f, m, cams

@@ -64,4 +64,4 @@ def test_error_codes():
     with pytest.raises(RuntimeError, match="NULL"):
         lib.call("mdn_ssim_fwd", None, None, None, 1, 4, 4, None)
     with pytest.raises(RuntimeError, match="shape"):
-        lib.call("mdn_flow_warp_bwd", 16, 16, 16, 16, 1, 3, 1, 8, None)
+        lib.call("mdn_flow_warp_bwd", 16, 16, 16, 16, 1, 3, 1, 8, 0, None)

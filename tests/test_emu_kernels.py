@@ -48,10 +48,10 @@ def test_upstream_gradient_scaling():
     from mdn_sfm_b200.loss_functions import Loss
     with emulated():
         f1, m1 = common.leaf(flows), common.leaf(mobiles)
-        _, l1 = Loss(opt, no_ssim=False, mode="T", photometric=True)(inputs, [-1, 1], f1, m1, inst, [0], cams)
+        _, l1 = Loss(opt, no_ssim=False, mode="T", photometric=True, arith="cpu")(inputs, [-1, 1], f1, m1, inst, [0], cams)
         l1["loss"].backward()
         f2, m2 = common.leaf(flows), common.leaf(mobiles)
-        _, l2 = Loss(opt, no_ssim=False, mode="T", photometric=True)(inputs, [-1, 1], f2, m2, inst, [0], cams)
+        _, l2 = Loss(opt, no_ssim=False, mode="T", photometric=True, arith="cpu")(inputs, [-1, 1], f2, m2, inst, [0], cams)
         (l2["loss"] * 3.5).backward()
     for k in f1:
         assert torch.allclose(f1[k].grad * 3.5, f2[k].grad, rtol=1e-6, atol=0)
@@ -77,7 +77,7 @@ def test_loss_module_methods():
                                                weight=weights[0] if mode == "TG" else None)
             lo.backward()
             fg, mg = f.clone().requires_grad_(True), m.clone().requires_grad_(True)
-            lm = LossModule(opt, batch=2, ssim=SSIM(), mode=mode)
+            lm = LossModule(opt, batch=2, ssim=SSIM(), mode=mode, arith="cpu")
             lg, pg, eg = lm.epipolar_loss(fg, mg, inst, inputs[("inv_K", 0)], R, t)
             lg.backward()
             assert float(lg) == pytest.approx(float(lo), rel=1e-5), mode
@@ -89,14 +89,14 @@ def test_loss_module_methods():
         lo, wo, do, vo = restate.photo_metric_loss(inputs[("color", 0, 0)], inputs[("color", 1, 0)], fo, pix, True)
         lo.backward()
         fg = f.clone().requires_grad_(True)
-        lm = LossModule(opt, batch=2, ssim=SSIM())
+        lm = LossModule(opt, batch=2, ssim=SSIM(), arith="cpu")
         lg, wg, dg, vg = lm.photo_metric_loss(inputs[("color", 0, 0)], inputs[("color", 1, 0)], fg)
         lg.backward()
         assert float(lg) == pytest.approx(float(lo), rel=1e-5)
         assert common.rel_max(wo, wg) < 1e-5 and common.rel_max(do, dg) < 1e-5 and torch.equal(vo, vg)
         assert common.rel_max(fo.grad, fg.grad) < 1e-4
         # forward()/consistency accumulate like the reference
-        lm = LossModule(opt, batch=2, mode="DC")
+        lm = LossModule(opt, batch=2, mode="DC", arith="cpu")
         lm.consistency_loss(mobiles[("mobile", -1, 1)], mobiles[("mobile", 1, 1)], 1)
         lm(inputs, [-1, 1], flows, mobiles[("mobile", 1, 1)], inst, cams, 1)
         olm = restate.LossModule(opt, mode="DC")
@@ -121,7 +121,7 @@ def test_free_functions():
         wo, vo = restate.inverse_warp(ref, fo, pix)
         (wo * x).sum().backward()
         fg = flow.clone().requires_grad_(True)
-        wg, vg = loss_utils.inverse_warp(ref, fg, pix, "zeros")
+        wg, vg = loss_utils.inverse_warp(ref, fg, pix, "zeros", arith="cpu")
         (wg * x).sum().backward()
         assert common.rel_max(wo, wg) < 1e-5 and torch.equal(vo, vg)
         assert common.rel_max(fo.grad, fg.grad) < 1e-4
@@ -152,7 +152,7 @@ def test_free_functions():
         m = torch.rand(B, 1, h, w, generator=g)
         assert float(loss_utils.smooth_loss(x, m)) == pytest.approx(float(restate.smooth_loss(x, m)), rel=1e-5)
         assert torch.equal(utils.binary_image(m, 0.4), restate.binary_image(m, 0.4))
-        a, b = utils.FlowWarp(B, h, w)(flow), restate.flow_warp_grid(flow)
+        a, b = utils.FlowWarp(B, h, w, arith="cpu")(flow), restate.flow_warp_grid(flow)
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
     # pure host helpers
     for wa, wb in zip(utils.gauss_distance_weight(4, 64, 96), restate.gauss_distance_weight(4, 64, 96)):

@@ -15,8 +15,11 @@ DEV = "cuda"
 @pytest.mark.parametrize("mode,photo,ssim_on,disable_min", common.CASES)
 def test_fused_vs_oracle_small(mode, photo, ssim_on, disable_min):
     opt, batch = common.make(2, 64, 96, disable_min=disable_min)
-    got = common.product_run(opt, batch, mode, photo, ssim_on, DEV)
+    # against the reference arithmetic run eagerly on this GPU ...
+    got = common.product_run(opt, batch, mode, photo, ssim_on, DEV, arith="cuda")
     common.compare(common.oracle_run(opt, batch, mode, photo, ssim_on, DEV), got, photo)
+    # ... and against the same code on the host CPU (whose `tensor /= scalar` rounds differently: arith="cpu")
+    got = common.product_run(opt, batch, mode, photo, ssim_on, DEV, arith="cpu")
     common.compare(common.oracle_run(opt, batch, mode, photo, ssim_on, "cpu"), got, photo)
 
 
