@@ -133,23 +133,31 @@ struct SsimOut {
   float dmu_x, dX2;        // same for x (used by the standalone SSIM backward)
 };
 
+// s / 9 correctly rounded without the IEEE-division subroutine: one Newton step on q = s * rn(1/9) (Markstein)
+MDN_DEV float div9(float s) {
+  const float r9 = 0.111111111f;
+  float q = __fmul_rn(s, r9);
+  return __fmaf_rn(__fmaf_rn(-9.f, q, s), r9, q);
+}
+
 MDN_DEV SsimOut ssim_window(float sx, float sy, float sxx, float syy, float sxy, bool want_grad) {
   const float C1 = 0.0001f, C2 = 0.0009f;
-  float mu_x = __fdiv_rn(sx, 9.f), mu_y = __fdiv_rn(sy, 9.f);
-  float sig_x = __fsub_rn(__fdiv_rn(sxx, 9.f), __fmul_rn(mu_x, mu_x));
-  float sig_y = __fsub_rn(__fdiv_rn(syy, 9.f), __fmul_rn(mu_y, mu_y));
-  float sig_xy = __fsub_rn(__fdiv_rn(sxy, 9.f), __fmul_rn(mu_x, mu_y));
+  // avg_pool2d divides the window sum by 9; sigma = E[x^2] - mu^2 cancels, so these quotients are kept exact
+  float mu_x = div9(sx), mu_y = div9(sy);
+  float sig_x = __fsub_rn(div9(sxx), __fmul_rn(mu_x, mu_x));
+  float sig_y = __fsub_rn(div9(syy), __fmul_rn(mu_y, mu_y));
+  float sig_xy = __fsub_rn(div9(sxy), __fmul_rn(mu_x, mu_y));
   float n1 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, mu_x), mu_y), C1);
   float n2 = __fadd_rn(__fmul_rn(2.f, sig_xy), C2);
   float d1 = __fadd_rn(__fadd_rn(__fmul_rn(mu_x, mu_x), __fmul_rn(mu_y, mu_y)), C1);
   float d2 = __fadd_rn(__fadd_rn(sig_x, sig_y), C2);
   float n = __fmul_rn(n1, n2), D = __fmul_rn(d1, d2);
-  float z = __fmul_rn(__fsub_rn(1.f, __fdiv_rn(n, D)), 0.5f);
+  float invD = __fdividef(1.f, D);        // D >= C1*C2 > 0; 2-ulp reciprocal is far inside the 1e-5 budget
+  float z = __fmul_rn(__fsub_rn(1.f, n * invD), 0.5f);
   SsimOut o;
   o.J = fminf(fmaxf(z, 0.f), 1.f);
   o.dmu_y = o.dY2 = o.dXY = o.dmu_x = o.dX2 = 0.f;
   if (want_grad && z >= 0.f && z <= 1.f) {   // clamp backward gate is inclusive
-    float invD = 1.f / D;
     float nbar = -0.5f * invD;            // dz/dn
     float Dbar = 0.5f * n * invD * invD;  // dz/dD
     float dn1 = nbar * n2, dn2 = nbar * n1, dd1 = Dbar * d2, dd2 = Dbar * d1;

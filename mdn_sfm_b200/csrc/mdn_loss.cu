@@ -110,367 +110,7 @@ __global__ void __launch_bounds__(NTHREADS) sn_max_kernel(const KParams P, unsig
   if ((threadIdx.x & 31) == 0 && best) atomicMax(keys + job, best);
 }
 
-// ----------------------------------------------------------------------------------------------- fused tile kernel
-struct Smem {
-  float* T;      // [3][R2N] target image
-  float* W;      // [3][R2N] warped source image (current pair)
-  float* M;      // [2][R1N] mask used by pair 0 / 1 (MIN, SHARED: only [0])
-  float* ABC;    // [9][R1N] SSIM adjoint terms per window: (A,B,C) x 3 channels (current pair)
-  float* D;      // [6][TN]  d(warped_c)/d(ix), d(warped_c)/d(iy) at interior pixels (current pair)
-  float* Mbar;   // [2][TN]  accumulated d(loss)/d(mask slot)
-  float* red;    // [nwarps][NSLOT]
-  uint8_t* V;    // [TN] validity of the current pair at interior pixels
-};
-
-__host__ __device__ inline size_t fused_smem_floats(bool photo, int nwarps) {
-  size_t n = 3 * R2N + 2 * R1N + 2 * TN + (size_t)nwarps * NSLOT + TN / 4;
-  if (photo) n += 3 * R2N + 9 * R1N + 6 * TN;
-  return n;
-}
-
-template <int NV>
-MDN_DEV void flush_acc(float* v, float* red, int slot_base) {
-  warp_reduce_transpose<NV>(v);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane < NV) red[warp * NSLOT + slot_base + lane] = v[0];
-}
-
-__global__ void __launch_bounds__(NTHREADS) fused_tile_kernel(const __grid_constant__ KParams P) {
-  MDN_DYN_SMEM(smem_raw);
-  const int tid = threadIdx.x, nthr = blockDim.x, nwarps = nthr >> 5;
-  const bool photo = (P.flags & MDN_TERM_PHOTO) != 0;
-  const bool use_ssim = photo && (P.flags & MDN_OPT_SSIM);
-  const bool epi_on = (P.flags & MDN_TERM_EPIPOLAR) != 0;
-  const bool smooth_on = (P.flags & MDN_TERM_SMOOTH) != 0;
-  const bool consis_on = (P.flags & MDN_TERM_CONSIS) != 0;
-  const bool grads = (P.flags & MDN_OPT_GRADS) != 0;
-  const bool own = P.mask_mode == MDN_MASK_OWN;
-  const bool need_tgt = photo || smooth_on;
-
-  Smem sm;
-  {
-    float* p = smem_raw;
-    sm.T = p; p += 3 * R2N;
-    sm.M = p; p += 2 * R1N;
-    sm.Mbar = p; p += 2 * TN;
-    sm.red = p; p += nwarps * NSLOT;
-    sm.V = reinterpret_cast<uint8_t*>(p); p += TN / 4;
-    sm.W = p; sm.ABC = p; sm.D = p;
-    if (photo) { sm.W = p; p += 3 * R2N; sm.ABC = p; p += 9 * R1N; sm.D = p; p += 6 * TN; }
-  }
-
-  // ---- which tile
-  int s = 0;
-#pragma unroll
-  for (int k = 1; k < MDN_MAX_SCALES; ++k)
-    if (k < P.n_scales && (int)blockIdx.x >= P.sc[k].tile_begin) s = k;
-  const KScale& S = P.sc[s];
-  int r = blockIdx.x - S.tile_begin;
-  const int tiles_per_img = S.tiles_x * S.tiles_y;
-  const int b = r / tiles_per_img;
-  r -= b * tiles_per_img;
-  const int ty = r / S.tiles_x, tx = r - ty * S.tiles_x;
-  const int x0 = tx * TW, y0 = ty * TH;
-  const int h = S.h, w = S.w, hw = h * w;
-
-  for (int i = tid; i < nwarps * NSLOT; i += nthr) sm.red[i] = 0.f;
-
-  // ---- P0: stage target image (halo 2) and the mask(s) (halo 1)
-  if (need_tgt) {
-    const float* tg = S.tgt + (long long)b * 3 * hw;
-    for (int i = tid; i < R2N; i += nthr) {
-      int ry = i / R2W, rx = i - ry * R2W;
-      int y = y0 - 2 + ry, x = x0 - 2 + rx;
-      bool in = (y >= 0) & (y < h) & (x >= 0) & (x < w);
-      long long o = (long long)y * w + x;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) sm.T[c * R2N + i] = in ? __ldg(tg + (long long)c * hw + o) : 0.f;
-    }
-  }
-  const bool need_mask = epi_on || smooth_on || consis_on;
-  if (need_mask) {
-    const float* m0 = S.mob[0] + (long long)b * hw;
-    const float* m1 = (P.mask_mode == MDN_MASK_SHARED) ? m0 : S.mob[1] + (long long)b * hw;
-    for (int i = tid; i < R1N; i += nthr) {
-      int ry = i / R1W, rx = i - ry * R1W;
-      int y = y0 - 1 + ry, x = x0 - 1 + rx;
-      bool in = (y >= 0) & (y < h) & (x >= 0) & (x < w);
-      float a0 = 0.f, a1 = 0.f;
-      if (in) { a0 = __ldg(m0 + (long long)y * w + x); a1 = (P.mask_mode == MDN_MASK_SHARED) ? a0 : __ldg(m1 + (long long)y * w + x); }
-      if (own) { sm.M[i] = a0; sm.M[R1N + i] = a1; }
-      else { sm.M[i] = (a0 <= a1) ? a0 : a1; sm.M[R1N + i] = 0.f; }   // torch.min(dim): first index on ties
-    }
-  }
-  for (int i = tid; i < 2 * TN; i += nthr) sm.Mbar[i] = 0.f;
-  __syncthreads();
-
-  // ---- per (target, source) pair
-  for (int pair = 0; pair < P.n_pairs; ++pair) {
-    float acc[PAIR_SLOTS];
-#pragma unroll
-    for (int k = 0; k < PAIR_SLOTS; ++k) acc[k] = 0.f;
-    const float* flx = S.flow[pair] + (long long)b * 2 * hw;
-    const float* fly = flx + hw;
-    const float* Mp = sm.M + (own ? pair : 0) * R1N;
-    float* Mbar = sm.Mbar + (own ? pair : 0) * TN;
-
-    if (photo) {
-      // -- P1: warp the source image over the halo-2 region
-      const float* rf = S.ref[pair] + (long long)b * 3 * hw;
-      for (int i = tid; i < R2N; i += nthr) {
-        int ry = i / R2W, rx = i - ry * R2W;
-        int y = y0 - 2 + ry, x = x0 - 2 + rx;
-        bool in = (y >= 0) & (y < h) & (x >= 0) & (x < w);
-        float wv[3] = {0.f, 0.f, 0.f};
-        if (in) {
-          long long o = (long long)y * w + x;
-          float fx = __fmul_rn(S.sx, __ldg(flx + o)), fy = __fmul_rn(S.sy, __ldg(fly + o));
-          WarpCoord wc = warp_coord((float)x, (float)y, fx, fy, S.geom);
-          Bilin bl = bilinear_setup(wc.ix, wc.iy, h, w);
-          int ly = ry - 2, lx = rx - 2;
-          bool interior = (ly >= 0) & (ly < TH) & (lx >= 0) & (lx < TW);
-          int li = ly * TW + lx;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float nw, ne, sw, se;
-            bilinear_fetch(rf + (long long)c * hw, w, bl, nw, ne, sw, se);
-            wv[c] = bilinear_value(bl, nw, ne, sw, se);
-            if (interior) {
-              if (grads) { float ddx, ddy; bilinear_deriv(bl, nw, ne, sw, se, ddx, ddy); sm.D[c * TN + li] = ddx; sm.D[(3 + c) * TN + li] = ddy; }
-              float df = fabsf(sm.T[c * R2N + i] - wv[c]);
-              df = wc.valid ? df : 0.f;
-              acc[SL_L1] += df;
-              if (S.warped[pair]) S.warped[pair][((long long)b * 3 + c) * hw + o] = wv[c];
-              if (S.diff[pair]) S.diff[pair][((long long)b * 3 + c) * hw + o] = df;
-            }
-          }
-          if (interior) {
-            sm.V[li] = wc.valid ? 1 : 0;
-            if (S.valid[pair]) S.valid[pair][(long long)b * hw + o] = wc.valid ? 1 : 0;
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sm.W[c * R2N + i] = wv[c];
-      }
-      __syncthreads();
-
-      // -- P2: SSIM per window over the halo-1 region
-      if (use_ssim) {
-        for (int i = tid; i < R1N; i += nthr) {
-          int ry = i / R1W, rx = i - ry * R1W;
-          int py = y0 - 1 + ry, px = x0 - 1 + rx;
-          bool in = (py >= 0) & (py < h) & (px >= 0) & (px < w);
-          bool interior = (ry >= 1) & (ry <= TH) & (rx >= 1) & (rx <= TW);
-          if (in) {
-            int ro[3], co[3];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              ro[d] = (reflect1(py + d - 1, h) - (y0 - 2)) * R2W;
-              co[d] = reflect1(px + d - 1, w) - (x0 - 2);
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
-#pragma unroll
-              for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                  float xv = sm.T[c * R2N + ro[dy] + co[dx]], yv = sm.W[c * R2N + ro[dy] + co[dx]];
-                  sx += xv; sy += yv; sxx += xv * xv; syy += yv * yv; sxy += xv * yv;
-                }
-              SsimOut so = ssim_window(sx, sy, sxx, syy, sxy, grads);
-              if (interior) {
-                acc[SL_SSIM] += so.J;
-                if (S.ssim_map[pair]) S.ssim_map[pair][((long long)b * 3 + c) * hw + (long long)py * w + px] = so.J;
-              }
-              const float k9 = S.c_ssim * (1.f / 9.f);
-              sm.ABC[(3 * c + 0) * R1N + i] = k9 * so.dmu_y;
-              sm.ABC[(3 * c + 1) * R1N + i] = k9 * 2.f * so.dY2;
-              sm.ABC[(3 * c + 2) * R1N + i] = k9 * so.dXY;
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) sm.ABC[k * R1N + i] = 0.f;
-          }
-        }
-        __syncthreads();
-      }
-    }
-
-    // -- P3: interior pixels: photometric adjoint -> d/dflow, epipolar forward + adjoint
-    {
-      float Fm[9];
-      if (epi_on) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Fm[k] = __ldg(S.fmat[pair] + b * 9 + k);
-      }
-      float snmax = 1.f;
-      if (epi_on && P.post == MDN_POST_SN) {
-        unsigned long long key = P.snkey[(s * P.n_pairs + pair) * P.batch + b];
-        snmax = __uint_as_float((unsigned)(key >> 32));
-      }
-      for (int li = tid; li < TN; li += nthr) {
-        int ly = li / TW, lx = li - ly * TW;
-        int y = y0 + ly, x = x0 + lx;
-        if (y >= h || x >= w) continue;
-        long long o = (long long)y * w + x;
-        int i1 = (ly + 1) * R1W + lx + 1, i2 = (ly + 2) * R2W + lx + 2;
-        float gfx = 0.f, gfy = 0.f;
-        if (photo && grads) {
-          float gix = 0.f, giy = 0.f;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float wb = 0.f;
-            float tv = sm.T[c * R2N + i2], wv = sm.W[c * R2N + i2];
-            if (use_ssim) {
-              float sa = 0.f, sb = 0.f, sc = 0.f;
-#pragma unroll
-              for (int dy = -1; dy <= 1; ++dy) {
-                int py = y + dy;
-                if (py < 0 || py >= h) continue;
-                int my = refl_mult(py, y, h);
-#pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                  int px = x + dx;
-                  if (px < 0 || px >= w) continue;
-                  float mlt = (float)(my * refl_mult(px, x, w));
-                  int j = i1 + dy * R1W + dx;
-                  sa += mlt * sm.ABC[(3 * c + 0) * R1N + j];
-                  sb += mlt * sm.ABC[(3 * c + 1) * R1N + j];
-                  sc += mlt * sm.ABC[(3 * c + 2) * R1N + j];
-                }
-              }
-              wb = sa + wv * sb + tv * sc;
-            }
-            if (sm.V[li]) wb -= S.c_l1 * signf_(tv - wv);
-            gix += wb * sm.D[c * TN + li];
-            giy += wb * sm.D[(3 + c) * TN + li];
-          }
-          gfx = gix * S.sx; gfy = giy * S.sy;   // (w-1)/2 * 2 / (w-1) * sx  (grid_sample, 2g-1, /(w-1), scale factor)
-        }
-        if (epi_on) {
-          float m = Mp[i1];
-          float phx = __ldg(flx + o), phy = __ldg(fly + o);
-          float u = __fadd_rn((float)x, __fmul_rn(S.sx, phx));
-          float v = __fadd_rn((float)y, __fmul_rn(S.sy, phy));
-          Epi e = epipolar_distance(Fm, (float)x, (float)y, u, v);
-          float ae = fabsf(e.d);
-          float dpost;
-          float post = post_process(P, S, ae, snmax, (int)o, dpost);
-          float kmask = 1.f;
-          if ((P.flags & (MDN_OPT_INST_MASK | MDN_OPT_CROSS_ENT)) != 0) kmask = (float)__ldg(S.inst + (long long)b * hw + o);
-          if (P.flags & MDN_OPT_INST_MASK) { post *= kmask; dpost *= kmask; }
-          float bg = 1.f - m;
-          float lg = logf(bg + 1e-5f);
-          float ml = m * lg;
-          acc[SL_EPI] += bg * post;
-          acc[SL_NT] += fabsf(ml);
-          float mb = 0.f;
-          if (P.flags & MDN_OPT_CROSS_ENT) {
-            float l1 = logf(m + 1e-10f), l0 = logf(bg + 1e-10f);
-            acc[SL_CE] += -(kmask * l1 + (1.f - kmask) * l0);
-            mb += S.c_ce * (-kmask / (m + 1e-10f) + (1.f - kmask) / (bg + 1e-10f));
-          }
-          if (S.post_map[pair]) S.post_map[pair][(long long)b * hw + o] = post;
-          if (S.ori_map[pair]) S.ori_map[pair][(long long)b * hw + o] = (P.post == MDN_POST_SN) ? __fdiv_rn(ae, snmax) : ae;
-          if (grads) {
-            mb += -S.c_epi * post + S.c_nt * signf_(ml) * (lg - m / (bg + 1e-5f));
-            Mbar[li] += mb;
-            float ebar = S.c_epi * bg * dpost;
-            float dbar = signf_(e.d) * ebar;
-            float inv_den = 1.f / e.den;
-            float g2 = dbar * inv_den;
-            float das = e.d / e.s;
-            gfx += g2 * e.a * S.sx;
-            gfy += g2 * e.b * S.sy;
-            float g0 = g2 * (u - das * e.a), g1 = g2 * (v - das * e.b);
-            float xf = (float)x, yf = (float)y;
-            acc[SL_GF + 0] += g0 * xf; acc[SL_GF + 1] += g0 * yf; acc[SL_GF + 2] += g0;
-            acc[SL_GF + 3] += g1 * xf; acc[SL_GF + 4] += g1 * yf; acc[SL_GF + 5] += g1;
-            acc[SL_GF + 6] += g2 * xf; acc[SL_GF + 7] += g2 * yf; acc[SL_GF + 8] += g2;
-          }
-        }
-        if (grads && S.g_flow[pair]) {
-          S.g_flow[pair][(long long)b * 2 * hw + o] = gfx;
-          S.g_flow[pair][(long long)b * 2 * hw + hw + o] = gfy;
-        }
-      }
-    }
-    flush_acc<PAIR_SLOTS>(acc, sm.red, pair * PAIR_SLOTS);
-    __syncthreads();   // W / ABC / D / V are reused by the next pair
-  }
-
-  // ---- P4: smoothness + consistency, then route d/dmask to the mobile maps
-  if (need_mask) {
-    float acc[TAIL_SLOTS];
-#pragma unroll
-    for (int k = 0; k < TAIL_SLOTS; ++k) acc[k] = 0.f;
-    const int n_masks = own ? P.n_pairs : 1;
-    // in MIN / SHARED mode the reference evaluates smooth_loss once per source frame with the SAME mask
-    const float rep = own ? 1.f : (float)P.n_pairs;
-    const float* m0g = S.mob[0] + (long long)b * hw;
-    const float* m1g = (P.mask_mode == MDN_MASK_SHARED) ? m0g : S.mob[1] + (long long)b * hw;
-    for (int li = tid; li < TN; li += nthr) {
-      int ly = li / TW, lx = li - ly * TW;
-      int y = y0 + ly, x = x0 + lx;
-      if (y >= h || x >= w) continue;
-      long long o = (long long)y * w + x;
-      int i1 = (ly + 1) * R1W + lx + 1, i2 = (ly + 2) * R2W + lx + 2;
-      float mbar[2] = {sm.Mbar[li], sm.Mbar[TN + li]};
-      if (smooth_on) {
-        // exp(-mean_c |I(x) - I(x+1)|) for the pairs (x-1,x), (x,x+1), (y-1,y), (y,y+1)
-        float ex_r = 0.f, ex_l = 0.f, ey_d = 0.f, ey_u = 0.f;
-        {
-          float gr = 0.f, gl = 0.f, gd = 0.f, gu = 0.f;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float t0 = sm.T[c * R2N + i2];
-            gr += fabsf(t0 - sm.T[c * R2N + i2 + 1]);
-            gl += fabsf(sm.T[c * R2N + i2 - 1] - t0);
-            gd += fabsf(t0 - sm.T[c * R2N + i2 + R2W]);
-            gu += fabsf(sm.T[c * R2N + i2 - R2W] - t0);
-          }
-          const float third = 1.f / 3.f;
-          if (x + 1 < w) ex_r = expf(-gr * third);
-          if (x > 0) ex_l = expf(-gl * third);
-          if (y + 1 < h) ey_d = expf(-gd * third);
-          if (y > 0) ey_u = expf(-gu * third);
-        }
-        for (int k = 0; k < n_masks; ++k) {
-          const float* Mk = sm.M + k * R1N;
-          float mc = Mk[i1];
-          float dr = mc - Mk[i1 + 1], dl = Mk[i1 - 1] - mc, dd = mc - Mk[i1 + R1W], du = Mk[i1 - R1W] - mc;
-          acc[SL_SMX + 2 * k] += fabsf(dr) * ex_r;   // ex_r == 0 at the last column
-          acc[SL_SMY + 2 * k] += fabsf(dd) * ey_d;
-          mbar[k] += rep * (S.c_smx * (signf_(dr) * ex_r - signf_(dl) * ex_l) + S.c_smy * (signf_(dd) * ey_d - signf_(du) * ey_u));
-        }
-      }
-      float a0 = __ldg(m0g + o), a1 = __ldg(m1g + o);
-      float g0, g1;
-      if (own) { g0 = mbar[0]; g1 = mbar[1]; }
-      else if (P.mask_mode == MDN_MASK_SHARED) { g0 = mbar[0]; g1 = 0.f; }
-      else { bool first = a0 <= a1; g0 = first ? mbar[0] : 0.f; g1 = first ? 0.f : mbar[0]; }
-      if (consis_on) {
-        float p = sigmoidf_(20.f * (a0 - 0.5f)), q = sigmoidf_(20.f * (a1 - 0.5f));
-        float df = p - q;
-        acc[SL_CONSIS] += df * df;
-        g0 += S.c_consis * 2.f * df * 20.f * p * (1.f - p);
-        g1 -= S.c_consis * 2.f * df * 20.f * q * (1.f - q);
-      }
-      if (grads) {
-        if (S.g_mob[0]) S.g_mob[0][(long long)b * hw + o] = g0;
-        if (S.g_mob[1] && P.mask_mode != MDN_MASK_SHARED) S.g_mob[1][(long long)b * hw + o] = g1;
-      }
-    }
-    flush_acc<TAIL_SLOTS>(acc, sm.red, TAIL_BASE);
-  }
-  __syncthreads();
-  for (int k = tid; k < NSLOT; k += nthr) {
-    float t = 0.f;
-    for (int wq = 0; wq < nwarps; ++wq) t += sm.red[wq * NSLOT + k];
-    P.partials[(long long)blockIdx.x * NSLOT + k] = t;
-  }
-}
+#include "mdn_fused.cuh"
 
 // ----------------------------------------------------------------------------------------------- finish
 struct FParams {
@@ -551,15 +191,20 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  __shared__ double tots[MDN_MAX_SCALES][NSLOT];
+  if (threadIdx.x < (unsigned)(P.n_scales * NSLOT)) {
+    const int ss = threadIdx.x / NSLOT, k = threadIdx.x % NSLOT;
+    double t2 = 0;
+    for (int bb = 0; bb < P.batch; ++bb) t2 += (double)Q.sample_sums[((long long)ss * P.batch + bb) * NSLOT + k];
+    tots[ss][k] = t2;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     double epip = 0, smooth = 0, consis = 0, photo = 0;
     const bool own = P.mask_mode == MDN_MASK_OWN;
     for (int ss = 0; ss < P.n_scales; ++ss) {
       const KScale& Z = P.sc[ss];
-      double tot[NSLOT];
-      for (int k = 0; k < NSLOT; ++k) tot[k] = 0;
-      for (int bb = 0; bb < P.batch; ++bb)
-        for (int k = 0; k < NSLOT; ++k) tot[k] += (double)Q.sample_sums[((long long)ss * P.batch + bb) * NSLOT + k];
+      const double* tot = tots[ss];
       const double N = (double)P.batch * Z.h * Z.w, div = Q.scale_div[ss];
       const double cx = (double)P.batch * Z.h * (Z.w - 1), cy = (double)P.batch * (Z.h - 1) * Z.w;
       for (int p = 0; p < P.n_pairs; ++p) {
@@ -951,15 +596,9 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
   }
   const bool photo = (d->flags & MDN_TERM_PHOTO) != 0;
   const size_t smem = fused_smem_floats(photo, NTHREADS / 32) * sizeof(float);
-#ifndef MDN_EMU
-  static bool attr_set = false;   // idempotent; a benign race sets it twice
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(fused_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fused_smem_floats(true, NTHREADS / 32) * sizeof(float))) != cudaSuccess)
-      return fail(MDN_ERR_CUDA, "cudaFuncSetAttribute failed");
-    attr_set = true;
-  }
-#endif
-  MDN_LAUNCH(fused_tile_kernel, dim3(K.n_tiles), dim3(NTHREADS), smem, stream, K);
+  static_assert(fused_smem_floats(true, NTHREADS / 32) * sizeof(float) <= 48 * 1024, "fits the default dynamic smem limit");
+  if (photo) MDN_LAUNCH(fused_tile_kernel<true>, dim3(K.n_tiles), dim3(NTHREADS), smem, stream, K);
+  else MDN_LAUNCH(fused_tile_kernel<false>, dim3(K.n_tiles), dim3(NTHREADS), smem, stream, K);
   MDN_LAUNCH(finish_kernel, dim3(d->n_scales * d->batch), dim3(FIN_ROWS * NSLOT), 0, stream, Q);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));

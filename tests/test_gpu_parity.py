@@ -85,7 +85,7 @@ def test_zero_flow_valid_mask_and_identity_quirk():
     lg, wg, dg, vg = LossModule(opt, ssim=SSIM()).photo_metric_loss(tgt, tgt, flow)
     assert torch.equal(vo, vg) and bool(vg.all())
     assert common.rel_max(wo, wg) < 1e-6
-    assert float(lg) == pytest.approx(float(lo), rel=1e-5, abs=1e-9)
+    assert float(lg) == pytest.approx(float(lo), rel=1e-5, abs=2e-8)   # the loss itself is ~3e-7: pure rounding noise of 1 - n/d
 
 
 def test_standalone_ops_on_gpu():
