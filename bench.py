@@ -278,7 +278,7 @@ def run_ours(args):
     for s in dev_sets:
         inputs, flows, mobiles, cams, inst = s
         with torch.no_grad():
-            data = loss_mod._scale_data(inputs, ids, flows, mobiles, inst, list(scales), cams, post, bits)
+            data, _ = loss_mod._scale_data(inputs, ids, flows, mobiles, inst, list(scales), cams, post, bits)
         cfg = fz.FusedConfig(batch=B, n_pairs=2, post=post, mask_mode=_cabi.MASK_MIN, flags=flags,
                              threshold=opt.threshold if post != 0 else None, alpha=opt.alpha, w_d2_sim=opt.w_d2_sim,
                              w_e=opt.w_e, w_s=opt.w_s, w_c=opt.w_c, w_p=opt.w_p)

@@ -152,6 +152,19 @@ MDN_API int mdn_loss_fused(const MdnLossDesc* desc, float* loss_out, void* works
 MDN_API int mdn_loss_scale_grads(const MdnLossDesc* desc, const float* g, float* applied, void* stream);
 
 /*
+ * Fundamental matrices for every (scale, source frame, sample) in one launch: F = K^-T ((t_x R) K^-1),
+ * loss_utils.py:50-62, with R = cam[:, :3, :3], t = cam[:, :3, 3] (loss_functions.py:45-46) and
+ * K^-1 = inv_K[:, :3, :3] (loss_functions.py:123).  `inv_K` is a HOST array of n_scales device pointers to (B,4,4)
+ * matrices, `cam` a HOST array of n_pairs device pointers to (B,4,4) poses; fmat is (n_scales, n_pairs, B, 3, 3).
+ * Each 3x3 product accumulates k = 0,1,2 with FMAs, the order of the batched SGEMM the reference runs.
+ * The backward takes g_fmat (same shape) and writes g_cam[p] (B,4,4): d/dR in [:3,:3], d/dt in [:3,3], zeros elsewhere.
+ */
+MDN_API int mdn_fundamental_fwd(const float* const* inv_K, const float* const* cam, float* fmat, int32_t n_scales,
+                                int32_t n_pairs, int32_t batch, void* stream);
+MDN_API int mdn_fundamental_bwd(const float* const* inv_K, const float* const* cam, const float* g_fmat,
+                                float* const* g_cam, int32_t n_scales, int32_t n_pairs, int32_t batch, void* stream);
+
+/*
  * get_epipolar_new (loss_utils.py:39-69) for arbitrary homogeneous point sets: p1, p2 are (B,3,N), fmat
  * (B,3,3); out (B,1,N) is the SIGNED distance.  The backward takes the upstream gradient g_out (B,1,N)
  * and writes g_p1, g_p2 (B,3,N, either may be NULL) and g_fmat (B,3,3, may be NULL).

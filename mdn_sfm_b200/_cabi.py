@@ -41,6 +41,7 @@ class MdnLossDesc(C.Structure):
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmdn_loss.so")
 
 EXPORTS = ("mdn_version", "mdn_last_error_string", "mdn_loss_workspace_bytes", "mdn_loss_fused", "mdn_loss_scale_grads",
+           "mdn_fundamental_fwd", "mdn_fundamental_bwd",
            "mdn_epipolar_points_fwd", "mdn_epipolar_points_bwd", "mdn_epipolar_points_workspace_bytes",
            "mdn_flow_warp_fwd", "mdn_flow_warp_bwd", "mdn_ssim_fwd", "mdn_ssim_bwd", "mdn_binary_image")
 
@@ -62,6 +63,8 @@ class Library:
             "mdn_loss_workspace_bytes": (sz, [D]),
             "mdn_loss_fused": (C.c_int, [D, _P, _P, sz, _P]),
             "mdn_loss_scale_grads": (C.c_int, [D, _P, _P, _P]),
+            "mdn_fundamental_fwd": (C.c_int, [C.POINTER(_P), C.POINTER(_P), _P, i32, i32, i32, _P]),
+            "mdn_fundamental_bwd": (C.c_int, [C.POINTER(_P), C.POINTER(_P), _P, C.POINTER(_P), i32, i32, i32, _P]),
             "mdn_epipolar_points_fwd": (C.c_int, [_P, _P, _P, _P, i32, i64, _P]),
             "mdn_epipolar_points_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, i32, i64, _P, sz, _P]),
             "mdn_epipolar_points_workspace_bytes": (sz, [i32, i64]),
@@ -105,6 +108,11 @@ def check_tensor(t, dtype=torch.float32, what="tensor"):
 
 def stream_ptr(ref_tensor):
     return torch.cuda.current_stream(ref_tensor.device).cuda_stream if ref_tensor.is_cuda else 0
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (the `const float* const*` arguments of the C ABI)."""
+    return (_P * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
 def ptr(t):

@@ -335,6 +335,98 @@ __global__ void epipolar_points_bwd_finish_kernel(const float* __restrict__ part
   g_fmat[b * 9 + k] = t;
 }
 
+struct FundArgs {
+  const float* inv_K[MDN_MAX_SCALES];
+  const float* cam[MDN_MAX_PAIRS];
+  float* g_cam[MDN_MAX_PAIRS];
+  int n_scales, n_pairs, batch;
+};
+
+MDN_DEV void mat3_mul(const float* A, const float* Bm, float* C) {   // C = A B, k-ordered FMA accumulation from 0
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float acc = __fmul_rn(A[i * 3], Bm[j]);
+      acc = __fmaf_rn(A[i * 3 + 1], Bm[3 + j], acc);
+      C[i * 3 + j] = __fmaf_rn(A[i * 3 + 2], Bm[6 + j], acc);
+    }
+}
+
+MDN_DEV void load_pose(const float* cam, float* R, float* tx) {   // (4,4) row-major -> R (3x3), [t]_x (3x3)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) R[i * 3 + j] = cam[i * 4 + j];
+  const float t0 = cam[3], t1 = cam[7], t2 = cam[11];
+  tx[0] = 0.f; tx[1] = -t2; tx[2] = t1; tx[3] = t2; tx[4] = 0.f; tx[5] = -t0; tx[6] = -t1; tx[7] = t0; tx[8] = 0.f;
+}
+
+__global__ void fundamental_fwd_kernel(const __grid_constant__ FundArgs A, float* __restrict__ fmat) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n_pairs * A.batch) return;
+  const int p = i / A.batch, b = i - p * A.batch;
+  float R[9], tx[9], M1[9];
+  load_pose(A.cam[p] + b * 16, R, tx);
+  mat3_mul(tx, R, M1);                                  // loss_utils.py:61
+  for (int s = 0; s < A.n_scales; ++s) {
+    float K[9], KT[9], M2[9], F[9];
+    const float* kp = A.inv_K[s] + b * 16;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { K[r * 3 + c] = kp[r * 4 + c]; KT[c * 3 + r] = kp[r * 4 + c]; }
+    mat3_mul(M1, K, M2);                                // loss_utils.py:62 (inner product first)
+    mat3_mul(KT, M2, F);
+    float* out = fmat + ((size_t)(s * A.n_pairs + p) * A.batch + b) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[k] = F[k];
+  }
+}
+
+__global__ void fundamental_bwd_kernel(const __grid_constant__ FundArgs A, const float* __restrict__ g_fmat) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n_pairs * A.batch) return;
+  const int p = i / A.batch, b = i - p * A.batch;
+  float R[9], tx[9], G1[9];
+  load_pose(A.cam[p] + b * 16, R, tx);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) G1[k] = 0.f;
+  for (int s = 0; s < A.n_scales; ++s) {                // dL/dM1 = sum_s K gF K^T   (K = K^-1 of scale s)
+    float K[9], KT[9], T1[9], T2[9];
+    const float* kp = A.inv_K[s] + b * 16;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { K[r * 3 + c] = kp[r * 4 + c]; KT[c * 3 + r] = kp[r * 4 + c]; }
+    const float* g = g_fmat + ((size_t)(s * A.n_pairs + p) * A.batch + b) * 9;
+    float gF[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) gF[k] = g[k];
+    mat3_mul(K, gF, T1);
+    mat3_mul(T1, KT, T2);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) G1[k] += T2[k];
+  }
+  float txT[9], RT[9], gR[9], gTx[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { txT[c * 3 + r] = tx[r * 3 + c]; RT[c * 3 + r] = R[r * 3 + c]; }
+  mat3_mul(txT, G1, gR);                                // M1 = t_x R
+  mat3_mul(G1, RT, gTx);
+  float* out = A.g_cam[p] + b * 16;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) out[k] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[r * 4 + c] = gR[r * 3 + c];
+  out[3] = gTx[7] - gTx[5];                             // t0: t_x[2][1] = t0, t_x[1][2] = -t0
+  out[7] = gTx[2] - gTx[6];                             // t1: t_x[0][2] = t1, t_x[2][0] = -t1
+  out[11] = gTx[3] - gTx[1];                            // t2: t_x[1][0] = t2, t_x[0][1] = -t2
+}
+
 __global__ void __launch_bounds__(NTHREADS) flow_warp_fwd_kernel(const float* __restrict__ ref, const float* __restrict__ flow,
                                                                  float* __restrict__ warped, float* __restrict__ grid_out,
                                                                  uint8_t* __restrict__ valid, int C, int h, int w, const WarpGeom G) {
@@ -626,6 +718,47 @@ extern "C" MDN_API int mdn_loss_scale_grads(const MdnLossDesc* d, const float* g
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return MDN_OK;
+}
+
+static int fund_args(FundArgs& A, const float* const* inv_K, const float* const* cam, float* const* g_cam, int n_scales,
+                     int n_pairs, int batch) {
+  if (!inv_K || !cam) return fail(MDN_ERR_NULL_POINTER, "inv_K / cam pointer array is NULL");
+  if (n_scales < 1 || n_scales > MDN_MAX_SCALES || n_pairs < 1 || n_pairs > MDN_MAX_PAIRS || batch < 1)
+    return fail(MDN_ERR_BAD_SHAPE, "n_scales / n_pairs / batch out of range");
+  memset(&A, 0, sizeof(A));
+  A.n_scales = n_scales; A.n_pairs = n_pairs; A.batch = batch;
+  for (int s = 0; s < n_scales; ++s) { if (!inv_K[s]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "inv_K[s]"); A.inv_K[s] = inv_K[s]; }
+  for (int p = 0; p < n_pairs; ++p) {
+    if (!cam[p]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "cam[p]");
+    A.cam[p] = cam[p];
+    if (g_cam) { if (!g_cam[p]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "g_cam[p]"); A.g_cam[p] = g_cam[p]; }
+  }
+  return MDN_OK;
+}
+
+extern "C" MDN_API int mdn_fundamental_fwd(const float* const* inv_K, const float* const* cam, float* fmat, int32_t n_scales,
+                                           int32_t n_pairs, int32_t batch, void* stream) {
+  FundArgs A;
+  int rc = fund_args(A, inv_K, cam, nullptr, n_scales, n_pairs, batch);
+  if (rc != MDN_OK) return rc;
+  if (!fmat) return fail(MDN_ERR_NULL_POINTER, "fmat is NULL");
+  const int n = n_pairs * batch;
+  MDN_LAUNCH(fundamental_fwd_kernel, dim3((n + 63) / 64), dim3(64), 0, (cudaStream_t)stream, A, fmat);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" MDN_API int mdn_fundamental_bwd(const float* const* inv_K, const float* const* cam, const float* g_fmat,
+                                           float* const* g_cam, int32_t n_scales, int32_t n_pairs, int32_t batch, void* stream) {
+  FundArgs A;
+  if (!g_cam) return fail(MDN_ERR_NULL_POINTER, "g_cam pointer array is NULL");
+  int rc = fund_args(A, inv_K, cam, g_cam, n_scales, n_pairs, batch);
+  if (rc != MDN_OK) return rc;
+  if (!g_fmat) return fail(MDN_ERR_NULL_POINTER, "g_fmat is NULL");
+  const int n = n_pairs * batch;
+  MDN_LAUNCH(fundamental_bwd_kernel, dim3((n + 63) / 64), dim3(64), 0, (cudaStream_t)stream, A, g_fmat);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }
 
 static inline unsigned blocks_for(long long n, int cap = 148 * 8) {

@@ -78,15 +78,16 @@ def _workspace(device, nbytes):
     return ws
 
 
-def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None):
+def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None, g_fmat_all=None):
     """Launches the fused kernel.
 
     need_grad: per scale a dict {"flow": [bool,bool], "mob": [bool,bool], "fmat": [bool,bool]}.
+    g_fmat_all: optional (S,P,B,3,3) buffer whose [k,p] slices receive d/dF (one tensor for the whole pyramid).
     Returns (loss_out (8,), grads (same structure, tensors or None), maps (dict name -> [pair tensors]), call).
     """
     library = library or _cabi.lib()
     dev = None
-    any_grad = any(any(v) for ng in need_grad for v in ng.values())
+    any_grad = any(any(v) for ng in need_grad for v in ng.values()) or g_fmat_all is not None
     flags = cfg.flags | (OPT_GRADS if any_grad else 0) | (OPT_CUDA_ARITH if cfg.cuda_arith else 0)
     call = _cabi.FusedCall(batch=cfg.batch, n_pairs=cfg.n_pairs, post=cfg.post, mask_mode=cfg.mask_mode, flags=flags,
                            threshold=cfg.threshold, alpha=cfg.alpha, w_d2_sim=cfg.w_d2_sim, w_e=cfg.w_e, w_s=cfg.w_s,
@@ -103,7 +104,9 @@ def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None
                 g["flow"][p] = torch.empty((B, 2, h, w), dtype=torch.float32, device=dev)
             if ng["mob"][p]:
                 g["mob"][p] = torch.empty((B, 1, h, w), dtype=torch.float32, device=dev)
-            if ng["fmat"][p]:
+            if g_fmat_all is not None and p < cfg.n_pairs:
+                g["fmat"][p] = g_fmat_all[k, p]
+            elif ng["fmat"][p]:
                 g["fmat"][p] = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
         if any_grad and cfg.mask_mode == MASK_MIN and (g["mob"][0] is None) != (g["mob"][1] is None):
             # the arg-min routing writes both maps; give the kernel a scratch target for the unused one
@@ -138,11 +141,15 @@ class _FusedLossFn(torch.autograd.Function):
     def forward(ctx, cfg, scales, slots, library, *diff_inputs):
         # slots[i] = (scale index, kind, pair) for diff_inputs[i]
         need = [{"flow": [False, False], "mob": [False, False], "fmat": [False, False]} for _ in scales]
+        g_fmat_all = None
         for (k, kind, p), t in zip(slots, diff_inputs):
-            if t.requires_grad:
+            if kind == "fmat_all":
+                g_fmat_all = torch.empty_like(t)
+            elif t.requires_grad:
                 need[k][kind][p] = True
-        loss_out, grads, maps, call = run_fused(cfg, scales, need, library)
+        loss_out, grads, maps, call = run_fused(cfg, scales, need, library, g_fmat_all)
         ctx.call, ctx.library, ctx.slots, ctx.grads, ctx.loss_out = call, library, slots, grads, loss_out
+        ctx.g_fmat_all = g_fmat_all
         ctx.maps = maps
         total = loss_out[0]
         terms = loss_out[1:5]
@@ -157,16 +164,23 @@ class _FusedLossFn(torch.autograd.Function):
         ctx.call.scale_grads(ctx.library, g, ctx.loss_out[OUT_APPLIED:], _cabi.stream_ptr(g))
         out = [None, None, None, None]
         for (k, kind, p) in ctx.slots:
-            out.append(ctx.grads[k][kind][p])
+            out.append(ctx.g_fmat_all if kind == "fmat_all" else ctx.grads[k][kind][p])
         return tuple(out)
 
 
-def fused_loss(cfg: FusedConfig, scales: List[ScaleData], library=None):
-    """-> (total 0-d tensor with grad_fn, terms (4,) = [epip, smooth, consis, photo] detached, maps dict)."""
+def fused_loss(cfg: FusedConfig, scales: List[ScaleData], library=None, fmat_all=None):
+    """-> (total 0-d tensor with grad_fn, terms (4,) = [epip, smooth, consis, photo] detached, maps dict).
+
+    fmat_all: the (S,P,B,3,3) tensor the per-scale `fmat` entries are slices of; when it requires grad its gradient
+    is returned as ONE tensor instead of S*P slice gradients."""
     library = library or _cabi.lib()
     slots, diff = [], []
+    grad_on = torch.is_grad_enabled()
+    if fmat_all is not None and fmat_all.requires_grad and grad_on:
+        slots.append((0, "fmat_all", 0))
+        diff.append(fmat_all)
     for k, S in enumerate(scales):
-        for kind in ("flow", "mob", "fmat"):
+        for kind in ("flow", "mob") + (() if fmat_all is not None else ("fmat",)):
             for p, t in enumerate(getattr(S, kind)):
                 if t is not None and t.requires_grad and torch.is_grad_enabled():
                     if kind == "mob" and cfg.mask_mode == MASK_SHARED and p == 1:

@@ -33,6 +33,7 @@ from .layers import SSIM, get_scale_factor  # noqa: F401  (re-exported like the 
 from .loss_utils import *  # noqa: F401,F403  (the reference does `from loss_utils import *`)
 from .loss_utils import create_coords as _create_coords
 from .loss_utils import _arith_flag, instance_mask_u8
+from .ops import fundamental_matrices
 from .utils import gauss_distance_weight
 
 MODES = ("SN", "T", "TG", "DS", "DC")
@@ -248,10 +249,8 @@ class Loss(nn.Module):
     def _scale_data(self, inputs, frame_id, flow, mobile, instances_info, scales, cam_T_cam, post, bits):
         lm = self._lm()
         ids = list(frame_id)
-        R = torch.stack([cam_T_cam[i][:, :3, :3] for i in ids], 0).unsqueeze(0)      # (1,P,B,3,3)
-        t = torch.stack([cam_T_cam[i][:, :3, -1] for i in ids], 0).unsqueeze(0)      # (1,P,B,3)
-        Kinv = torch.stack([inputs[("inv_K", s)][:, :3, :3] for s in scales], 0).unsqueeze(1)   # (S,1,B,3,3)
-        F_all = fused.fundamental_matrix(Kinv, R, t).contiguous()                    # (S,P,B,3,3)
+        # one prologue launch: F for every (scale, source frame, sample); gradients flow back to the poses
+        F_all = fundamental_matrices([inputs[("inv_K", s)] for s in scales], [cam_T_cam[i] for i in ids], self._library)
         data = []
         for k, s in enumerate(scales):
             tgt = _c(inputs[("color", 0, s)], "target image")
@@ -270,7 +269,7 @@ class Loss(nn.Module):
                 S.mob[1] = _c(mobile[("mobile", 1, s)], "mobile mask")
             S.weight, S.inst = lm._epi_extras(post, bits, h, w, tgt.device, instances_info)
             data.append(S)
-        return data
+        return data, F_all
 
     def forward(self, inputs, frame_id, flow, mobile, instances_info, scales, cam_T_cam):
         o = self.opt
@@ -285,13 +284,13 @@ class Loss(nn.Module):
             flags |= TERM_CONSIS
         if self.photometric:
             flags |= TERM_PHOTO | (OPT_SSIM if self.ssim is not None else 0)
-        data = self._scale_data(inputs, ids, flow, mobile, instances_info, scales, cam_T_cam, post, bits)
+        data, F_all = self._scale_data(inputs, ids, flow, mobile, instances_info, scales, cam_T_cam, post, bits)
         b = data[0].tgt.shape[0]
         cfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=len(ids), post=post, mask_mode=MASK_OWN if o.disable_min else MASK_MIN,
                                 flags=flags, threshold=getattr(o, "threshold", None) if post != fused.POST_SN else None,
                                 alpha=o.alpha, w_d2_sim=o.w_d2_sim, w_e=o.w_e, w_s=o.w_s, w_c=o.w_c,
                                 w_p=getattr(o, "w_p", 1.0) if self.photometric else 0.0)
-        total, terms, _ = fused.fused_loss(cfg, data, self._library)
+        total, terms, _ = fused.fused_loss(cfg, data, self._library, fmat_all=F_all)
         losses = {"consis": terms[OUT_CONSIS - 1] if not o.disable_consisloss else 0, "epip": terms[OUT_EPIP - 1],
                   "smooth": terms[OUT_SMOOTH - 1] if not o.disable_smoothloss else 0, "loss": total}
         if self.photometric:
