@@ -249,8 +249,16 @@ class Loss(nn.Module):
     def _scale_data(self, inputs, frame_id, flow, mobile, instances_info, scales, cam_T_cam, post, bits):
         lm = self._lm()
         ids = list(frame_id)
-        # one prologue launch: F for every (scale, source frame, sample); gradients flow back to the poses
-        F_all = fundamental_matrices([inputs[("inv_K", s)] for s in scales], [cam_T_cam[i] for i in ids], self._library)
+        if self._cuda_arith:
+            # one prologue launch: F for every (scale, source frame, sample); gradients flow back to the poses.  Its
+            # 3x3 products accumulate like the batched SGEMM the reference runs on CUDA.
+            F_all = fundamental_matrices([inputs[("inv_K", s)] for s in scales], [cam_T_cam[i] for i in ids], self._library)
+        else:
+            # arith="cpu": the reference's own three torch.matmul calls (loss_utils.py:61-62), batched over scales / frames
+            R = torch.stack([cam_T_cam[i][:, :3, :3] for i in ids], 0).unsqueeze(0)      # (1,P,B,3,3)
+            t = torch.stack([cam_T_cam[i][:, :3, -1] for i in ids], 0).unsqueeze(0)      # (1,P,B,3)
+            Kinv = torch.stack([inputs[("inv_K", s)][:, :3, :3] for s in scales], 0).unsqueeze(1)   # (S,1,B,3,3)
+            F_all = fused.fundamental_matrix(Kinv, R, t).contiguous()                    # (S,P,B,3,3)
         data = []
         for k, s in enumerate(scales):
             tgt = _c(inputs[("color", 0, s)], "target image")

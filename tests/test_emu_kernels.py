@@ -162,3 +162,30 @@ def test_free_functions():
         assert torch.equal(layers.transformation_from_parameters(aa, tt, inv), restate.transformation_from_parameters(aa, tt, inv))
     assert torch.equal(layers.get_scale_factor(2, 5, 7).contiguous(), restate.get_scale_factor(2, 5, 7).contiguous())
     assert torch.equal(loss_utils.create_coords(2, 5, 7), restate.create_coords(2, 5, 7))
+
+
+def test_fundamental_matrix_prologue():
+    """mdn_fundamental_fwd/bwd vs the reference's three matmuls (loss_utils.py:50-62) and their autograd."""
+    from mdn_sfm_b200 import fused
+    from mdn_sfm_b200.ops import fundamental_matrices
+    g = torch.Generator().manual_seed(2)
+    B, S, P = 3, 4, 2
+    cams = [synthetic.make_pose(torch.randn(B, 1, 1, 3, generator=g) * 0.05, torch.randn(B, 1, 1, 3, generator=g) * 0.2)
+            for _ in range(P)]
+    Ks = []
+    for s in range(S):
+        K = torch.tensor([[0.58 * 640 / 2 ** s, 0, 320 / 2 ** s, 0], [0, 1.92 * 192 / 2 ** s, 96 / 2 ** s, 0],
+                          [0, 0, 1, 0], [0, 0, 0, 1]], dtype=torch.float32)
+        Ks.append(torch.linalg.pinv(K).unsqueeze(0).repeat(B, 1, 1))
+    wgt = torch.randn(S, P, B, 3, 3, generator=g)
+    co = [c.clone().requires_grad_(True) for c in cams]
+    Fo = torch.stack([torch.stack([restate.fundamental_matrix(Ks[s][:, :3, :3], co[p][:, :3, :3], co[p][:, :3, -1])
+                                   for p in range(P)]) for s in range(S)])
+    (Fo * wgt).sum().backward()
+    with emulated():
+        cg = [c.clone().requires_grad_(True) for c in cams]
+        Fg = fundamental_matrices(Ks, cg)
+        (Fg * wgt).sum().backward()
+    assert Fg.shape == Fo.shape and common.rel_max(Fo, Fg) < 1e-6
+    for a, b in zip(co, cg):
+        assert common.rel_max(a.grad, b.grad) < 1e-5

@@ -42,8 +42,14 @@ def test_cuda_reproduces_netinit_golden(mode):
     photo, ssim_on, dmin = gu.NETINIT_MODES[mode]
     (B, H, W), batch = gu.load_netinit_batch()
     opt = synthetic.default_opt(B, H, W, disable_min=dmin)
+    z = gu.load_outputs("netinit_" + mode)
     got = common.product_run(opt, batch, mode, photo, ssim_on, "cuda", pose_grad=True, arith="cpu")  # fixtures come from the CPU run of the reference
-    gu.check_against_golden(gu.load_outputs("netinit_" + mode), got, photo, common.FWD_TOL, common.GRAD_TOL)
+    # This fixture has a near-degenerate pose (random-init PoseNet: |t| ~ 1e-4), so p2^T F p1 cancels almost completely
+    # and the reference's OWN arithmetic, run eagerly on this GPU, differs from its CPU run (the fixture) by ~1-2e-5 in the
+    # epipolar maps (cuBLAS vs MKL rounding of F; profiles/ has the measured table).  The maps are therefore held to
+    # max(1e-5, 1.5 x that measured reference-vs-reference floor); scalars and gradients keep the plain tolerances.
+    floor = gu.map_noise_floor(z, common.oracle_run(opt, batch, mode, photo, ssim_on, "cuda"))
+    gu.check_against_golden(z, got, photo, common.FWD_TOL, common.GRAD_TOL, map_tol=max(common.FWD_TOL, 1.5 * floor))
 
 
 @pytest.mark.gpu

@@ -118,6 +118,31 @@ def test_standalone_ops_on_gpu():
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
 
 
+def test_fundamental_matrix_prologue_gpu():
+    from mdn_sfm_b200.ops import fundamental_matrices
+    from oracle import restate
+    g = torch.Generator().manual_seed(2)
+    B, S, P = 12, 4, 2
+    cams = [synthetic.make_pose(torch.randn(B, 1, 1, 3, generator=g) * 0.05, torch.randn(B, 1, 1, 3, generator=g) * 0.2).to(DEV)
+            for _ in range(P)]
+    Ks = []
+    for s in range(S):
+        K = torch.tensor([[0.58 * 640 / 2 ** s, 0, 320 / 2 ** s, 0], [0, 1.92 * 192 / 2 ** s, 96 / 2 ** s, 0],
+                          [0, 0, 1, 0], [0, 0, 0, 1]], dtype=torch.float32)
+        Ks.append(torch.linalg.pinv(K).unsqueeze(0).repeat(B, 1, 1).to(DEV))
+    wgt = torch.randn(S, P, B, 3, 3, generator=g).to(DEV)
+    co = [c.clone().requires_grad_(True) for c in cams]
+    Fo = torch.stack([torch.stack([restate.fundamental_matrix(Ks[s][:, :3, :3], co[p][:, :3, :3], co[p][:, :3, -1])
+                                   for p in range(P)]) for s in range(S)])
+    (Fo * wgt).sum().backward()
+    cg = [c.clone().requires_grad_(True) for c in cams]
+    Fg = fundamental_matrices(Ks, cg)
+    (Fg * wgt).sum().backward()
+    assert common.rel_max(Fo, Fg) < 1e-6
+    for a, b in zip(co, cg):
+        assert common.rel_max(a.grad, b.grad) < 1e-5
+
+
 def test_native_library_is_what_ran():
     """Guards against a silent fallback: the in-tree .so must be mapped into this process."""
     from mdn_sfm_b200 import _cabi
