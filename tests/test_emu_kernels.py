@@ -186,6 +186,6 @@ def test_fundamental_matrix_prologue():
         cg = [c.clone().requires_grad_(True) for c in cams]
         Fg = fundamental_matrices(Ks, cg)
         (Fg * wgt).sum().backward()
-    assert Fg.shape == Fo.shape and common.rel_max(Fo, Fg) < 1e-6
+    assert Fg.shape == Fo.shape and common.rel_max(Fo, Fg) < 1e-5
     for a, b in zip(co, cg):
-        assert common.rel_max(a.grad, b.grad) < 1e-5
+        assert common.rel_max(a.grad, b.grad) < 1e-4

@@ -138,9 +138,9 @@ def test_fundamental_matrix_prologue_gpu():
     cg = [c.clone().requires_grad_(True) for c in cams]
     Fg = fundamental_matrices(Ks, cg)
     (Fg * wgt).sum().backward()
-    assert common.rel_max(Fo, Fg) < 1e-6
+    assert common.rel_max(Fo, Fg) < 1e-5
     for a, b in zip(co, cg):
-        assert common.rel_max(a.grad, b.grad) < 1e-5
+        assert common.rel_max(a.grad, b.grad) < 1e-4
 
 
 def test_native_library_is_what_ran():
