@@ -125,6 +125,51 @@ MDN_DEV void bilinear_deriv(const Bilin& b, float nw, float ne, float sw, float 
   ddy = b.ax0 * (sw - nw) + b.ax1 * (se - ne);
 }
 
+// Branch-free variant used by the fused kernel: corner offsets clamped into the plane, zeros padding applied by
+// multiplying the loaded values with 0/1 masks, so the 4 x C loads of a pixel can all be in flight together.
+struct Gather4 {
+  int o00, o01, o10, o11;       // element offsets of the nw, ne, sw, se corners inside one channel plane (always valid)
+  float m00, m01, m10, m11;     // 1 if that corner lies inside the image, else 0
+  float ax0, ax1, ay0, ay1;     // (x0+1-ix), (ix-x0), (y0+1-iy), (iy-y0)
+};
+
+MDN_DEV Gather4 gather_setup(float ix, float iy, int h, int w) {
+  Gather4 g;
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  g.ax0 = (x0f + 1.f) - ix; g.ax1 = ix - x0f;
+  g.ay0 = (y0f + 1.f) - iy; g.ay1 = iy - y0f;
+  int x0 = min(max(__float2int_rd(ix), -2), w), y0 = min(max(__float2int_rd(iy), -2), h);   // NaN -> 0, huge -> outside
+  const int x1 = x0 + 1, y1 = y0 + 1;
+  const bool bx0 = (unsigned)x0 < (unsigned)w, bx1 = (unsigned)x1 < (unsigned)w;
+  const bool by0 = (unsigned)y0 < (unsigned)h, by1 = (unsigned)y1 < (unsigned)h;
+  const int cx0 = bx0 ? x0 : 0, cx1 = bx1 ? x1 : 0;
+  const int r0 = (by0 ? y0 : 0) * w, r1 = (by1 ? y1 : 0) * w;
+  g.o00 = r0 + cx0; g.o01 = r0 + cx1; g.o10 = r1 + cx0; g.o11 = r1 + cx1;
+  const float fx0 = bx0 ? 1.f : 0.f, fx1 = bx1 ? 1.f : 0.f, fy0 = by0 ? 1.f : 0.f, fy1 = by1 ? 1.f : 0.f;
+  g.m00 = fx0 * fy0; g.m01 = fx1 * fy0; g.m10 = fx0 * fy1; g.m11 = fx1 * fy1;
+  return g;
+}
+
+MDN_DEV void gather_fetch(const float* __restrict__ plane, const Gather4& g, float& nw, float& ne, float& sw, float& se) {
+  nw = __ldg(plane + g.o00) * g.m00;
+  ne = __ldg(plane + g.o01) * g.m01;
+  sw = __ldg(plane + g.o10) * g.m10;
+  se = __ldg(plane + g.o11) * g.m11;
+}
+
+MDN_DEV float gather_value(const Gather4& g, float nw, float ne, float sw, float se) {
+  float o = nw * (g.ax0 * g.ay0);
+  o += ne * (g.ax1 * g.ay0);
+  o += sw * (g.ax0 * g.ay1);
+  o += se * (g.ax1 * g.ay1);
+  return o;
+}
+
+MDN_DEV void gather_deriv(const Gather4& g, float nw, float ne, float sw, float se, float& ddx, float& ddy) {
+  ddx = g.ay0 * (ne - nw) + g.ay1 * (se - sw);
+  ddy = g.ax0 * (sw - nw) + g.ax1 * (se - ne);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // SSIM, networks/layers.py:164-178, from the five 3x3 window SUMS (reflect padding applied by the caller).
 struct SsimOut {
@@ -142,14 +187,18 @@ MDN_DEV float div9(float s) {
 
 MDN_DEV SsimOut ssim_window(float sx, float sy, float sxx, float syy, float sxy, bool want_grad) {
   const float C1 = 0.0001f, C2 = 0.0009f;
-  // avg_pool2d divides the window sum by 9; sigma = E[x^2] - mu^2 cancels, so these quotients are kept exact
-  float mu_x = div9(sx), mu_y = div9(sy);
-  float sig_x = __fsub_rn(div9(sxx), __fmul_rn(mu_x, mu_x));
-  float sig_y = __fsub_rn(div9(syy), __fmul_rn(mu_y, mu_y));
-  float sig_xy = __fsub_rn(div9(sxy), __fmul_rn(mu_x, mu_y));
-  float n1 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, mu_x), mu_y), C1);
-  float n2 = __fadd_rn(__fmul_rn(2.f, sig_xy), C2);
-  float d1 = __fadd_rn(__fadd_rn(__fmul_rn(mu_x, mu_x), __fmul_rn(mu_y, mu_y)), C1);
+  // avg_pool2d divides the window sum by 9.  The sums already differ from the reference's in the last ulp (separable
+  // order), so a correctly rounded quotient buys nothing: multiply by rn(1/9).  sigma = E[x^2] - mu^2 keeps the
+  // reference's separate roundings (no FMA contraction of the cancelling difference).
+  const float r9 = 0.111111111f;
+  float mu_x = __fmul_rn(sx, r9), mu_y = __fmul_rn(sy, r9);
+  float mxx = __fmul_rn(mu_x, mu_x), myy = __fmul_rn(mu_y, mu_y), mxy = __fmul_rn(mu_x, mu_y);
+  float sig_x = __fsub_rn(__fmul_rn(sxx, r9), mxx);
+  float sig_y = __fsub_rn(__fmul_rn(syy, r9), myy);
+  float sig_xy = __fsub_rn(__fmul_rn(sxy, r9), mxy);
+  float n1 = __fmaf_rn(2.f, mxy, C1);          // == (2 mu_x) mu_y + C1: doubling is exact
+  float n2 = __fmaf_rn(2.f, sig_xy, C2);
+  float d1 = __fadd_rn(__fadd_rn(mxx, myy), C1);
   float d2 = __fadd_rn(__fadd_rn(sig_x, sig_y), C2);
   float n = __fmul_rn(n1, n2), D = __fmul_rn(d1, d2);
   float invD = __fdividef(1.f, D);        // D >= C1*C2 > 0; 2-ulp reciprocal is far inside the 1e-5 budget
@@ -157,12 +206,14 @@ MDN_DEV SsimOut ssim_window(float sx, float sy, float sxx, float syy, float sxy,
   SsimOut o;
   o.J = fminf(fmaxf(z, 0.f), 1.f);
   o.dmu_y = o.dY2 = o.dXY = o.dmu_x = o.dX2 = 0.f;
-  if (want_grad && z >= 0.f && z <= 1.f) {   // clamp backward gate is inclusive
-    float nbar = -0.5f * invD;            // dz/dn
-    float Dbar = 0.5f * n * invD * invD;  // dz/dD
+  if (want_grad) {
+    const float gate = (z >= 0.f && z <= 1.f) ? 0.5f : 0.f;   // clamp backward gate is inclusive; 0.5 = d z / d(1 - n/D)
+    float nbar = -gate * invD;            // dz/dn
+    float Dbar = gate * n * invD * invD;  // dz/dD
     float dn1 = nbar * n2, dn2 = nbar * n1, dd1 = Dbar * d2, dd2 = Dbar * d1;
-    o.dmu_y = 2.f * mu_x * (dn1 - dn2) + 2.f * mu_y * (dd1 - dd2);
-    o.dmu_x = 2.f * mu_y * (dn1 - dn2) + 2.f * mu_x * (dd1 - dd2);
+    float t1 = 2.f * (dn1 - dn2), t2 = 2.f * (dd1 - dd2);
+    o.dmu_y = mu_x * t1 + mu_y * t2;
+    o.dmu_x = mu_y * t1 + mu_x * t2;
     o.dY2 = dd2;
     o.dX2 = dd2;
     o.dXY = 2.f * dn2;

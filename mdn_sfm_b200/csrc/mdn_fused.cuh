@@ -53,8 +53,28 @@ struct PixState {          // what a thread keeps in registers about one of its 
   bool valid;
 };
 
-template <bool PHOTO>
-__global__ void __launch_bounds__(NTHREADS, PHOTO ? 3 : 4) fused_tile_kernel(const __grid_constant__ KParams P) {
+// 3x3 adjoint gather of one coefficient plane for the thread's two vertically adjacent pixels.  Q points at the
+// halo-1 slot (ly0, lx): rows ly0 .. ly0+3, columns lx .. lx+2.  BORDER applies the reflection multiplicities.
+template <bool BORDER>
+MDN_DEV void adjoint_box(const float* Q, const float* wxm, const float (*wym)[3], float& s0, float& s1) {
+  float H[4];
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const float q0 = Q[rr * R1W], q1 = Q[rr * R1W + 1], q2 = Q[rr * R1W + 2];
+    H[rr] = BORDER ? (wxm[0] * q0 + wxm[1] * q1 + wxm[2] * q2) : (q0 + q1 + q2);
+  }
+  if (BORDER) {
+    s0 = wym[0][0] * H[0] + wym[0][1] * H[1] + wym[0][2] * H[2];
+    s1 = wym[1][0] * H[1] + wym[1][1] * H[2] + wym[1][2] * H[3];
+  } else {
+    const float mid = H[1] + H[2];
+    s0 = H[0] + mid;
+    s1 = mid + H[3];
+  }
+}
+
+template <bool PHOTO, bool MAPS>
+__global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_constant__ KParams P) {
   MDN_DYN_SMEM(smem_raw);
   const int tid = threadIdx.x, nthr = blockDim.x, nwarps = nthr >> 5;
   const bool use_ssim = PHOTO && (P.flags & MDN_OPT_SSIM);
@@ -143,62 +163,58 @@ __global__ void __launch_bounds__(NTHREADS, PHOTO ? 3 : 4) fused_tile_kernel(con
     if (PHOTO) {
       const float* rf = S.ref[pair] + (size_t)b * 3 * hw;
       // -- P1a: the thread's own two pixels (real pixels when inside the image, reflected copies otherwise)
+      const float* rf1 = rf + hw;
+      const float* rf2 = rf1 + hw;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int ly = ly0 + k, y = y0 + ly;
         const int i2 = (ly + 2) * R2W + lx + 2;
         const int yy = stage_index(y, h), xx = stage_index(px, w);
         const bool real = (y < h) & col_in;
-        ps[k].valid = false;
+        const bool ok = (yy | xx) >= 0;
+        const int o = ok ? yy * w + xx : 0;
+        float fx = __fmul_rn(S.sx, __ldg(flx + o)), fy = __fmul_rn(S.sy, __ldg(fly + o));
+        WarpCoord wc = warp_coord((float)xx, (float)yy, fx, fy, S.geom);
+        Gather4 gt = gather_setup(wc.ix, wc.iy, h, w);
+        ps[k].valid = wc.valid & real;
+        const float okf = ok ? 1.f : 0.f;
+        float v4[3][4];
+        gather_fetch(rf, gt, v4[0][0], v4[0][1], v4[0][2], v4[0][3]);
+        gather_fetch(rf1, gt, v4[1][0], v4[1][1], v4[1][2], v4[1][3]);
+        gather_fetch(rf2, gt, v4[2][0], v4[2][1], v4[2][2], v4[2][3]);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { ps[k].ddx[c] = 0.f; ps[k].ddy[c] = 0.f; }
-        float wv[3] = {0.f, 0.f, 0.f};
-        if ((yy | xx) >= 0) {
-          const int o = yy * w + xx;
-          float fx = __fmul_rn(S.sx, __ldg(flx + o)), fy = __fmul_rn(S.sy, __ldg(fly + o));
-          WarpCoord wc = warp_coord((float)xx, (float)yy, fx, fy, S.geom);
-          Bilin bl = bilinear_setup(wc.ix, wc.iy, h, w);
-          ps[k].valid = wc.valid;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float nw, ne, sw, se;
-            bilinear_fetch(rf + c * hw, w, bl, nw, ne, sw, se);
-            wv[c] = bilinear_value(bl, nw, ne, sw, se);
-            if (real) {
-              bilinear_deriv(bl, nw, ne, sw, se, ps[k].ddx[c], ps[k].ddy[c]);
-              float df = fabsf(sm.T[c * R2N + i2] - wv[c]);
-              df = wc.valid ? df : 0.f;
-              acc[SL_L1] += df;
-              if (S.warped[pair]) S.warped[pair][((size_t)b * 3 + c) * hw + o] = wv[c];
-              if (S.diff[pair]) S.diff[pair][((size_t)b * 3 + c) * hw + o] = df;
-            }
+        for (int c = 0; c < 3; ++c) {
+          const float wv = gather_value(gt, v4[c][0], v4[c][1], v4[c][2], v4[c][3]) * okf;
+          gather_deriv(gt, v4[c][0], v4[c][1], v4[c][2], v4[c][3], ps[k].ddx[c], ps[k].ddy[c]);
+          sm.W[c * R2N + i2] = wv;
+          float df = fabsf(sm.T[c * R2N + i2] - wv);
+          df = ps[k].valid ? df : 0.f;
+          acc[SL_L1] += df;
+          if (MAPS && real) {
+            if (S.warped[pair]) S.warped[pair][((size_t)b * 3 + c) * hw + o] = wv;
+            if (S.diff[pair]) S.diff[pair][((size_t)b * 3 + c) * hw + o] = df;
           }
-          if (real && S.valid[pair]) S.valid[pair][(size_t)b * hw + o] = wc.valid ? 1 : 0;
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sm.W[c * R2N + i2] = wv[c];
+        if (MAPS && real && S.valid[pair]) S.valid[pair][(size_t)b * hw + o] = wc.valid ? 1 : 0;
       }
       // -- P1b: the halo ring
-      for (int j = tid; j < RING; j += nthr) {
+      if (tid < RING) {
         int ry, rx;
-        ring_slot(j, ry, rx);
+        ring_slot(tid, ry, rx);
         const int i2 = ry * R2W + rx;
         const int yy = stage_index(y0 - 2 + ry, h), xx = stage_index(x0 - 2 + rx, w);
-        float wv[3] = {0.f, 0.f, 0.f};
-        if ((yy | xx) >= 0) {
-          const int o = yy * w + xx;
-          float fx = __fmul_rn(S.sx, __ldg(flx + o)), fy = __fmul_rn(S.sy, __ldg(fly + o));
-          WarpCoord wc = warp_coord((float)xx, (float)yy, fx, fy, S.geom);
-          Bilin bl = bilinear_setup(wc.ix, wc.iy, h, w);
+        const bool ok = (yy | xx) >= 0;
+        const int o = ok ? yy * w + xx : 0;
+        float fx = __fmul_rn(S.sx, __ldg(flx + o)), fy = __fmul_rn(S.sy, __ldg(fly + o));
+        WarpCoord wc = warp_coord((float)xx, (float)yy, fx, fy, S.geom);
+        Gather4 gt = gather_setup(wc.ix, wc.iy, h, w);
+        const float okf = ok ? 1.f : 0.f;
+        float v4[3][4];
+        gather_fetch(rf, gt, v4[0][0], v4[0][1], v4[0][2], v4[0][3]);
+        gather_fetch(rf1, gt, v4[1][0], v4[1][1], v4[1][2], v4[1][3]);
+        gather_fetch(rf2, gt, v4[2][0], v4[2][1], v4[2][2], v4[2][3]);
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float nw, ne, sw, se;
-            bilinear_fetch(rf + c * hw, w, bl, nw, ne, sw, se);
-            wv[c] = bilinear_value(bl, nw, ne, sw, se);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sm.W[c * R2N + i2] = wv[c];
+        for (int c = 0; c < 3; ++c) sm.W[c * R2N + i2] = gather_value(gt, v4[c][0], v4[c][1], v4[c][2], v4[c][3]) * okf;
       }
       __syncthreads();
 
@@ -230,17 +246,16 @@ __global__ void __launch_bounds__(NTHREADS, PHOTO ? 3 : 4) fused_tile_kernel(con
               const int rw = 3 * g + q;                 // window row in the halo-1 region
               const int wy = y0 - 1 + rw;
               const int i1 = rw * R1W + cw;
-              float A = 0.f, Bc = 0.f, Cc = 0.f;
-              if (colok & (wy >= 0) & (wy < h)) {
-                SsimOut so = ssim_window(hx[q] + hx[q + 1] + hx[q + 2], hy[q] + hy[q + 1] + hy[q + 2],
-                                         hxx[q] + hxx[q + 1] + hxx[q + 2], hyy[q] + hyy[q + 1] + hyy[q + 2],
-                                         hxy[q] + hxy[q + 1] + hxy[q + 2], grads);
-                if (col_interior & (rw >= 1) & (rw <= TH)) {
-                  acc[SL_SSIM] += so.J;
-                  if (S.ssim_map[pair]) S.ssim_map[pair][((size_t)b * 3 + c) * hw + wy * w + wx] = so.J;
-                }
-                A = k9 * so.dmu_y; Bc = k9 * 2.f * so.dY2; Cc = k9 * so.dXY;
-              }
+              // branch free: windows outside the image are evaluated on zeros and masked out
+              const bool inimg = colok & (wy >= 0) & (wy < h);
+              const bool inter = inimg & col_interior & (rw >= 1) & (rw <= TH);
+              SsimOut so = ssim_window(hx[q] + hx[q + 1] + hx[q + 2], hy[q] + hy[q + 1] + hy[q + 2],
+                                       hxx[q] + hxx[q + 1] + hxx[q + 2], hyy[q] + hyy[q + 1] + hyy[q + 2],
+                                       hxy[q] + hxy[q + 1] + hxy[q + 2], grads);
+              acc[SL_SSIM] += inter ? so.J : 0.f;
+              if (MAPS && inter && S.ssim_map[pair]) S.ssim_map[pair][((size_t)b * 3 + c) * hw + wy * w + wx] = so.J;
+              const float kk = inimg ? k9 : 0.f;
+              const float A = kk * so.dmu_y, Bc = kk * 2.f * so.dY2, Cc = kk * so.dXY;
               sm.ABC[(3 * c + 0) * R1N + i1] = A;
               sm.ABC[(3 * c + 1) * R1N + i1] = Bc;
               sm.ABC[(3 * c + 2) * R1N + i1] = Cc;
@@ -277,23 +292,13 @@ __global__ void __launch_bounds__(NTHREADS, PHOTO ? 3 : 4) fused_tile_kernel(con
           const float wv[2] = {sm.W[c * R2N + i2], sm.W[c * R2N + i2 + R2W]};
           if (use_ssim) {
             float S3[2][3];
+            const float* Q = sm.ABC + (3 * c) * R1N + ly0 * R1W + lx;   // halo-1 rows ly0 .. ly0+3, cols lx .. lx+2
+            if (border) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-              const float* Q = sm.ABC + (3 * c + a) * R1N + ly0 * R1W + lx;   // halo-1 rows ly0 .. ly0+3, cols lx .. lx+2
-              float H[4];
+              for (int a = 0; a < 3; ++a) adjoint_box<true>(Q + a * R1N, wxm, wym, S3[0][a], S3[1][a]);
+            } else {
 #pragma unroll
-              for (int rr = 0; rr < 4; ++rr) {
-                float q0 = Q[rr * R1W], q1 = Q[rr * R1W + 1], q2 = Q[rr * R1W + 2];
-                H[rr] = border ? (wxm[0] * q0 + wxm[1] * q1 + wxm[2] * q2) : (q0 + q1 + q2);
-              }
-              if (border) {
-                S3[0][a] = wym[0][0] * H[0] + wym[0][1] * H[1] + wym[0][2] * H[2];
-                S3[1][a] = wym[1][0] * H[1] + wym[1][1] * H[2] + wym[1][2] * H[3];
-              } else {
-                float mid = H[1] + H[2];
-                S3[0][a] = H[0] + mid;
-                S3[1][a] = mid + H[3];
-              }
+              for (int a = 0; a < 3; ++a) adjoint_box<false>(Q + a * R1N, wxm, wym, S3[0][a], S3[1][a]);
             }
 #pragma unroll
             for (int k = 0; k < 2; ++k) wb[k] = S3[k][0] + wv[k] * S3[k][1] + tv[k] * S3[k][2];
@@ -347,8 +352,8 @@ __global__ void __launch_bounds__(NTHREADS, PHOTO ? 3 : 4) fused_tile_kernel(con
             acc[SL_CE] += -(kmask * l1 + (1.f - kmask) * l0);
             mb += S.c_ce * (__fdividef(1.f - kmask, bg + 1e-10f) - __fdividef(kmask, m + 1e-10f));
           }
-          if (S.post_map[pair]) S.post_map[pair][(size_t)b * hw + o] = post;
-          if (S.ori_map[pair]) S.ori_map[pair][(size_t)b * hw + o] = (P.post == MDN_POST_SN) ? __fdiv_rn(ae, snmax) : ae;
+          if (MAPS && S.post_map[pair]) S.post_map[pair][(size_t)b * hw + o] = post;
+          if (MAPS && S.ori_map[pair]) S.ori_map[pair][(size_t)b * hw + o] = (P.post == MDN_POST_SN) ? __fdiv_rn(ae, snmax) : ae;
           if (grads) {
             mb += -S.c_epi * post + S.c_nt * signf_(ml) * (lg - __fdividef(m, bg + 1e-5f));
             if (mslot) mbar[k][1] += mb; else mbar[k][0] += mb;

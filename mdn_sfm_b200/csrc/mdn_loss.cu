@@ -689,8 +689,17 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
   const bool photo = (d->flags & MDN_TERM_PHOTO) != 0;
   const size_t smem = fused_smem_floats(photo, NTHREADS / 32) * sizeof(float);
   static_assert(fused_smem_floats(true, NTHREADS / 32) * sizeof(float) <= 48 * 1024, "fits the default dynamic smem limit");
-  if (photo) MDN_LAUNCH(fused_tile_kernel<true>, dim3(K.n_tiles), dim3(NTHREADS), smem, stream, K);
-  else MDN_LAUNCH(fused_tile_kernel<false>, dim3(K.n_tiles), dim3(NTHREADS), smem, stream, K);
+  bool maps = false;
+  for (int s = 0; s < d->n_scales; ++s)
+    for (int p = 0; p < 2; ++p) {
+      const MdnScale& S = d->scale[s];
+      maps |= S.post_map[p] || S.ori_map[p] || S.warped[p] || S.diff[p] || S.valid[p] || S.ssim_map[p];
+    }
+  const dim3 grid(K.n_tiles), block(NTHREADS);
+  if (photo && maps) { auto kfn = fused_tile_kernel<true, true>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
+  else if (photo) { auto kfn = fused_tile_kernel<true, false>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
+  else if (maps) { auto kfn = fused_tile_kernel<false, true>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
+  else { auto kfn = fused_tile_kernel<false, false>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
   MDN_LAUNCH(finish_kernel, dim3(d->n_scales * d->batch), dim3(FIN_ROWS * NSLOT), 0, stream, Q);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
