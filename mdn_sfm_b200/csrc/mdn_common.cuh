@@ -234,6 +234,22 @@ MDN_DEV int refl_mult(int p, int q, int n) {
   return c;
 }
 
+// 4-byte asynchronous global -> shared copy (LDGSTS); zero-fills when `pred` is false.  Completion: cp_async_wait_all().
+MDN_DEV void cp_async_f32(float* smem_dst, const float* gsrc, bool pred) {
+#ifdef MDN_EMU
+  *smem_dst = pred ? *gsrc : 0.f;
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+#endif
+}
+MDN_DEV void cp_async_wait_all() {
+#ifndef MDN_EMU
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
+
 MDN_DEV float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 MDN_DEV float signf_(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 

@@ -18,13 +18,13 @@ constexpr int RING = R2N - TN;   // halo slots of the halo-2 region
 struct Smem {
   float* T;      // [3][R2N] target image, reflection padded
   float* W;      // [3][R2N] warped source image (current pair), reflection padded
-  float* M;      // [2][R1N] mask used by pair 0 / 1 (MIN, SHARED: only [0])
+  float* M;      // [3][R1N] raw mobile maps 0 / 1 and, in MIN mode, their minimum
   float* ABC;    // [9][R1N] SSIM adjoint coefficients per window: (A,B,C) x 3 channels (current pair)
   float* red;    // [nwarps][NSLOT]
 };
 
 __host__ __device__ constexpr size_t fused_smem_floats(bool photo, int nwarps) {
-  return 3 * R2N + 2 * R1N + (size_t)nwarps * NSLOT + (photo ? 3 * R2N + 9 * R1N : 0);
+  return 3 * R2N + 3 * R1N + (size_t)nwarps * NSLOT + (photo ? 3 * R2N + 9 * R1N : 0);
 }
 
 template <int NV>
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_co
   {
     float* p = smem_raw;
     sm.T = p; p += 3 * R2N;
-    sm.M = p; p += 2 * R1N;
+    sm.M = p; p += 3 * R1N;
     sm.red = p; p += nwarps * NSLOT;
     sm.W = p; sm.ABC = p;
     if (PHOTO) { sm.W = p; p += 3 * R2N; sm.ABC = p; }
@@ -120,32 +120,42 @@ __global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_co
 
   for (int i = tid; i < nwarps * NSLOT; i += nthr) sm.red[i] = 0.f;
 
-  // ---- P0: stage the target image (halo 2, reflection padded) and the mask(s) (halo 1)
+  // ---- P0: stage the target image (halo 2, reflection padded) and the raw mobile maps (halo 1) with cp.async:
+  // no registers, no waiting -- the copies land while P1 computes coordinates and gathers the source image.
   if (need_tgt) {
     const float* tg = S.tgt + (size_t)b * 3 * hw;
-    for (int i = tid; i < R2N; i += nthr) {
-      int ry = i / R2W, rx = i - ry * R2W;
-      int yy = stage_index(y0 - 2 + ry, h), xx = stage_index(x0 - 2 + rx, w);
-      bool ok = (yy | xx) >= 0;
-      int o = yy * w + xx;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) sm.T[c * R2N + i] = ok ? __ldg(tg + c * hw + o) : 0.f;
+    for (int j = 0; j < (R2N + NTHREADS - 1) / NTHREADS; ++j) {
+      const int i = tid + j * NTHREADS;
+      if (i < R2N) {
+        const int ry = i / R2W, rx = i - ry * R2W;
+        const int yy = stage_index(y0 - 2 + ry, h), xx = stage_index(x0 - 2 + rx, w);
+        const bool ok = (yy | xx) >= 0;
+        const float* src = tg + (ok ? yy * w + xx : 0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cp_async_f32(sm.T + c * R2N + i, src + c * hw, ok);
+      }
     }
   }
   if (need_mask) {
     const float* m0 = S.mob[0] + (size_t)b * hw;
     const float* m1 = shared_mask ? m0 : S.mob[1] + (size_t)b * hw;
-    for (int i = tid; i < R1N; i += nthr) {
-      int ry = i / R1W, rx = i - ry * R1W;
-      int y = y0 - 1 + ry, x = x0 - 1 + rx;
-      bool in = (y >= 0) & (y < h) & (x >= 0) & (x < w);
-      float a0 = 0.f, a1 = 0.f;
-      if (in) { a0 = __ldg(m0 + y * w + x); a1 = shared_mask ? a0 : __ldg(m1 + y * w + x); }
-      if (own) { sm.M[i] = a0; sm.M[R1N + i] = a1; }
-      else { sm.M[i] = (a0 <= a1) ? a0 : a1; }   // torch.min(dim): first index on ties
+#pragma unroll
+    for (int j = 0; j < (R1N + NTHREADS - 1) / NTHREADS; ++j) {
+      const int i = tid + j * NTHREADS;
+      if (i < R1N) {
+        const int ry = i / R1W, rx = i - ry * R1W;
+        const int y = y0 - 1 + ry, x = x0 - 1 + rx;
+        const bool in = (y >= 0) & (y < h) & (x >= 0) & (x < w);
+        const int o = in ? y * w + x : 0;
+        cp_async_f32(sm.M + i, m0 + o, in);
+        if (!shared_mask) cp_async_f32(sm.M + R1N + i, m1 + o, in);
+      }
     }
   }
-  __syncthreads();
+  // which plane the 3x3 / stencil reads of a pair use: its own map (OWN), the given map (SHARED) or the minimum (MIN)
+  const float* Mmin = (own | shared_mask) ? sm.M : sm.M + 2 * R1N;
+  bool staged = false;   // cp.async copies completed, minimum plane built, block synchronised
 
   float mbar[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [pixel][mask slot] accumulated d(loss)/d(mask)
 
@@ -157,27 +167,47 @@ __global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_co
     const float* flx = S.flow[pair] + (size_t)b * 2 * hw;
     const float* fly = flx + hw;
     const int mslot = own ? pair : 0;
-    const float* Mp = sm.M + mslot * R1N;
+    const float* Mp = own ? sm.M + pair * R1N : Mmin;
     PixState ps[2];
+    float pfx[2] = {0.f, 0.f}, pfy[2] = {0.f, 0.f};   // pixel flow of the two own pixels (P1 -> P3)
 
     if (PHOTO) {
       const float* rf = S.ref[pair] + (size_t)b * 3 * hw;
-      // -- P1a: the thread's own two pixels (real pixels when inside the image, reflected copies otherwise)
+      // -- P1: flow -> coordinates -> bilinear gather for the thread's three halo-2 slots: its own two pixels (real
+      // pixels when inside the image, reflected copies otherwise) and one slot of the halo ring.  All six flow loads
+      // are issued before the first use, then the 12 gathers of each slot are in flight together.
       const float* rf1 = rf + hw;
       const float* rf2 = rf1 + hw;
+      int so[3], si2[3], sxx[3], syy[3];
+      bool sok[3];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const int ly = ly0 + k, y = y0 + ly;
-        const int i2 = (ly + 2) * R2W + lx + 2;
-        const int yy = stage_index(y, h), xx = stage_index(px, w);
-        const bool real = (y < h) & col_in;
-        const bool ok = (yy | xx) >= 0;
-        const int o = ok ? yy * w + xx : 0;
-        float fx = __fmul_rn(S.sx, __ldg(flx + o)), fy = __fmul_rn(S.sy, __ldg(fly + o));
-        WarpCoord wc = warp_coord((float)xx, (float)yy, fx, fy, S.geom);
+        syy[k] = stage_index(y0 + ly0 + k, h); sxx[k] = stage_index(px, w);
+        si2[k] = (ly0 + k + 2) * R2W + lx + 2;
+      }
+      {
+        int ry, rx;
+        ring_slot(tid < RING ? tid : 0, ry, rx);
+        syy[2] = stage_index(y0 - 2 + ry, h); sxx[2] = stage_index(x0 - 2 + rx, w);
+        si2[2] = ry * R2W + rx;
+      }
+      float ffx[3], ffy[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        sok[k] = (syy[k] | sxx[k]) >= 0;
+        so[k] = sok[k] ? syy[k] * w + sxx[k] : 0;
+        ffx[k] = __ldg(flx + so[k]); ffy[k] = __ldg(fly + so[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (k == 2 && tid >= RING) break;
+        const bool real = (k < 2) && (y0 + ly0 + k < h) && col_in;
+        const float fx = __fmul_rn(S.sx, ffx[k]), fy = __fmul_rn(S.sy, ffy[k]);
+        if (k < 2) { pfx[k] = fx; pfy[k] = fy; }
+        WarpCoord wc = warp_coord((float)sxx[k], (float)syy[k], fx, fy, S.geom);
         Gather4 gt = gather_setup(wc.ix, wc.iy, h, w);
-        ps[k].valid = wc.valid & real;
-        const float okf = ok ? 1.f : 0.f;
+        if (k < 2) ps[k].valid = wc.valid & real;
+        const float okf = sok[k] ? 1.f : 0.f;
         float v4[3][4];
         gather_fetch(rf, gt, v4[0][0], v4[0][1], v4[0][2], v4[0][3]);
         gather_fetch(rf1, gt, v4[1][0], v4[1][1], v4[1][2], v4[1][3]);
@@ -185,36 +215,22 @@ __global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_co
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float wv = gather_value(gt, v4[c][0], v4[c][1], v4[c][2], v4[c][3]) * okf;
-          gather_deriv(gt, v4[c][0], v4[c][1], v4[c][2], v4[c][3], ps[k].ddx[c], ps[k].ddy[c]);
-          sm.W[c * R2N + i2] = wv;
-          float df = fabsf(sm.T[c * R2N + i2] - wv);
-          df = ps[k].valid ? df : 0.f;
-          acc[SL_L1] += df;
-          if (MAPS && real) {
-            if (S.warped[pair]) S.warped[pair][((size_t)b * 3 + c) * hw + o] = wv;
-            if (S.diff[pair]) S.diff[pair][((size_t)b * 3 + c) * hw + o] = df;
+          if (k < 2) gather_deriv(gt, v4[c][0], v4[c][1], v4[c][2], v4[c][3], ps[k].ddx[c], ps[k].ddy[c]);
+          sm.W[c * R2N + si2[k]] = wv;
+          if (MAPS && real && S.warped[pair]) S.warped[pair][((size_t)b * 3 + c) * hw + so[k]] = wv;
+        }
+        if (MAPS && real && S.valid[pair]) S.valid[pair][(size_t)b * hw + so[k]] = wc.valid ? 1 : 0;
+      }
+      if (!staged) {   // first pair only: the staging copies must have landed before anybody reads T / M
+        cp_async_wait_all();
+        if (need_mask & !own & !shared_mask) {
+#pragma unroll
+          for (int j = 0; j < (R1N + NTHREADS - 1) / NTHREADS; ++j) {
+            const int i = tid + j * NTHREADS;   // the slots this thread staged itself
+            if (i < R1N) { const float a0 = sm.M[i], a1 = sm.M[R1N + i]; sm.M[2 * R1N + i] = (a0 <= a1) ? a0 : a1; }
           }
         }
-        if (MAPS && real && S.valid[pair]) S.valid[pair][(size_t)b * hw + o] = wc.valid ? 1 : 0;
-      }
-      // -- P1b: the halo ring
-      if (tid < RING) {
-        int ry, rx;
-        ring_slot(tid, ry, rx);
-        const int i2 = ry * R2W + rx;
-        const int yy = stage_index(y0 - 2 + ry, h), xx = stage_index(x0 - 2 + rx, w);
-        const bool ok = (yy | xx) >= 0;
-        const int o = ok ? yy * w + xx : 0;
-        float fx = __fmul_rn(S.sx, __ldg(flx + o)), fy = __fmul_rn(S.sy, __ldg(fly + o));
-        WarpCoord wc = warp_coord((float)xx, (float)yy, fx, fy, S.geom);
-        Gather4 gt = gather_setup(wc.ix, wc.iy, h, w);
-        const float okf = ok ? 1.f : 0.f;
-        float v4[3][4];
-        gather_fetch(rf, gt, v4[0][0], v4[0][1], v4[0][2], v4[0][3]);
-        gather_fetch(rf1, gt, v4[1][0], v4[1][1], v4[1][2], v4[1][3]);
-        gather_fetch(rf2, gt, v4[2][0], v4[2][1], v4[2][2], v4[2][3]);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sm.W[c * R2N + i2] = gather_value(gt, v4[c][0], v4[c][1], v4[c][2], v4[c][3]) * okf;
+        staged = true;
       }
       __syncthreads();
 
@@ -266,9 +282,35 @@ __global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_co
       }
     }
 
+    if (!PHOTO && !staged) {
+      cp_async_wait_all();
+      if (need_mask & !own & !shared_mask) {
+#pragma unroll
+        for (int j = 0; j < (R1N + NTHREADS - 1) / NTHREADS; ++j) {
+          const int i = tid + j * NTHREADS;
+          if (i < R1N) { const float a0 = sm.M[i], a1 = sm.M[R1N + i]; sm.M[2 * R1N + i] = (a0 <= a1) ? a0 : a1; }
+        }
+      }
+      staged = true;
+      __syncthreads();
+    }
     // -- P3: the thread's two pixels: photometric adjoint -> d/dflow, epipolar forward + adjoint
     {
       float gfx[2] = {0.f, 0.f}, gfy[2] = {0.f, 0.f};
+      if (PHOTO) {   // L1 term: |tgt - warped| * valid  (loss_functions.py:109-110)
+        const int i2 = (ly0 + 2) * R2W + lx + 2;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float df = fabsf(sm.T[c * R2N + i2 + k * R2W] - sm.W[c * R2N + i2 + k * R2W]);
+            df = ps[k].valid ? df : 0.f;     // valid already implies "real pixel"
+            acc[SL_L1] += df;
+            if (MAPS && S.diff[pair] && (y0 + ly0 + k < h) && col_in)
+              S.diff[pair][((size_t)b * 3 + c) * hw + (y0 + ly0 + k) * w + px] = df;
+          }
+        }
+      }
       if (PHOTO && grads) {
         float wxm[3] = {1.f, 1.f, 1.f}, wym[2][3] = {{1.f, 1.f, 1.f}, {1.f, 1.f, 1.f}};
         if (border) {
@@ -332,8 +374,9 @@ __global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_co
         if (epi_on) {
           const float m = Mp[(ly + 1) * R1W + lx + 1];
           const float xf = (float)px, yf = (float)y;
-          float u = __fadd_rn(xf, __fmul_rn(S.sx, __ldg(flx + o)));
-          float v = __fadd_rn(yf, __fmul_rn(S.sy, __ldg(fly + o)));
+          float u, v;
+          if (PHOTO) { u = __fadd_rn(xf, pfx[k]); v = __fadd_rn(yf, pfy[k]); }
+          else { u = __fadd_rn(xf, __fmul_rn(S.sx, __ldg(flx + o))); v = __fadd_rn(yf, __fmul_rn(S.sy, __ldg(fly + o))); }
           Epi e = epipolar_distance(Fm, xf, yf, u, v);
           float ae = fabsf(e.d);
           float dpost;
@@ -387,8 +430,6 @@ __global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_co
     const int n_masks = own ? P.n_pairs : 1;
     // in MIN / SHARED mode the reference evaluates smooth_loss once per source frame with the SAME mask
     const float rep = own ? 1.f : (float)P.n_pairs;
-    const float* m0g = S.mob[0] + (size_t)b * hw;
-    const float* m1g = shared_mask ? m0g : S.mob[1] + (size_t)b * hw;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int ly = ly0 + k, y = y0 + ly;
@@ -414,7 +455,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_co
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           if (q < n_masks) {
-            const float* Mk = sm.M + q * R1N;
+            const float* Mk = own ? sm.M + q * R1N : Mmin;
             float mc = Mk[i1];
             float dr = mc - Mk[i1 + 1], dl = Mk[i1 - 1] - mc, dd = mc - Mk[i1 + R1W], du = Mk[i1 - R1W] - mc;
             acc[SL_SMX + 2 * q] += fabsf(dr) * ex_r;   // ex_r == 0 at the last column
@@ -423,7 +464,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_co
           }
         }
       }
-      float a0 = __ldg(m0g + o), a1 = __ldg(m1g + o);
+      const float a0 = sm.M[i1], a1 = shared_mask ? a0 : sm.M[R1N + i1];   // raw maps at this pixel
       float g0, g1;
       if (own) { g0 = mbar[k][0]; g1 = mbar[k][1]; }
       else if (shared_mask) { g0 = mbar[k][0]; g1 = 0.f; }
