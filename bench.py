@@ -375,9 +375,10 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
                         "path": "mdn_sfm_b200.loss_functions.Loss.forward + backward (eager public API), pinned host inputs"},
-                "gpu_launches": 3 * args.steps,
-                "launches_per_step": "mdn::fused_tile_kernel, mdn::finish_kernel, mdn::scale_grads_kernel (+1 memset node, "
-                                     "+ torch's tiny F-matrix ops)",
+                "gpu_launches": 5 * args.steps,
+                "launches_per_step": "mdn::fundamental_fwd_kernel, mdn::fused_tile_kernel, mdn::finish_kernel, "
+                                     "mdn::scale_grads_kernel, mdn::fundamental_bwd_kernel (+1 memset node and torch's "
+                                     "ones_like fill for the upstream gradient)",
                 "roofline": roofline, "cpu_baseline": cpu_base}
         print(json.dumps(line), flush=True)
     if world > 1:

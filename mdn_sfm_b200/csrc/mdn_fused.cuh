@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_co
           const bool colok = (wx >= 0) & (wx < w);
           const bool col_interior = (cw >= 1) & (cw <= TW);
           const float k9 = S.c_ssim * (1.f / 9.f);
-#pragma unroll
+#pragma unroll 1   // keep the body once in the instruction cache: the kernel is fetch-sensitive (4 CTAs in 4 different phases)
           for (int c = 0; c < 3; ++c) {
             const float* Tc = sm.T + c * R2N + (3 * g) * R2W + cw;
             const float* Wc = sm.W + c * R2N + (3 * g) * R2W + cw;
