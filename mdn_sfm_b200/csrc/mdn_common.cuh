@@ -171,6 +171,105 @@ MDN_DEV void gather_deriv(const Gather4& g, float nw, float ne, float sw, float 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE-rn results per issue slot).  The FP32 pipe
+// does the same lane-operations per clock either way; what the packed forms save is ISSUE slots, which is what
+// bounds the fused kernel.  Every op is rn per half, never contracted, so results are
+// identical to the scalar __f*_rn forms.
+#ifdef MDN_EMU
+MDN_DEV float2 add2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+MDN_DEV float2 mul2(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+MDN_DEV float2 fma2(float2 a, float2 b, float2 c) { return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
+MDN_DEV float rcp_fast(float x) { return 1.0f / x; }
+MDN_DEV float ex2_fast(float x) { return exp2f(x); }
+MDN_DEV float lg2_fast(float x) { return log2f(x); }
+#else
+MDN_DEV float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+MDN_DEV float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+MDN_DEV float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+MDN_DEV float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+MDN_DEV float ex2_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+MDN_DEV float lg2_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
+MDN_DEV float2 splat2(float a) { return make_float2(a, a); }
+MDN_DEV float2 ld2s(const float* p) { return *reinterpret_cast<const float2*>(p); }     // 8-byte aligned
+MDN_DEV void st2s(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+
+// ---------------------------------------------------------------------------------------------------
+// Two horizontally adjacent output pixels of the flow warp at once (packed fp32x2): the coordinate chain of
+// warp_coord() with the same roundings (2 g - 1 and (g + 1) / 2 * (n - 1) need one rounding each because the
+// doubling / halving is exact), the bilinear footprint with the zero padding folded into the FRACTIONS (a masked
+// fraction zeroes both the value weight and the derivative coefficient of its corners), values and
+// d(value)/d(ix, iy) of the three channels.  Corner addresses are clamped into the plane, so every load is legal
+// and the 24 loads of a pixel pair are in flight together.
+struct Gather2 {
+  float2 val[3];      // warped value, channel c   (x = first pixel, y = second)
+  float2 dx[3], dy[3];
+  bool valid_a, valid_b;
+};
+
+template <bool DERIV>
+MDN_DEV void gather_pair(const float* __restrict__ rf, int hw, int h, int w, float2 xs, float2 ys, float2 fx, float2 fy,
+                         const WarpGeom& G, Gather2& out) {
+  const float2 one = splat2(1.f), neg1 = splat2(-1.f), two = splat2(2.f);
+  const float2 px = add2(xs, fx), py = add2(ys, fy);
+  float2 gx, gy;
+  if (G.cuda_arith) { gx = mul2(px, splat2(G.inv_wm1)); gy = mul2(py, splat2(G.inv_hm1)); }
+  else {
+    gx = make_float2(__fdiv_rn(px.x, G.wm1), __fdiv_rn(px.y, G.wm1));
+    gy = make_float2(__fdiv_rn(py.x, G.hm1), __fdiv_rn(py.y, G.hm1));
+  }
+  gx = fma2(two, gx, neg1);                     // loss_utils.py:31
+  gy = fma2(two, gy, neg1);
+  out.valid_a = (fabsf(gx.x) <= 1.f) & (fabsf(gy.x) <= 1.f);
+  out.valid_b = (fabsf(gx.y) <= 1.f) & (fabsf(gy.y) <= 1.f);
+  const float2 ix = mul2(add2(gx, one), splat2(0.5f * G.wm1));   // grid_sample un-normalisation, align_corners=True
+  const float2 iy = mul2(add2(gy, one), splat2(0.5f * G.hm1));
+  const float2 x0f = make_float2(floorf(ix.x), floorf(ix.y)), y0f = make_float2(floorf(iy.x), floorf(iy.y));
+  float2 ax1 = fma2(x0f, neg1, ix), ax0 = fma2(ix, neg1, add2(x0f, one));
+  float2 ay1 = fma2(y0f, neg1, iy), ay0 = fma2(iy, neg1, add2(y0f, one));
+  int o00[2], o01[2], o10[2], o11[2];
+  float mx0[2], mx1[2], my0[2], my1[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int x0 = min(max(__float2int_rd(e ? ix.y : ix.x), -2), w), y0 = min(max(__float2int_rd(e ? iy.y : iy.x), -2), h);
+    const int x1 = x0 + 1, y1 = y0 + 1;
+    const bool bx0 = (unsigned)x0 < (unsigned)w, bx1 = (unsigned)x1 < (unsigned)w;
+    const bool by0 = (unsigned)y0 < (unsigned)h, by1 = (unsigned)y1 < (unsigned)h;
+    const int cx0 = bx0 ? x0 : 0, cx1 = bx1 ? x1 : 0;
+    const int r0 = (by0 ? y0 : 0) * w, r1 = (by1 ? y1 : 0) * w;
+    o00[e] = r0 + cx0; o01[e] = r0 + cx1; o10[e] = r1 + cx0; o11[e] = r1 + cx1;
+    mx0[e] = bx0 ? 1.f : 0.f; mx1[e] = bx1 ? 1.f : 0.f; my0[e] = by0 ? 1.f : 0.f; my1[e] = by1 ? 1.f : 0.f;
+  }
+  const float2 fx0 = make_float2(mx0[0], mx0[1]), fx1 = make_float2(mx1[0], mx1[1]);
+  const float2 fy0 = make_float2(my0[0], my0[1]), fy1 = make_float2(my1[0], my1[1]);
+  ax0 = mul2(ax0, fx0); ax1 = mul2(ax1, fx1); ay0 = mul2(ay0, fy0); ay1 = mul2(ay1, fy1);
+  const float2 w00 = mul2(ax0, ay0), w01 = mul2(ax1, ay0), w10 = mul2(ax0, ay1), w11 = mul2(ax1, ay1);
+  float2 cx00, cx01, cx10, cx11, cy00, cy01, cy10, cy11;
+  if (DERIV) {
+    const float2 nfx0 = mul2(fx0, neg1), nfy0 = mul2(fy0, neg1);
+    cx00 = mul2(ay0, nfx0); cx01 = mul2(ay0, fx1); cx10 = mul2(ay1, nfx0); cx11 = mul2(ay1, fx1);
+    cy00 = mul2(ax0, nfy0); cy01 = mul2(ax1, nfy0); cy10 = mul2(ax0, fy1); cy11 = mul2(ax1, fy1);
+  }
+  float2 v00[3], v01[3], v10[3], v11[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* pl = rf + (size_t)c * hw;
+    v00[c] = make_float2(__ldg(pl + o00[0]), __ldg(pl + o00[1]));
+    v01[c] = make_float2(__ldg(pl + o01[0]), __ldg(pl + o01[1]));
+    v10[c] = make_float2(__ldg(pl + o10[0]), __ldg(pl + o10[1]));
+    v11[c] = make_float2(__ldg(pl + o11[0]), __ldg(pl + o11[1]));
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    out.val[c] = fma2(v11[c], w11, fma2(v10[c], w10, fma2(v01[c], w01, mul2(v00[c], w00))));
+    if (DERIV) {
+      out.dx[c] = fma2(v11[c], cx11, fma2(v10[c], cx10, fma2(v01[c], cx01, mul2(v00[c], cx00))));
+      out.dy[c] = fma2(v11[c], cy11, fma2(v10[c], cy10, fma2(v01[c], cy01, mul2(v00[c], cy00))));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // SSIM, networks/layers.py:164-178, from the five 3x3 window SUMS (reflect padding applied by the caller).
 struct SsimOut {
   float J;            // clamp((1 - n/d)/2, 0, 1)
@@ -221,6 +320,41 @@ MDN_DEV SsimOut ssim_window(float sx, float sy, float sxx, float syy, float sxy,
   return o;
 }
 
+// Two windows at once (packed fp32x2), used by the fused kernel.  kk = c_ssim / 9 per window, or 0 for a window
+// outside the image.  Returns J = clamp((1 - n/D) / 2, 0, 1) and the adjoint coefficients of
+//   d(sum_w k_w J_w) / d(warped tap y) = A + B * y + C * x        (x = target tap)
+// i.e. A = kk dJ/dmu_y, B = 2 kk dJ/dE[y^2], C = kk dJ/dE[xy].  sigma = E[.^2] - mu^2 keeps the reference's two
+// roundings (fma(-1, m, t) rounds t - m once, t already rounded).
+struct Ssim2 { float2 J, A, B, C; };
+
+MDN_DEV Ssim2 ssim_window2(float2 sx, float2 sy, float2 sxx, float2 syy, float2 sxy, float2 kk) {
+  const float2 r9 = splat2(0.111111111f), neg1 = splat2(-1.f), two = splat2(2.f);
+  const float2 C1 = splat2(0.0001f), C2 = splat2(0.0009f);
+  const float2 mx = mul2(sx, r9), my = mul2(sy, r9);
+  const float2 mxx = mul2(mx, mx), myy = mul2(my, my), mxy = mul2(mx, my);
+  const float2 vx = fma2(mxx, neg1, mul2(sxx, r9));
+  const float2 vy = fma2(myy, neg1, mul2(syy, r9));
+  const float2 cxy = fma2(mxy, neg1, mul2(sxy, r9));
+  const float2 n1 = fma2(two, mxy, C1), n2 = fma2(two, cxy, C2);
+  const float2 d1 = add2(add2(mxx, myy), C1), d2 = add2(add2(vx, vy), C2);
+  const float2 n = mul2(n1, n2), D = mul2(d1, d2);           // D >= C1 * C2 > 0
+  const float2 r = make_float2(rcp_fast(D.x), rcp_fast(D.y));
+  const float2 S = mul2(n, r);
+  Ssim2 o;
+  o.J.x = __saturatef(fmaf(S.x, -0.5f, 0.5f));               // (1 - S) / 2: the halving is exact
+  o.J.y = __saturatef(fmaf(S.y, -0.5f, 0.5f));
+  // clamp gate (inclusive, like clamp's backward): 0 <= (1 - S)/2 <= 1  <=>  |S| <= 1
+  const float2 kg = make_float2(fabsf(S.x) <= 1.f ? kk.x : 0.f, fabsf(S.y) <= 1.f ? kk.y : 0.f);
+  const float2 a = mul2(kg, r);                              // -2 kk dJ/dn
+  const float2 e = mul2(a, S);                               //  2 kk dJ/dD * (-1) ... e d2 = 2 kk dJ/dd1, e d1 = 2 kk dJ/dd2
+  const float2 t1 = mul2(a, fma2(n2, neg1, n1));             // 2 kk (dJ/dn1 - dJ/dn2) = a (n1 - n2)
+  const float2 t2 = mul2(e, fma2(d1, neg1, d2));             // 2 kk (dJ/dd1 - dJ/dd2)
+  o.A = fma2(my, t2, mul2(mx, t1));
+  o.B = mul2(e, d1);
+  o.C = mul2(a, mul2(n1, neg1));
+  return o;
+}
+
 MDN_DEV int reflect1(int t, int n) {   // ReflectionPad2d(1): -1 -> 1, n -> n-2
   t = t < 0 ? -t : t;
   return t >= n ? 2 * n - 2 - t : t;
@@ -242,6 +376,16 @@ MDN_DEV void cp_async_f32(float* smem_dst, const float* gsrc, bool pred) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   const int sz = pred ? 4 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+#endif
+}
+// 16-byte variant (both addresses 16-byte aligned); zero-fills when `pred` is false
+MDN_DEV void cp_async_f32x4(float* smem_dst, const float* gsrc, bool pred) {
+#ifdef MDN_EMU
+  for (int i = 0; i < 4; ++i) smem_dst[i] = pred ? gsrc[i] : 0.f;
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 #endif
 }
 MDN_DEV void cp_async_wait_all() {

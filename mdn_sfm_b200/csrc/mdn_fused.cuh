@@ -1,37 +1,47 @@
 // mdn_fused.cuh -- the fused tile kernel.  Included by mdn_loss.cu INSIDE namespace mdn (after KParams).
 //
-// One CTA = one 32x16 tile of one sample at one scale; both (target, source) pairs are processed by the same CTA
-// so that d(loss)/d(mobile) is written exactly once.  Per pair:
-//   P1  flow -> sampling coordinates -> bilinear gather of the source image over the tile + 2-pixel halo, written to
-//       shared memory ALREADY reflection-padded (slot -1 holds pixel 1, slot h holds pixel h-2), so every 3x3 window
-//       below is a plain box; the two pixels a thread owns keep d(warped)/d(ix,iy) and the validity bit in registers
-//   P2  SSIM over the tile + 1-pixel halo: each thread slides down 3 windows of one column, sharing the horizontal
-//       3-tap sums of 5 rows (separable box filter); writes the three adjoint coefficients (A,B,C) per channel
-//   P3  the thread's two vertically adjacent pixels: 3x3 adjoint gather (sharing 4 rows of horizontal sums), L1
-//       adjoint, chain rule to the flow; epipolar distance, post-processing, masked sums, their adjoints
-// then  P4 smoothness + consistency + routing of d/dmask through the min, and the block reduction of 40 partial sums.
+// One CTA (FT threads) = one TW x TH = 64x16 tile of one sample at one scale; both (target, source) pairs are
+// processed by the same CTA so that d(loss)/d(mobile) is written exactly once.  A thread owns a 2-column x PR-row
+// patch of pixels (lane = column pair, warp = row group): every global access is an 8-byte vector, every shared
+// memory access an LDS.64 / STS.64, and the arithmetic of the two columns is packed fp32x2 (FFMA2 / FADD2 / FMUL2).
+// Per-row loops are ROLLED: the kernel is issue- and instruction-fetch-bound, so code size is kept near 2.5 k
+// instructions; state that must survive a rolled loop lives in thread-private shared memory (sm.D) or rotates
+// through a register ring.
 //
-// The kernel is ISSUE-bound, not HBM-bound: everything here is about instruction count.
+// Shared memory (73 KB -> 3 CTAs per SM):
+//   sT [3][R2P]      target image, tile + 2-pixel halo, reflection padded (slot -1 holds pixel 1, slot n holds n-2)
+//   sW [3][R2P]      warped source image of the current pair, same layout
+//   sQ [3][R1P]      SSIM adjoint coefficient planes (A, B, C) of the current pair AND channel, tile + 1-pixel halo
+//   sD [6][PR][FT]   thread-private float2 slots: d(warped_c)/d(ix), d(warped_c)/d(iy) of the own pixels
+// Per pair:
+//   P1  one rolled loop over pixel PAIRS: the thread's PR own pairs, then its share of the halo ring.  flow ->
+//       sampling coordinates -> bilinear gather of the 3 source channels (gather_pair) -> sW; derivatives -> sD
+//   per channel c (rolled):
+//     P2  SSIM windows over the tile + 1-pixel halo in 2x3 patches: 3-tap row sums of (x, y, x^2, y^2, xy) for two
+//         columns from two LDS.64 per image row, a sliding column sum, two windows per packed evaluation
+//         (ssim_window2); writes the adjoint planes of channel c
+//     P3  the thread's own pixels: separable 3x3 adjoint gather of the three planes (packed), L1 term, chain rule
+//         to d(loss)/d(ix, iy)
+//   P4  rolled over rows: epipolar distance, post-processing, masked sums and their adjoints; d(loss)/d(flow)
+// then the tail (rolled over rows): smoothness + consistency + routing of d/dmask through the min; block reduction.
 
-constexpr int RING = R2N - TN;   // halo slots of the halo-2 region
-
-struct Smem {
-  float* T;      // [3][R2N] target image, reflection padded
-  float* W;      // [3][R2N] warped source image (current pair), reflection padded
-  float* M;      // [3][R1N] raw mobile maps 0 / 1 and, in MIN mode, their minimum
-  float* ABC;    // [9][R1N] SSIM adjoint coefficients per window: (A,B,C) x 3 channels (current pair)
-  float* red;    // [nwarps][NSLOT]
+struct FusedSmem {
+  float* T;      // [3][R2P]
+  float* W;      // [3][R2P]
+  float* Q;      // [3][R1P]
+  float* D;      // [6][PR][FT] float2
+  float* red;    // [FWARPS][NSLOT]
 };
 
-__host__ __device__ constexpr size_t fused_smem_floats(bool photo, int nwarps) {
-  return 3 * R2N + 3 * R1N + (size_t)nwarps * NSLOT + (photo ? 3 * R2N + 9 * R1N : 0);
+__host__ __device__ constexpr size_t fused_smem_floats(bool photo) {
+  return 3 * R2P + (size_t)FWARPS * NSLOT + (photo ? 3 * R2P + 3 * R1P + 6 * PR * FT * 2 : 0);
 }
 
 template <int NV>
 MDN_DEV void flush_acc(float* v, float* red, int slot_base) {
   warp_reduce_transpose<NV>(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane < NV) red[warp * NSLOT + slot_base + lane] = v[0];
+  if (lane < NV) red[warp * NSLOT + slot_base + lane] += v[0];
 }
 
 // image coordinate whose value a shared-memory slot at coordinate t holds (ReflectionPad2d(1)); -1 = none
@@ -41,42 +51,23 @@ MDN_DEV int stage_index(int t, int n) {
   return t;
 }
 
-// (ry, rx) of the j-th halo slot of the halo-2 region: two top rows, two bottom rows, then the side columns
-MDN_DEV void ring_slot(int j, int& ry, int& rx) {
-  if (j < 2 * R2W) { ry = j / R2W; rx = j - ry * R2W; }
-  else if (j < 4 * R2W) { j -= 2 * R2W; ry = j / R2W; rx = j - ry * R2W; ry += TH + 2; }
-  else { j -= 4 * R2W; ry = 2 + (j >> 2); int k = j & 3; rx = (k < 2) ? k : TW + k; }
+// (r, j) of the first pixel of the i-th PAIR of the halo ring of the halo-2 region: two top rows, two bottom rows
+// (S2 / 2 pairs each), then the two side pairs of every interior row
+constexpr int RINGP = 2 * S2 + 2 * TH;
+MDN_DEV void ring_pair(int i, int& r, int& j) {
+  constexpr int HP = S2 / 2;
+  if (i < 2 * HP) { r = i / HP; j = 2 * (i - r * HP); }
+  else if (i < 4 * HP) { i -= 2 * HP; r = i / HP; j = 2 * (i - r * HP); r += TH + 2; }
+  else { i -= 4 * HP; r = 2 + (i >> 1); j = (i & 1) ? TW + 2 : 0; }
 }
 
-struct PixState {          // what a thread keeps in registers about one of its two pixels, per pair
-  float ddx[3], ddy[3];    // d(warped_c)/d(ix), d(warped_c)/d(iy)
-  bool valid;
-};
-
-// 3x3 adjoint gather of one coefficient plane for the thread's two vertically adjacent pixels.  Q points at the
-// halo-1 slot (ly0, lx): rows ly0 .. ly0+3, columns lx .. lx+2.  BORDER applies the reflection multiplicities.
-template <bool BORDER>
-MDN_DEV void adjoint_box(const float* Q, const float* wxm, const float (*wym)[3], float& s0, float& s1) {
-  float H[4];
-#pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const float q0 = Q[rr * R1W], q1 = Q[rr * R1W + 1], q2 = Q[rr * R1W + 2];
-    H[rr] = BORDER ? (wxm[0] * q0 + wxm[1] * q1 + wxm[2] * q2) : (q0 + q1 + q2);
-  }
-  if (BORDER) {
-    s0 = wym[0][0] * H[0] + wym[0][1] * H[1] + wym[0][2] * H[2];
-    s1 = wym[1][0] * H[1] + wym[1][1] * H[2] + wym[1][2] * H[3];
-  } else {
-    const float mid = H[1] + H[2];
-    s0 = H[0] + mid;
-    s1 = mid + H[3];
-  }
-}
+MDN_DEV float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
 template <bool PHOTO, bool MAPS>
-__global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(const __grid_constant__ KParams P) {
   MDN_DYN_SMEM(smem_raw);
-  const int tid = threadIdx.x, nthr = blockDim.x, nwarps = nthr >> 5;
+  const int tid = threadIdx.x;
+  const int t = tid & 31, g = tid >> 5;    // column pair, row group (= warp)
   const bool use_ssim = PHOTO && (P.flags & MDN_OPT_SSIM);
   const bool epi_on = (P.flags & MDN_TERM_EPIPOLAR) != 0;
   const bool smooth_on = (P.flags & MDN_TERM_SMOOTH) != 0;
@@ -84,18 +75,16 @@ __global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_co
   const bool grads = (P.flags & MDN_OPT_GRADS) != 0;
   const bool own = P.mask_mode == MDN_MASK_OWN;
   const bool shared_mask = P.mask_mode == MDN_MASK_SHARED;
+  const bool minmode = !own && !shared_mask;
   const bool need_tgt = PHOTO || smooth_on;
   const bool need_mask = epi_on || smooth_on || consis_on;
 
-  Smem sm;
-  {
-    float* p = smem_raw;
-    sm.T = p; p += 3 * R2N;
-    sm.M = p; p += 3 * R1N;
-    sm.red = p; p += nwarps * NSLOT;
-    sm.W = p; sm.ABC = p;
-    if (PHOTO) { sm.W = p; p += 3 * R2N; sm.ABC = p; }
-  }
+  FusedSmem sm;
+  sm.T = smem_raw;
+  sm.red = sm.T + 3 * R2P;
+  sm.W = sm.red + FWARPS * NSLOT;
+  sm.Q = sm.W + 3 * R2P;
+  sm.D = sm.Q + 3 * R1P;
 
   // ---- which tile
   int s = 0;
@@ -103,390 +92,494 @@ __global__ void __launch_bounds__(NTHREADS, 4) fused_tile_kernel(const __grid_co
   for (int k = 1; k < MDN_MAX_SCALES; ++k)
     if (k < P.n_scales && (int)blockIdx.x >= P.sc[k].tile_begin) s = k;
   const KScale& S = P.sc[s];
-  int r = blockIdx.x - S.tile_begin;
+  int rem = blockIdx.x - S.tile_begin;
   const int tiles_per_img = S.tiles_x * S.tiles_y;
-  const int b = r / tiles_per_img;
-  r -= b * tiles_per_img;
-  const int ty = r / S.tiles_x, tx = r - ty * S.tiles_x;
+  const int b = rem / tiles_per_img;
+  rem -= b * tiles_per_img;
+  const int ty = rem / S.tiles_x, tx = rem - ty * S.tiles_x;
   const int x0 = tx * TW, y0 = ty * TH;
   const int h = S.h, w = S.w, hw = h * w;
   // tile holds a pixel whose 3x3 adjoint gather sees a reflected tap (rows 1, h-2 / columns 1, w-2)
   const bool border = (y0 == 0) | (h - 2 >= y0 && h - 2 < y0 + TH) | (x0 == 0) | (w - 2 >= x0 && w - 2 < x0 + TW);
 
-  // the two pixels this thread owns: same column, vertically adjacent
-  const int lx = tid & 31, ly0 = (tid >> 5) * 2;
-  const int px = x0 + lx;
-  const bool col_in = px < w;
+  // the 2 x PR pixels this thread owns
+  const int px0 = x0 + 2 * t, px1 = px0 + 1;
+  const int py0 = y0 + PR * g;
+  const bool in0 = px0 < w, in1 = px1 < w;
+  const bool weven = (w & 1) == 0;
+  const bool vec = weven & in1;             // 8-byte accesses at (row, px0): aligned and both columns inside
+  const int o2own = OFF2 + (PR * g + 2) * S2 + 2 * t + 2;   // halo-2 slot of the patch's first pixel
 
-  for (int i = tid; i < nwarps * NSLOT; i += nthr) sm.red[i] = 0.f;
+  for (int i = tid; i < FWARPS * NSLOT; i += FT) sm.red[i] = 0.f;
 
-  // ---- P0: stage the target image (halo 2, reflection padded) and the raw mobile maps (halo 1) with cp.async:
-  // no registers, no waiting -- the copies land while P1 computes coordinates and gathers the source image.
+  // ---- P0: stage the target image (halo 2, reflection padded) with cp.async; the copies land while P1 runs
   if (need_tgt) {
     const float* tg = S.tgt + (size_t)b * 3 * hw;
-#pragma unroll
-    for (int j = 0; j < (R2N + NTHREADS - 1) / NTHREADS; ++j) {
-      const int i = tid + j * NTHREADS;
-      if (i < R2N) {
-        const int ry = i / R2W, rx = i - ry * R2W;
-        const int yy = stage_index(y0 - 2 + ry, h), xx = stage_index(x0 - 2 + rx, w);
+    if (((w & 3) == 0) & (x0 + TW <= w)) {
+      // interior columns as 16-byte copies (global x0 + 4q and slot OFF2 + 2 + 4q are both 16-byte aligned)
+      for (int i = tid; i < 3 * R2H * (TW / 4); i += FT) {
+        const int c = i / (R2H * (TW / 4)), rr = i - c * (R2H * (TW / 4));
+        const int r = rr / (TW / 4), q = rr - r * (TW / 4);
+        const int yy = stage_index(y0 - 2 + r, h);
+        const bool ok = yy >= 0;
+        cp_async_f32x4(sm.T + c * R2P + OFF2 + r * S2 + 2 + 4 * q, tg + (size_t)c * hw + (ok ? yy * w : 0) + x0 + 4 * q, ok);
+      }
+      for (int i = tid; i < 3 * R2H * 4; i += FT) {
+        const int c = i / (R2H * 4), rr = i - c * (R2H * 4);
+        const int r = rr >> 2, k = rr & 3;
+        const int j = (k < 2) ? k : TW + k;
+        const int yy = stage_index(y0 - 2 + r, h), xx = stage_index(x0 - 2 + j, w);
+        const bool ok = (yy | xx) >= 0;
+        cp_async_f32(sm.T + c * R2P + OFF2 + r * S2 + j, tg + (size_t)c * hw + (ok ? yy * w + xx : 0), ok);
+      }
+    } else {
+      for (int i = tid; i < R2H * S2; i += FT) {
+        const int r = i / S2, j = i - r * S2;
+        const int yy = stage_index(y0 - 2 + r, h), xx = stage_index(x0 - 2 + j, w);
         const bool ok = (yy | xx) >= 0;
         const float* src = tg + (ok ? yy * w + xx : 0);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) cp_async_f32(sm.T + c * R2N + i, src + c * hw, ok);
+        for (int c = 0; c < 3; ++c) cp_async_f32(sm.T + c * R2P + OFF2 + i, src + (size_t)c * hw, ok);
       }
     }
   }
-  if (need_mask) {
-    const float* m0 = S.mob[0] + (size_t)b * hw;
-    const float* m1 = shared_mask ? m0 : S.mob[1] + (size_t)b * hw;
-#pragma unroll
-    for (int j = 0; j < (R1N + NTHREADS - 1) / NTHREADS; ++j) {
-      const int i = tid + j * NTHREADS;
-      if (i < R1N) {
-        const int ry = i / R1W, rx = i - ry * R1W;
-        const int y = y0 - 1 + ry, x = x0 - 1 + rx;
-        const bool in = (y >= 0) & (y < h) & (x >= 0) & (x < w);
-        const int o = in ? y * w + x : 0;
-        cp_async_f32(sm.M + i, m0 + o, in);
-        if (!shared_mask) cp_async_f32(sm.M + R1N + i, m1 + o, in);
-      }
-    }
-  }
-  // which plane the 3x3 / stencil reads of a pair use: its own map (OWN), the given map (SHARED) or the minimum (MIN)
-  const float* Mmin = (own | shared_mask) ? sm.M : sm.M + 2 * R1N;
-  bool staged = false;   // cp.async copies completed, minimum plane built, block synchronised
+  bool staged = false;   // cp.async copies completed and the block synchronised
 
-  float mbar[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [pixel][mask slot] accumulated d(loss)/d(mask)
+  // accumulated d(loss)/d(mask used by the pairs) of the own pixels; the rolled row loops rotate this ring
+  float2 mbar[PR];
+#pragma unroll
+  for (int k = 0; k < PR; ++k) mbar[k] = make_float2(0.f, 0.f);
+
+  const float* mob0 = need_mask ? S.mob[0] + (size_t)b * hw : nullptr;
+  const float* mob1 = need_mask ? (shared_mask ? mob0 : S.mob[1] + (size_t)b * hw) : nullptr;
+
+  // the two horizontally adjacent values at (y, px0), (y, px1) of a plane; 0 outside the image
+  auto load_pair = [&](const float* plane, int y) -> float2 {
+    if (!(((unsigned)y < (unsigned)h) & in0)) return make_float2(0.f, 0.f);
+    const float* p = plane + y * w + px0;
+    if (vec) return ldg2(p);
+    return make_float2(__ldg(p), in1 ? __ldg(p + 1) : 0.f);
+  };
+  auto store_pair = [&](float* plane, int y, float2 v) {   // caller guarantees y < h and in0
+    float* p = plane + y * w + px0;
+    if (vec) *reinterpret_cast<float2*>(p) = v;
+    else { p[0] = v.x; if (in1) p[1] = v.y; }
+  };
+  auto load_one = [&](const float* plane, int y, int x) -> float {
+    return (((unsigned)y < (unsigned)h) & ((unsigned)x < (unsigned)w)) ? __ldg(plane + y * w + x) : 0.f;
+  };
+
+  // ---- tail (per mask q): smoothness + consistency + routing of d/dmask to the mobile maps, rolled over the rows
+  // of the patch.  OWN mode calls it once per pair with that pair's own map, MIN / SHARED once after both pairs.
+  auto tail = [&](const int q) {
+    float acc[TAIL_SLOTS];
+#pragma unroll
+    for (int k = 0; k < TAIL_SLOTS; ++k) acc[k] = 0.f;
+    // in MIN / SHARED mode the reference evaluates smooth_loss once per source frame with the SAME mask
+    const float rep = own ? 1.f : (float)P.n_pairs;
+    const float cx = rep * S.c_smx, cy = rep * S.c_smy;
+    const float third_l2e = (1.f / 3.f) * 1.4426950408889634f;
+    const float* mq = (own && q) ? mob1 : mob0;     // first raw map the stencil reads
+    // raw maps of the row below the current one (the loop carries current / above), the stencil mask derived from them
+    float2 a0c = make_float2(0.f, 0.f), a1c = a0c, mc = a0c, mu = a0c;
+    float2 tc[3];
+    float2 evu = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tc[c] = make_float2(0.f, 0.f);
+    // iteration k works on row py0 + k with the rows above / below carried in registers; it loads row py0 + k + 1,
+    // so k = -2 and -1 only fill the pipeline (rows py0 - 1 and py0)
+#pragma unroll 1
+    for (int k = -2; k < PR; ++k) {
+      const int y = py0 + k;                        // current row; this iteration loads row y + 1
+      const float2 a0n = load_pair(mq, y + 1);
+      const float2 a1n = minmode ? load_pair(mob1, y + 1) : a0n;
+      const float2 mn = minmode ? make_float2((a0n.x <= a1n.x) ? a0n.x : a1n.x, (a0n.y <= a1n.y) ? a0n.y : a1n.y) : a0n;
+      float2 tn[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tn[c] = make_float2(0.f, 0.f);
+      float2 evd = make_float2(0.f, 0.f);           // vertical edge weights (y | y+1) of the two columns
+      if (smooth_on) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          tn[c] = ld2s(sm.T + c * R2P + o2own + (k + 1) * S2);
+          s0 += fabsf(tc[c].x - tn[c].x); s1 += fabsf(tc[c].y - tn[c].y);
+        }
+        const bool ok = (y >= 0) & (y + 1 < h);
+        evd.x = (ok & in0) ? ex2_fast(-s0 * third_l2e) : 0.f;
+        evd.y = (ok & in1) ? ex2_fast(-s1 * third_l2e) : 0.f;
+      }
+      if (k >= 0 && (y < h) & in0) {
+        float2 gm = mbar[0];
+        if (smooth_on) {
+          // horizontal edges (x-1|x), (x|x+1), (x+1|x+2) of this row
+          float sl = 0.f, smid = 0.f, sr = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float* Tr = sm.T + c * R2P + o2own + k * S2;
+            const float tl = Tr[-1], tr = Tr[2];
+            sl += fabsf(tl - tc[c].x); smid += fabsf(tc[c].x - tc[c].y); sr += fabsf(tc[c].y - tr);
+          }
+          const float e0 = (px0 > 0) ? ex2_fast(-sl * third_l2e) : 0.f;
+          const float e1 = in1 ? ex2_fast(-smid * third_l2e) : 0.f;
+          const float e2 = (px1 + 1 < w) ? ex2_fast(-sr * third_l2e) : 0.f;
+          float ml, mr;
+          if (minmode) {
+            const float l0 = load_one(mob0, y, px0 - 1), l1 = load_one(mob1, y, px0 - 1);
+            const float r0 = load_one(mob0, y, px1 + 1), r1 = load_one(mob1, y, px1 + 1);
+            ml = (l0 <= l1) ? l0 : l1; mr = (r0 <= r1) ? r0 : r1;
+          } else { ml = load_one(mq, y, px0 - 1); mr = load_one(mq, y, px1 + 1); }
+          // d0 = m(x-1) - m(x), d1 = m(x) - m(x+1), d2 = m(x+1) - m(x+2); each pixel counts its right / lower edge
+          const float d0 = ml - mc.x, d1 = mc.x - mc.y, d2 = mc.y - mr;
+          acc[SL_SMX + 2 * q] += fabsf(d1) * e1 + fabsf(d2) * e2;
+          const float s0 = signf_(d0) * e0, s1 = signf_(d1) * e1, s2 = signf_(d2) * e2;
+          const float u0 = mu.x - mc.x, u1 = mu.y - mc.y, n0 = mc.x - mn.x, n1 = mc.y - mn.y;
+          acc[SL_SMY + 2 * q] += fabsf(n0) * evd.x + fabsf(n1) * evd.y;
+          gm.x += cx * (s1 - s0) + cy * (signf_(n0) * evd.x - signf_(u0) * evu.x);
+          gm.y += cx * (s2 - s1) + cy * (signf_(n1) * evd.y - signf_(u1) * evu.y);
+        }
+        float2 g0, g1;
+        if (own) { g0 = q ? make_float2(0.f, 0.f) : gm; g1 = q ? gm : make_float2(0.f, 0.f); }
+        else if (shared_mask) { g0 = gm; g1 = make_float2(0.f, 0.f); }
+        else {
+          const bool f0 = a0c.x <= a1c.x, f1 = a0c.y <= a1c.y;
+          g0 = make_float2(f0 ? gm.x : 0.f, f1 ? gm.y : 0.f);
+          g1 = make_float2(f0 ? 0.f : gm.x, f1 ? 0.f : gm.y);
+        }
+        // raw maps of this row: (a0c, a1c) are (first map read, second) = (map q, -) in OWN mode
+        const float2 r0 = (own && q) ? (consis_on ? load_pair(mob0, y) : a0c) : a0c;
+        const float2 r1 = own ? (q ? a0c : (consis_on ? load_pair(mob1, y) : a0c)) : a1c;
+        if (consis_on) {
+          // sigmoid(20 (m - 0.5)) = 1 / (1 + 2^(-20 log2(e) (m - 0.5)))
+          const float kk = -20.f * 1.4426950408889634f;
+          const float p0 = rcp_fast(1.f + ex2_fast(kk * (r0.x - 0.5f))), q0 = rcp_fast(1.f + ex2_fast(kk * (r1.x - 0.5f)));
+          const float p1 = rcp_fast(1.f + ex2_fast(kk * (r0.y - 0.5f))), q1 = rcp_fast(1.f + ex2_fast(kk * (r1.y - 0.5f)));
+          const float df0 = p0 - q0, df1 = in1 ? p1 - q1 : 0.f;
+          // OWN mode visits every pixel once per map: count the value once, and give each map its own gradient
+          if (!own || q == 0) {
+            acc[SL_CONSIS] += df0 * df0 + df1 * df1;
+            g0.x += S.c_consis * 40.f * df0 * p0 * (1.f - p0);
+            g0.y += S.c_consis * 40.f * df1 * p1 * (1.f - p1);
+          }
+          if (!own || q == 1 || P.n_pairs == 1) {
+            g1.x -= S.c_consis * 40.f * df0 * q0 * (1.f - q0);
+            g1.y -= S.c_consis * 40.f * df1 * q1 * (1.f - q1);
+          }
+        }
+        if (grads) {
+          if (S.g_mob[0] && (!own || q == 0)) store_pair(S.g_mob[0] + (size_t)b * hw, y, g0);
+          if (S.g_mob[1] && !shared_mask && (!own || q == 1 || P.n_pairs == 1)) store_pair(S.g_mob[1] + (size_t)b * hw, y, g1);
+        }
+      }
+      if (k >= 0) {   // rotate the gradient ring (and clear it for the next use)
+#pragma unroll
+        for (int i = 0; i + 1 < PR; ++i) mbar[i] = mbar[i + 1];
+        mbar[PR - 1] = make_float2(0.f, 0.f);
+      }
+      mu = mc; mc = mn; a0c = a0n; a1c = a1n; evu = evd;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tc[c] = tn[c];
+    }
+    flush_acc<TAIL_SLOTS>(acc, sm.red, TAIL_BASE);
+  };
 
   // ---- per (target, source) pair
+#pragma unroll 1
   for (int pair = 0; pair < P.n_pairs; ++pair) {
     float acc[PAIR_SLOTS];
 #pragma unroll
     for (int k = 0; k < PAIR_SLOTS; ++k) acc[k] = 0.f;
     const float* flx = S.flow[pair] + (size_t)b * 2 * hw;
     const float* fly = flx + hw;
-    const int mslot = own ? pair : 0;
-    const float* Mp = own ? sm.M + pair * R1N : Mmin;
-    PixState ps[2];
-    float pfx[2] = {0.f, 0.f}, pfy[2] = {0.f, 0.f};   // pixel flow of the two own pixels (P1 -> P3)
+    float2 gix[PR], giy[PR];         // d(loss)/d(ix), d(loss)/d(iy) of the own pixels
+#pragma unroll
+    for (int k = 0; k < PR; ++k) { gix[k] = giy[k] = make_float2(0.f, 0.f); }
 
     if (PHOTO) {
       const float* rf = S.ref[pair] + (size_t)b * 3 * hw;
-      // -- P1: flow -> coordinates -> bilinear gather for the thread's three halo-2 slots: its own two pixels (real
-      // pixels when inside the image, reflected copies otherwise) and one slot of the halo ring.  All six flow loads
-      // are issued before the first use, then the 12 gathers of each slot are in flight together.
-      const float* rf1 = rf + hw;
-      const float* rf2 = rf1 + hw;
-      int so[3], si2[3], sxx[3], syy[3];
-      bool sok[3];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        syy[k] = stage_index(y0 + ly0 + k, h); sxx[k] = stage_index(px, w);
-        si2[k] = (ly0 + k + 2) * R2W + lx + 2;
-      }
-      {
-        int ry, rx;
-        ring_slot(tid < RING ? tid : 0, ry, rx);
-        syy[2] = stage_index(y0 - 2 + ry, h); sxx[2] = stage_index(x0 - 2 + rx, w);
-        si2[2] = ry * R2W + rx;
-      }
-      float ffx[3], ffy[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        sok[k] = (syy[k] | sxx[k]) >= 0;
-        so[k] = sok[k] ? syy[k] * w + sxx[k] : 0;
-        ffx[k] = __ldg(flx + so[k]); ffy[k] = __ldg(fly + so[k]);
-      }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (k == 2 && tid >= RING) break;
-        const bool real = (k < 2) && (y0 + ly0 + k < h) && col_in;
-        const float fx = __fmul_rn(S.sx, ffx[k]), fy = __fmul_rn(S.sy, ffy[k]);
-        if (k < 2) { pfx[k] = fx; pfy[k] = fy; }
-        WarpCoord wc = warp_coord((float)sxx[k], (float)syy[k], fx, fy, S.geom);
-        Gather4 gt = gather_setup(wc.ix, wc.iy, h, w);
-        if (k < 2) ps[k].valid = wc.valid & real;
-        const float okf = sok[k] ? 1.f : 0.f;
-        float v4[3][4];
-        gather_fetch(rf, gt, v4[0][0], v4[0][1], v4[0][2], v4[0][3]);
-        gather_fetch(rf1, gt, v4[1][0], v4[1][1], v4[1][2], v4[1][3]);
-        gather_fetch(rf2, gt, v4[2][0], v4[2][1], v4[2][2], v4[2][3]);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float wv = gather_value(gt, v4[c][0], v4[c][1], v4[c][2], v4[c][3]) * okf;
-          if (k < 2) gather_deriv(gt, v4[c][0], v4[c][1], v4[c][2], v4[c][3], ps[k].ddx[c], ps[k].ddy[c]);
-          sm.W[c * R2N + si2[k]] = wv;
-          if (MAPS && real && S.warped[pair]) S.warped[pair][((size_t)b * 3 + c) * hw + so[k]] = wv;
+      unsigned vbits = 0;            // validity of own pixel (k, e): bit 2k + e
+      // -- P1: own pairs (it < PR), then this thread's share of the halo ring
+      constexpr int N_IT = PR + (RINGP + FT - 1) / FT;
+#pragma unroll 1
+      for (int it = 0; it < N_IT; ++it) {
+        int r, j;
+        const bool own_it = it < PR;
+        if (own_it) { r = PR * g + 2 + it; j = 2 * t + 2; }
+        else {
+          const int i = tid + (it - PR) * FT;
+          if (i >= RINGP) break;
+          ring_pair(i, r, j);
         }
-        if (MAPS && real && S.valid[pair]) S.valid[pair][(size_t)b * hw + so[k]] = wc.valid ? 1 : 0;
-      }
-      if (!staged) {   // first pair only: the staging copies must have landed before anybody reads T / M
-        cp_async_wait_all();
-        if (need_mask & !own & !shared_mask) {
-#pragma unroll
-          for (int j = 0; j < (R1N + NTHREADS - 1) / NTHREADS; ++j) {
-            const int i = tid + j * NTHREADS;   // the slots this thread staged itself
-            if (i < R1N) { const float a0 = sm.M[i], a1 = sm.M[R1N + i]; sm.M[2 * R1N + i] = (a0 <= a1) ? a0 : a1; }
-          }
+        // source pixels of the two slots: real pixels inside the image, reflected copies on the padding ring
+        const int ya = stage_index(y0 - 2 + r, h);
+        const int xa = stage_index(x0 - 2 + j, w), xb = stage_index(x0 - 1 + j, w);
+        const bool oka = (ya | xa) >= 0, okb = (ya | xb) >= 0;
+        float2 fxr, fyr;
+        if (oka & okb & weven & (xb == xa + 1)) {
+          fxr = ldg2(flx + ya * w + xa); fyr = ldg2(fly + ya * w + xa);
+        } else {
+          const int oa = oka ? ya * w + xa : 0, ob = okb ? ya * w + xb : 0;
+          fxr = make_float2(__ldg(flx + oa), __ldg(flx + ob)); fyr = make_float2(__ldg(fly + oa), __ldg(fly + ob));
         }
-        staged = true;
-      }
-      __syncthreads();
-
-      // -- P2: SSIM; thread (column cw of the halo-1 region, group g) slides over windows rows 3g .. 3g+2
-      if (use_ssim) {
-        if (tid < R1W * (R1H / 3)) {
-          const int g = tid / R1W, cw = tid - g * R1W;
-          const int wx = x0 - 1 + cw;
-          const bool colok = (wx >= 0) & (wx < w);
-          const bool col_interior = (cw >= 1) & (cw <= TW);
-          const float k9 = S.c_ssim * (1.f / 9.f);
-#pragma unroll 1   // keep the body once in the instruction cache: the kernel is fetch-sensitive (4 CTAs in 4 different phases)
-          for (int c = 0; c < 3; ++c) {
-            const float* Tc = sm.T + c * R2N + (3 * g) * R2W + cw;
-            const float* Wc = sm.W + c * R2N + (3 * g) * R2W + cw;
-            float hx[5], hy[5], hxx[5], hyy[5], hxy[5];
+        Gather2 G2;
+        // flow -> pixels with SCALAR multiplies: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it honours
+        // .rn only for scalar ops), which would move x + sx * f by an ulp and flip bilinear cells
+        const float2 fxp = make_float2(__fmul_rn(S.sx, fxr.x), __fmul_rn(S.sx, fxr.y));
+        const float2 fyp = make_float2(__fmul_rn(S.sy, fyr.x), __fmul_rn(S.sy, fyr.y));
+        gather_pair<true>(rf, hw, h, w, make_float2((float)xa, (float)xb), splat2((float)ya), fxp, fyp, S.geom, G2);
+        const float2 okm = make_float2(oka ? 1.f : 0.f, okb ? 1.f : 0.f);
+        float* Wd = sm.W + OFF2 + r * S2 + j;
 #pragma unroll
-            for (int rr = 0; rr < 5; ++rr) {
-              float a0 = Tc[rr * R2W], a1 = Tc[rr * R2W + 1], a2 = Tc[rr * R2W + 2];
-              float b0 = Wc[rr * R2W], b1 = Wc[rr * R2W + 1], b2 = Wc[rr * R2W + 2];
-              hx[rr] = a0 + a1 + a2;
-              hy[rr] = b0 + b1 + b2;
-              hxx[rr] = a0 * a0 + a1 * a1 + a2 * a2;
-              hyy[rr] = b0 * b0 + b1 * b1 + b2 * b2;
-              hxy[rr] = a0 * b0 + a1 * b1 + a2 * b2;
-            }
+        for (int c = 0; c < 3; ++c) st2s(Wd + c * R2P, mul2(G2.val[c], okm));
+        if (own_it) {
+          const int y = y0 - 2 + r;
+          const bool ra = (y < h) & in0, rb = (y < h) & in1;     // real pixels (not padding)
+          vbits |= ((G2.valid_a & ra) ? 1u : 0u) << (2 * it);
+          vbits |= ((G2.valid_b & rb) ? 2u : 0u) << (2 * it);
+          float* Dd = sm.D + (it * FT + tid) * 2;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-              const int rw = 3 * g + q;                 // window row in the halo-1 region
-              const int wy = y0 - 1 + rw;
-              const int i1 = rw * R1W + cw;
-              // branch free: windows outside the image are evaluated on zeros and masked out
-              const bool inimg = colok & (wy >= 0) & (wy < h);
-              const bool inter = inimg & col_interior & (rw >= 1) & (rw <= TH);
-              SsimOut so = ssim_window(hx[q] + hx[q + 1] + hx[q + 2], hy[q] + hy[q + 1] + hy[q + 2],
-                                       hxx[q] + hxx[q + 1] + hxx[q + 2], hyy[q] + hyy[q + 1] + hyy[q + 2],
-                                       hxy[q] + hxy[q + 1] + hxy[q + 2], grads);
-              acc[SL_SSIM] += inter ? so.J : 0.f;
-              if (MAPS && inter && S.ssim_map[pair]) S.ssim_map[pair][((size_t)b * 3 + c) * hw + wy * w + wx] = so.J;
-              const float kk = inimg ? k9 : 0.f;
-              const float A = kk * so.dmu_y, Bc = kk * 2.f * so.dY2, Cc = kk * so.dXY;
-              sm.ABC[(3 * c + 0) * R1N + i1] = A;
-              sm.ABC[(3 * c + 1) * R1N + i1] = Bc;
-              sm.ABC[(3 * c + 2) * R1N + i1] = Cc;
+          for (int c = 0; c < 3; ++c) { st2s(Dd + (2 * c) * PR * FT * 2, G2.dx[c]); st2s(Dd + (2 * c + 1) * PR * FT * 2, G2.dy[c]); }
+          if (MAPS && ra) {
+            const size_t o = (size_t)y * w + px0;
+            if (S.valid[pair]) { S.valid[pair][(size_t)b * hw + o] = G2.valid_a ? 1 : 0; if (rb) S.valid[pair][(size_t)b * hw + o + 1] = G2.valid_b ? 1 : 0; }
+            if (S.warped[pair]) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                S.warped[pair][((size_t)b * 3 + c) * hw + o] = G2.val[c].x;
+                if (rb) S.warped[pair][((size_t)b * 3 + c) * hw + o + 1] = G2.val[c].y;
+              }
             }
           }
         }
-        __syncthreads();
+      }
+      if (!staged) { cp_async_wait_all(); staged = true; }
+      __syncthreads();
+
+      float2 vmask[PR];   // validity of the own pixels as 0 / 1
+#pragma unroll
+      for (int k = 0; k < PR; ++k) vmask[k] = make_float2((vbits >> (2 * k)) & 1u ? 1.f : 0.f, (vbits >> (2 * k + 1)) & 1u ? 1.f : 0.f);
+
+      // reflection multiplicities of the adjoint gather (border tiles only): pixel column 1 / w-2 and pixel row
+      // 1 / h-2 collect the out-of-image tap of the windows in column 0 / w-1 and row 0 / h-1 a second time
+      float2 fl = make_float2(0.f, 0.f), fr = fl;
+      float ft[PR], fb[PR];
+#pragma unroll
+      for (int k = 0; k < PR; ++k) ft[k] = fb[k] = 0.f;
+      if (border) {
+        fl = make_float2(px0 == 1 ? 1.f : 0.f, px1 == 1 ? 1.f : 0.f);
+        fr = make_float2(px0 == w - 2 ? 1.f : 0.f, px1 == w - 2 ? 1.f : 0.f);
+#pragma unroll
+        for (int k = 0; k < PR; ++k) { ft[k] = (py0 + k == 1) ? 1.f : 0.f; fb[k] = (py0 + k == h - 2) ? 1.f : 0.f; }
+      }
+
+#pragma unroll 1
+      for (int c = 0; c < 3; ++c) {
+        // -- P2: SSIM windows of channel c, 2 columns x WPR rows per patch
+        if (use_ssim) {
+          const float kq = S.c_ssim * (1.f / 9.f);
+#pragma unroll 1
+          for (int patch = tid; patch < NPATCH; patch += FT) {
+            const int rg = patch / NCP, cp = patch - rg * NCP;
+            const int o2 = c * R2P + OFF2 + (WPR * rg) * S2 + 2 * cp;
+            const float* Tp = sm.T + o2;
+            const float* Wp = sm.W + o2;
+            const int wx0 = x0 - 1 + 2 * cp, wy0 = y0 - 1 + WPR * rg;
+            const bool ci0 = (unsigned)wx0 < (unsigned)w, ci1 = (unsigned)(wx0 + 1) < (unsigned)w;
+            // windows that belong to this tile's own pixels (the SSIM loss sum counts every window once)
+            const float it0 = (ci0 & (cp >= 1)) ? 1.f : 0.f, it1 = (ci1 & (cp < NCP - 1)) ? 1.f : 0.f;
+            const float2 kcol = make_float2(ci0 ? kq : 0.f, ci1 ? kq : 0.f);
+            float2 H[3][5];   // 3-tap row sums of (x, y, xx, yy, xy) of the last three image rows, for both columns
+#pragma unroll
+            for (int rr = 0; rr < WPR + 2; ++rr) {
+              const float2 ta = ld2s(Tp + rr * S2), tb = ld2s(Tp + rr * S2 + 2);
+              const float2 wa = ld2s(Wp + rr * S2), wb = ld2s(Wp + rr * S2 + 2);
+              float2* Hc = H[rr % 3];
+              const float mt = ta.y + tb.x, mw = wa.y + wb.x;
+              Hc[0] = make_float2(ta.x + mt, mt + tb.y);
+              Hc[1] = make_float2(wa.x + mw, mw + wb.y);
+              const float mtt = fmaf(tb.x, tb.x, ta.y * ta.y), mww = fmaf(wb.x, wb.x, wa.y * wa.y), mtw = fmaf(tb.x, wb.x, ta.y * wa.y);
+              Hc[2] = make_float2(fmaf(ta.x, ta.x, mtt), fmaf(tb.y, tb.y, mtt));
+              Hc[3] = make_float2(fmaf(wa.x, wa.x, mww), fmaf(wb.y, wb.y, mww));
+              Hc[4] = make_float2(fmaf(ta.x, wa.x, mtw), fmaf(tb.y, wb.y, mtw));
+              if (rr >= 2) {
+                const int q = rr - 2;                       // window row inside the patch
+                const int r1 = WPR * rg + q, wy = wy0 + q;  // halo-1 row, image row
+                const bool ri = (unsigned)wy < (unsigned)h;
+                float2 V[5];
+#pragma unroll
+                for (int m = 0; m < 5; ++m) V[m] = add2(add2(H[0][m], H[1][m]), H[2][m]);
+                const Ssim2 so = ssim_window2(V[0], V[1], V[2], V[3], V[4], ri ? kcol : make_float2(0.f, 0.f));
+                const float rit = (ri & (r1 >= 1) & (r1 <= TH)) ? 1.f : 0.f;
+                acc[SL_SSIM] += so.J.x * (rit * it0) + so.J.y * (rit * it1);
+                if (MAPS && S.ssim_map[pair] && rit != 0.f) {
+                  float* dst = S.ssim_map[pair] + ((size_t)b * 3 + c) * hw + (size_t)wy * w + wx0;
+                  if (it0 != 0.f) dst[0] = so.J.x;
+                  if (it1 != 0.f) dst[1] = so.J.y;
+                }
+                float* Qd = sm.Q + r1 * S1 + 2 * cp;
+                st2s(Qd, so.A); st2s(Qd + R1P, so.B); st2s(Qd + 2 * R1P, so.C);
+              }
+            }
+          }
+          __syncthreads();
+        }
+        // -- P3: the own pixels of channel c
+        {
+          float2 tv[PR], wv[PR];
+#pragma unroll
+          for (int k = 0; k < PR; ++k) {
+            tv[k] = ld2s(sm.T + c * R2P + o2own + k * S2);
+            wv[k] = ld2s(sm.W + c * R2P + o2own + k * S2);
+          }
+          float2 wbar[PR];
+#pragma unroll
+          for (int k = 0; k < PR; ++k) wbar[k] = make_float2(0.f, 0.f);
+          if (use_ssim & grads) {
+            float2 Sg[3][PR];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              const float* Qa = sm.Q + a * R1P + (PR * g) * S1 + 2 * t;
+              float2 Hq[PR + 2];
+#pragma unroll
+              for (int rr = 0; rr < PR + 2; ++rr) {
+                const float2 qa = ld2s(Qa + rr * S1), qb = ld2s(Qa + rr * S1 + 2);
+                const float m = qa.y + qb.x;
+                Hq[rr] = make_float2(qa.x + m, m + qb.y);
+                if (border) Hq[rr] = fma2(fr, qb, fma2(fl, qa, Hq[rr]));
+              }
+#pragma unroll
+              for (int k = 0; k < PR; k += 2) {       // rows k, k+1 share Hq[k+1] + Hq[k+2]
+                const float2 m12 = add2(Hq[k + 1], Hq[k + 2]);
+                Sg[a][k] = add2(Hq[k], m12); Sg[a][k + 1] = add2(m12, Hq[k + 3]);
+              }
+              if (border) {
+#pragma unroll
+                for (int k = 0; k < PR; ++k) Sg[a][k] = fma2(splat2(fb[k]), Hq[k + 2], fma2(splat2(ft[k]), Hq[k], Sg[a][k]));
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < PR; ++k) wbar[k] = fma2(tv[k], Sg[2][k], fma2(wv[k], Sg[1][k], Sg[0][k]));
+          }
+          // L1 term: |tgt - warped| * valid  (loss_functions.py:109-110)
+#pragma unroll
+          for (int k = 0; k < PR; ++k) {
+            const float d0 = tv[k].x - wv[k].x, d1 = tv[k].y - wv[k].y;
+            const float a0 = fabsf(d0) * vmask[k].x, a1 = fabsf(d1) * vmask[k].y;
+            acc[SL_L1] += a0 + a1;
+            if (MAPS && S.diff[pair]) {
+              const int y = py0 + k;
+              if ((y < h) & in0) S.diff[pair][((size_t)b * 3 + c) * hw + (size_t)y * w + px0] = a0;
+              if ((y < h) & in1) S.diff[pair][((size_t)b * 3 + c) * hw + (size_t)y * w + px1] = a1;
+            }
+            if (grads) {
+              wbar[k].x -= S.c_l1 * signf_(d0) * vmask[k].x;
+              wbar[k].y -= S.c_l1 * signf_(d1) * vmask[k].y;
+              const float* Dd = sm.D + (k * FT + tid) * 2 + (2 * c) * PR * FT * 2;
+              gix[k] = fma2(wbar[k], ld2s(Dd), gix[k]);
+              giy[k] = fma2(wbar[k], ld2s(Dd + PR * FT * 2), giy[k]);
+            }
+          }
+        }
+        if (use_ssim) __syncthreads();   // Q (and, after the last channel, W) is rewritten next
       }
     }
 
-    if (!PHOTO && !staged) {
-      cp_async_wait_all();
-      if (need_mask & !own & !shared_mask) {
-#pragma unroll
-        for (int j = 0; j < (R1N + NTHREADS - 1) / NTHREADS; ++j) {
-          const int i = tid + j * NTHREADS;
-          if (i < R1N) { const float a0 = sm.M[i], a1 = sm.M[R1N + i]; sm.M[2 * R1N + i] = (a0 <= a1) ? a0 : a1; }
-        }
-      }
-      staged = true;
-      __syncthreads();
-    }
-    // -- P3: the thread's two pixels: photometric adjoint -> d/dflow, epipolar forward + adjoint
+    if (!PHOTO && !staged) { cp_async_wait_all(); staged = true; __syncthreads(); }
+
+    // -- P4: epipolar forward + adjoint, d(loss)/d(flow); rolled over the rows of the patch (gix / giy / mbar rotate)
     {
-      float gfx[2] = {0.f, 0.f}, gfy[2] = {0.f, 0.f};
-      if (PHOTO) {   // L1 term: |tgt - warped| * valid  (loss_functions.py:109-110)
-        const int i2 = (ly0 + 2) * R2W + lx + 2;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float df = fabsf(sm.T[c * R2N + i2 + k * R2W] - sm.W[c * R2N + i2 + k * R2W]);
-            df = ps[k].valid ? df : 0.f;     // valid already implies "real pixel"
-            acc[SL_L1] += df;
-            if (MAPS && S.diff[pair] && (y0 + ly0 + k < h) && col_in)
-              S.diff[pair][((size_t)b * 3 + c) * hw + (y0 + ly0 + k) * w + px] = df;
-          }
-        }
-      }
-      if (PHOTO && grads) {
-        float wxm[3] = {1.f, 1.f, 1.f}, wym[2][3] = {{1.f, 1.f, 1.f}, {1.f, 1.f, 1.f}};
-        if (border) {
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            int pxx = px + d - 1;
-            wxm[d] = (pxx >= 0 && pxx < w) ? (float)refl_mult(pxx, px, w) : 0.f;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              int yq = y0 + ly0 + k, pyy = yq + d - 1;
-              wym[k][d] = (pyy >= 0 && pyy < h) ? (float)refl_mult(pyy, yq, h) : 0.f;
-            }
-          }
-        }
-        float gix[2] = {0.f, 0.f}, giy[2] = {0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float wb[2] = {0.f, 0.f};
-          const int i2 = (ly0 + 2) * R2W + lx + 2;
-          const float tv[2] = {sm.T[c * R2N + i2], sm.T[c * R2N + i2 + R2W]};
-          const float wv[2] = {sm.W[c * R2N + i2], sm.W[c * R2N + i2 + R2W]};
-          if (use_ssim) {
-            float S3[2][3];
-            const float* Q = sm.ABC + (3 * c) * R1N + ly0 * R1W + lx;   // halo-1 rows ly0 .. ly0+3, cols lx .. lx+2
-            if (border) {
-#pragma unroll
-              for (int a = 0; a < 3; ++a) adjoint_box<true>(Q + a * R1N, wxm, wym, S3[0][a], S3[1][a]);
-            } else {
-#pragma unroll
-              for (int a = 0; a < 3; ++a) adjoint_box<false>(Q + a * R1N, wxm, wym, S3[0][a], S3[1][a]);
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k) wb[k] = S3[k][0] + wv[k] * S3[k][1] + tv[k] * S3[k][2];
-          }
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            if (ps[k].valid) wb[k] -= S.c_l1 * signf_(tv[k] - wv[k]);
-            gix[k] += wb[k] * ps[k].ddx[c];
-            giy[k] += wb[k] * ps[k].ddy[c];
-          }
-        }
-        // (w-1)/2 [grid_sample] * 2 [2g-1] / (w-1) [/= w-1] * sx [scale factor]
-#pragma unroll
-        for (int k = 0; k < 2; ++k) { gfx[k] = gix[k] * S.sx; gfy[k] = giy[k] * S.sy; }
-      }
       float Fm[9];
       float snmax = 1.f;
       if (epi_on) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) Fm[k] = __ldg(S.fmat[pair] + b * 9 + k);
         if (P.post == MDN_POST_SN) {
-          unsigned long long key = P.snkey[(s * P.n_pairs + pair) * P.batch + b];
+          const unsigned long long key = P.snkey[(s * P.n_pairs + pair) * P.batch + b];
           snmax = __uint_as_float((unsigned)(key >> 32));
         }
       }
+      const float* mq0 = (own && pair) ? mob1 : mob0;
+#pragma unroll 1
+      for (int k = 0; k < PR; ++k) {
+        const int y = py0 + k;
+        // (w-1)/2 [grid_sample] * 2 [2g-1] / (w-1) [/= w-1] * sx [scale factor]
+        float gfx[2] = {gix[0].x * S.sx, gix[0].y * S.sx}, gfy[2] = {giy[0].x * S.sy, giy[0].y * S.sy};
+        float mb[2] = {0.f, 0.f};
+        if ((y < h) & in0) {
+          const int o = y * w + px0;
+          if (epi_on) {
+            const float2 fxr = load_pair(flx, y), fyr = load_pair(fly, y);
+            const float2 m0 = load_pair(mq0, y);
+            const float2 m1 = minmode ? load_pair(mob1, y) : m0;
+            float kin[2] = {1.f, 1.f}, wgt[2] = {1.f, 1.f};
+            if ((P.flags & (MDN_OPT_INST_MASK | MDN_OPT_CROSS_ENT)) != 0) {
+              kin[0] = (float)__ldg(S.inst + (size_t)b * hw + o);
+              kin[1] = in1 ? (float)__ldg(S.inst + (size_t)b * hw + o + 1) : 0.f;
+            }
+            if (P.post == MDN_POST_TG) { wgt[0] = __ldg(S.weight + o); wgt[1] = in1 ? __ldg(S.weight + o + 1) : 1.f; }
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int ly = ly0 + k, y = y0 + ly;
-        if (!((y < h) & col_in)) continue;
-        const int o = y * w + px;
-        if (epi_on) {
-          const float m = Mp[(ly + 1) * R1W + lx + 1];
-          const float xf = (float)px, yf = (float)y;
-          float u, v;
-          if (PHOTO) { u = __fadd_rn(xf, pfx[k]); v = __fadd_rn(yf, pfy[k]); }
-          else { u = __fadd_rn(xf, __fmul_rn(S.sx, __ldg(flx + o))); v = __fadd_rn(yf, __fmul_rn(S.sy, __ldg(fly + o))); }
-          Epi e = epipolar_distance(Fm, xf, yf, u, v);
-          float ae = fabsf(e.d);
-          float dpost;
-          float post = post_process(P, S, ae, snmax, o, dpost);
-          float kmask = 1.f;
-          if ((P.flags & (MDN_OPT_INST_MASK | MDN_OPT_CROSS_ENT)) != 0) kmask = (float)__ldg(S.inst + (size_t)b * hw + o);
-          if (P.flags & MDN_OPT_INST_MASK) { post *= kmask; dpost *= kmask; }
-          float bg = 1.f - m;
-          float lg = __logf(bg + 1e-5f);
-          float ml = m * lg;
-          acc[SL_EPI] += bg * post;
-          acc[SL_NT] += fabsf(ml);
-          float mb = 0.f;
-          if (P.flags & MDN_OPT_CROSS_ENT) {
-            float l1 = __logf(m + 1e-10f), l0 = __logf(bg + 1e-10f);
-            acc[SL_CE] += -(kmask * l1 + (1.f - kmask) * l0);
-            mb += S.c_ce * (__fdividef(1.f - kmask, bg + 1e-10f) - __fdividef(kmask, m + 1e-10f));
+            for (int e = 0; e < 2; ++e) {
+              if (e && !in1) continue;
+              const float ma = e ? m0.y : m0.x, mbv = e ? m1.y : m1.x;
+              const float m = (ma <= mbv) ? ma : mbv;
+              const float xf = (float)(px0 + e), yf = (float)y;
+              const float u = __fadd_rn(xf, __fmul_rn(S.sx, e ? fxr.y : fxr.x)), v = __fadd_rn(yf, __fmul_rn(S.sy, e ? fyr.y : fyr.x));
+              const Epi ep = epipolar_distance(Fm, xf, yf, u, v);
+              const float ae = fabsf(ep.d);
+              float dpost;
+              float post = post_process(P, ae, snmax, wgt[e], dpost);
+              const float kmask = kin[e];
+              if (P.flags & MDN_OPT_INST_MASK) { post *= kmask; dpost *= kmask; }
+              const float bg = 1.f - m;
+              const float lg = __logf(bg + 1e-5f);
+              const float ml = m * lg;
+              acc[SL_EPI] += bg * post;
+              acc[SL_NT] += fabsf(ml);
+              if (P.flags & MDN_OPT_CROSS_ENT) {
+                const float l1 = __logf(m + 1e-10f), l0 = __logf(bg + 1e-10f);
+                acc[SL_CE] += -(kmask * l1 + (1.f - kmask) * l0);
+                mb[e] += S.c_ce * (__fdividef(1.f - kmask, bg + 1e-10f) - __fdividef(kmask, m + 1e-10f));
+              }
+              if (MAPS && S.post_map[pair]) S.post_map[pair][(size_t)b * hw + o + e] = post;
+              if (MAPS && S.ori_map[pair]) S.ori_map[pair][(size_t)b * hw + o + e] = (P.post == MDN_POST_SN) ? __fdiv_rn(ae, snmax) : ae;
+              if (grads) {
+                mb[e] += -S.c_epi * post + S.c_nt * signf_(ml) * (lg - __fdividef(m, bg + 1e-5f));
+                const float ebar = S.c_epi * bg * dpost;
+                const float dbar = signf_(ep.d) * ebar;
+                const float g2 = __fdividef(dbar, ep.den);
+                const float das = __fdividef(ep.d, ep.s);
+                gfx[e] += g2 * ep.a * S.sx;
+                gfy[e] += g2 * ep.b * S.sy;
+                const float g0 = g2 * (u - das * ep.a), g1 = g2 * (v - das * ep.b);
+                acc[SL_GF + 0] += g0 * xf; acc[SL_GF + 1] += g0 * yf; acc[SL_GF + 2] += g0;
+                acc[SL_GF + 3] += g1 * xf; acc[SL_GF + 4] += g1 * yf; acc[SL_GF + 5] += g1;
+                acc[SL_GF + 6] += g2 * xf; acc[SL_GF + 7] += g2 * yf; acc[SL_GF + 8] += g2;
+              }
+            }
           }
-          if (MAPS && S.post_map[pair]) S.post_map[pair][(size_t)b * hw + o] = post;
-          if (MAPS && S.ori_map[pair]) S.ori_map[pair][(size_t)b * hw + o] = (P.post == MDN_POST_SN) ? __fdiv_rn(ae, snmax) : ae;
-          if (grads) {
-            mb += -S.c_epi * post + S.c_nt * signf_(ml) * (lg - __fdividef(m, bg + 1e-5f));
-            if (mslot) mbar[k][1] += mb; else mbar[k][0] += mb;
-            float ebar = S.c_epi * bg * dpost;
-            float dbar = signf_(e.d) * ebar;
-            float g2 = __fdividef(dbar, e.den);
-            float das = __fdividef(e.d, e.s);
-            gfx[k] += g2 * e.a * S.sx;
-            gfy[k] += g2 * e.b * S.sy;
-            float g0 = g2 * (u - das * e.a), g1 = g2 * (v - das * e.b);
-            acc[SL_GF + 0] += g0 * xf; acc[SL_GF + 1] += g0 * yf; acc[SL_GF + 2] += g0;
-            acc[SL_GF + 3] += g1 * xf; acc[SL_GF + 4] += g1 * yf; acc[SL_GF + 5] += g1;
-            acc[SL_GF + 6] += g2 * xf; acc[SL_GF + 7] += g2 * yf; acc[SL_GF + 8] += g2;
+          if (grads && S.g_flow[pair]) {
+            float* gx = S.g_flow[pair] + (size_t)b * 2 * hw;
+            store_pair(gx, y, make_float2(gfx[0], gfx[1]));
+            store_pair(gx + hw, y, make_float2(gfy[0], gfy[1]));
           }
         }
-        if (grads && S.g_flow[pair]) {
-          S.g_flow[pair][(size_t)b * 2 * hw + o] = gfx[k];
-          S.g_flow[pair][(size_t)b * 2 * hw + hw + o] = gfy[k];
-        }
+        // rotate the rings: row k + 1 moves to the front, the updated mask gradient to the back
+        const float2 mnew = make_float2(mbar[0].x + mb[0], mbar[0].y + mb[1]);
+#pragma unroll
+        for (int i = 0; i + 1 < PR; ++i) { gix[i] = gix[i + 1]; giy[i] = giy[i + 1]; mbar[i] = mbar[i + 1]; }
+        mbar[PR - 1] = mnew;
       }
     }
     flush_acc<PAIR_SLOTS>(acc, sm.red, pair * PAIR_SLOTS);
-    __syncthreads();   // W / ABC are reused by the next pair
+    if (need_mask && own) tail(pair);
   }
+  if (need_mask && !own) tail(0);
 
-  // ---- P4: smoothness + consistency, then route d/dmask to the mobile maps
-  if (need_mask) {
-    float acc[TAIL_SLOTS];
-#pragma unroll
-    for (int k = 0; k < TAIL_SLOTS; ++k) acc[k] = 0.f;
-    const int n_masks = own ? P.n_pairs : 1;
-    // in MIN / SHARED mode the reference evaluates smooth_loss once per source frame with the SAME mask
-    const float rep = own ? 1.f : (float)P.n_pairs;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int ly = ly0 + k, y = y0 + ly;
-      if (!((y < h) & col_in)) continue;
-      const int o = y * w + px;
-      const int i1 = (ly + 1) * R1W + lx + 1, i2 = (ly + 2) * R2W + lx + 2;
-      if (smooth_on) {
-        // exp(-mean_c |I(x) - I(x+1)|) for the pixel pairs (x-1,x), (x,x+1), (y-1,y), (y,y+1)
-        float gr = 0.f, gl = 0.f, gd = 0.f, gu = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float t0 = sm.T[c * R2N + i2];
-          gr += fabsf(t0 - sm.T[c * R2N + i2 + 1]);
-          gl += fabsf(sm.T[c * R2N + i2 - 1] - t0);
-          gd += fabsf(t0 - sm.T[c * R2N + i2 + R2W]);
-          gu += fabsf(sm.T[c * R2N + i2 - R2W] - t0);
-        }
-        const float third = 1.f / 3.f;
-        const float ex_r = (px + 1 < w) ? __expf(-gr * third) : 0.f;
-        const float ex_l = (px > 0) ? __expf(-gl * third) : 0.f;
-        const float ey_d = (y + 1 < h) ? __expf(-gd * third) : 0.f;
-        const float ey_u = (y > 0) ? __expf(-gu * third) : 0.f;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (q < n_masks) {
-            const float* Mk = own ? sm.M + q * R1N : Mmin;
-            float mc = Mk[i1];
-            float dr = mc - Mk[i1 + 1], dl = Mk[i1 - 1] - mc, dd = mc - Mk[i1 + R1W], du = Mk[i1 - R1W] - mc;
-            acc[SL_SMX + 2 * q] += fabsf(dr) * ex_r;   // ex_r == 0 at the last column
-            acc[SL_SMY + 2 * q] += fabsf(dd) * ey_d;
-            mbar[k][q] += rep * (S.c_smx * (signf_(dr) * ex_r - signf_(dl) * ex_l) + S.c_smy * (signf_(dd) * ey_d - signf_(du) * ey_u));
-          }
-        }
-      }
-      const float a0 = sm.M[i1], a1 = shared_mask ? a0 : sm.M[R1N + i1];   // raw maps at this pixel
-      float g0, g1;
-      if (own) { g0 = mbar[k][0]; g1 = mbar[k][1]; }
-      else if (shared_mask) { g0 = mbar[k][0]; g1 = 0.f; }
-      else { bool first = a0 <= a1; g0 = first ? mbar[k][0] : 0.f; g1 = first ? 0.f : mbar[k][0]; }
-      if (consis_on) {
-        float p = __fdividef(1.f, 1.f + __expf(-20.f * (a0 - 0.5f))), q = __fdividef(1.f, 1.f + __expf(-20.f * (a1 - 0.5f)));
-        float df = p - q;
-        acc[SL_CONSIS] += df * df;
-        g0 += S.c_consis * 40.f * df * p * (1.f - p);
-        g1 -= S.c_consis * 40.f * df * q * (1.f - q);
-      }
-      if (grads) {
-        if (S.g_mob[0]) S.g_mob[0][(size_t)b * hw + o] = g0;
-        if (S.g_mob[1] && !shared_mask) S.g_mob[1][(size_t)b * hw + o] = g1;
-      }
-    }
-    flush_acc<TAIL_SLOTS>(acc, sm.red, TAIL_BASE);
-  }
   __syncthreads();
-  for (int k = tid; k < NSLOT; k += nthr) {
-    float t = 0.f;
-    for (int wq = 0; wq < nwarps; ++wq) t += sm.red[wq * NSLOT + k];
-    P.partials[(size_t)blockIdx.x * NSLOT + k] = t;
+  for (int k = tid; k < NSLOT; k += FT) {
+    float tsum = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < FWARPS; ++wq) tsum += sm.red[wq * NSLOT + k];
+    P.partials[(size_t)blockIdx.x * NSLOT + k] = tsum;
   }
 }

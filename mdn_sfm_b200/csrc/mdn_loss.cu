@@ -19,11 +19,29 @@
 namespace mdn {
 
 // ----------------------------------------------------------------------------------------------- geometry
-constexpr int TW = 32, TH = 16;                       // interior tile
-constexpr int R2W = TW + 4, R2H = TH + 4, R2N = R2W * R2H;   // halo 2: target + warped image
-constexpr int R1W = TW + 2, R1H = TH + 2, R1N = R1W * R1H;   // halo 1: SSIM windows, masks
-constexpr int TN = TW * TH;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 256;                         // block size of the small standalone kernels
+// fused kernel: TW x TH tile, one thread per 2-column x 4-row patch of pixels
+constexpr int TW = 64, TH = 16;
+#ifndef MDN_PATCH_ROWS
+#define MDN_PATCH_ROWS 4
+#endif
+constexpr int PR = MDN_PATCH_ROWS;                           // rows of the per-thread pixel patch (2 or 4)
+static_assert((PR == 2 || PR == 4) && TH % PR == 0, "patch rows");
+constexpr int FT = (TW / 2) * (TH / PR), FWARPS = FT / 32;   // lane = column pair, warp = row group
+static_assert(TW == 64, "one warp spans the tile width: 32 lanes x 2 columns");
+// halo-2 planes (target / warped image): rows y0-2 .. y0+TH+1, columns x0-2 .. x0+TW+1.  Slot (r, j) lives at
+// OFF2 + r * S2 + j; OFF2 = 2 makes column x0 (j = 2) 16-byte aligned for the cp.async staging and every even j
+// 8-byte aligned for LDS.64.
+constexpr int S2 = TW + 4, R2H = TH + 4, OFF2 = 2, R2P = ((OFF2 + S2 * R2H + 3) / 4) * 4;
+// halo-1 planes (SSIM adjoint coefficients): window rows y0-1 .. y0+TH, columns x0-1 .. x0+TW
+constexpr int S1 = TW + 4, R1H = TH + 2, R1P = S1 * R1H;
+constexpr int WPR = 3;                                // window rows per SSIM patch (2 columns x WPR rows)
+static_assert((TH + 2) % WPR == 0, "SSIM patches tile the halo-1 region exactly");
+constexpr int NCP = (TW + 2) / 2, NPATCH = NCP * ((TH + 2) / WPR);
+constexpr int RING = S2 * R2H - TW * TH;              // halo slots of the halo-2 region
+#ifndef MDN_FUSED_MIN_CTAS
+#define MDN_FUSED_MIN_CTAS 3
+#endif
 
 // partial-sum slots per tile
 constexpr int PAIR_SLOTS = 16;   // epi, nt, ce, l1, ssim, gF[9], pad, pad
@@ -54,8 +72,8 @@ struct KParams {
   KScale sc[MDN_MAX_SCALES];
 };
 
-MDN_DEV float post_process(const KParams& P, const KScale& S, float e, float snmax, int pix, float& dpost_de) {
-  // returns post (before the DS mask) and d(post)/d(e)
+MDN_DEV float post_process(const KParams& P, float e, float snmax, float wgt, float& dpost_de) {
+  // returns post (before the DS mask) and d(post)/d(e); wgt = Gaussian distance weight of the pixel (TG only)
   if (P.post == MDN_POST_SN) {
     float q = __fdiv_rn(e, snmax);            // loss_utils.py:98
     dpost_de = 2.f * q / snmax;
@@ -66,7 +84,7 @@ MDN_DEV float post_process(const KParams& P, const KScale& S, float e, float snm
     r = (P.flags & MDN_OPT_CUDA_ARITH) ? __fmul_rn(r, P.inv_threshold) : __fdiv_rn(r, P.threshold);
     dr = dr * P.inv_threshold;
   }
-  if (P.post == MDN_POST_TG) { float wgt = __ldg(S.weight + pix); r = __fdiv_rn(r, wgt); dr = dr / wgt; }   // :87-88
+  if (P.post == MDN_POST_TG) { r = __fdiv_rn(r, wgt); dr = dr / wgt; }   // :87-88
   dpost_de = 2.f * r * dr;
   return __fmul_rn(r, r);                     // :89
 }
@@ -687,15 +705,22 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
     MDN_LAUNCH(sn_max_kernel, grid, dim3(NTHREADS), 0, stream, K, keys, chunks);
   }
   const bool photo = (d->flags & MDN_TERM_PHOTO) != 0;
-  const size_t smem = fused_smem_floats(photo, NTHREADS / 32) * sizeof(float);
-  static_assert(fused_smem_floats(true, NTHREADS / 32) * sizeof(float) <= 48 * 1024, "fits the default dynamic smem limit");
+  const size_t smem = fused_smem_floats(photo) * sizeof(float);
+  static_assert(fused_smem_floats(true) * sizeof(float) <= 75 * 1024, "three CTAs per SM");
   bool maps = false;
   for (int s = 0; s < d->n_scales; ++s)
     for (int p = 0; p < 2; ++p) {
       const MdnScale& S = d->scale[s];
       maps |= S.post_map[p] || S.ori_map[p] || S.warped[p] || S.diff[p] || S.valid[p] || S.ssim_map[p];
     }
-  const dim3 grid(K.n_tiles), block(NTHREADS);
+  const dim3 grid(K.n_tiles), block(FT);
+  static bool smem_opt_in = false;   // > 48 KB of dynamic shared memory needs the opt-in attribute (idempotent; set once)
+  if (!smem_opt_in) {
+    const int bytes = (int)(fused_smem_floats(true) * sizeof(float));
+    cudaFuncSetAttribute(fused_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(fused_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    smem_opt_in = true;
+  }
   if (photo && maps) { auto kfn = fused_tile_kernel<true, true>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
   else if (photo) { auto kfn = fused_tile_kernel<true, false>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
   else if (maps) { auto kfn = fused_tile_kernel<false, true>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }

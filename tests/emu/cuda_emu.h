@@ -160,6 +160,7 @@ static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c);
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline float __saturatef(float a) { return a < 0.f ? 0.f : (a > 1.f ? 1.f : a); }
 #define __expf(a) expf(a)
 #define __logf(a) logf(a)
 using std::max;

@@ -189,3 +189,13 @@ def test_fundamental_matrix_prologue():
     assert Fg.shape == Fo.shape and common.rel_max(Fo, Fg) < 1e-5
     for a, b in zip(co, cg):
         assert common.rel_max(a.grad, b.grad) < 1e-4
+
+
+def test_multiple_tiles_in_x_and_vector_staging():
+    # 136 = two full 64-wide tiles + a ragged one (w % 4 == 0: 16-byte staging path); 68 at scale 1; heights 24 / 12
+    opt, batch = common.make(1, 24, 136, scales=(0, 1), seed=17, flow_std=0.06)
+    for mode in ("T", "SN"):
+        ref = common.oracle_run(opt, batch, mode, True, True)
+        with emulated():
+            got = common.product_run(opt, batch, mode, True, True, "cpu")
+            common.compare(ref, got, True)
