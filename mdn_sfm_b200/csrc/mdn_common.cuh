@@ -191,6 +191,16 @@ MDN_DEV float ex2_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=
 MDN_DEV float lg2_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #endif
 MDN_DEV float2 splat2(float a) { return make_float2(a, a); }
+// Makes a pointer opaque to the optimiser, so that it is kept as ONE 64-bit register pair and `p + u32_offset` is a
+// single IMAD.WIDE.U32.  Without it nvcc keeps "constant-bank base + 64-bit element index" and re-derives every
+// address with a 4-instruction IADD3 / IADD3.X / LEA / LEA.HI.X sequence.
+template <class T>
+MDN_DEV T* opaque_ptr(T* p) {
+#ifndef MDN_EMU
+  asm volatile("" : "+l"(p));
+#endif
+  return p;
+}
 MDN_DEV float2 ld2s(const float* p) { return *reinterpret_cast<const float2*>(p); }     // 8-byte aligned
 MDN_DEV void st2s(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
 
@@ -208,9 +218,11 @@ struct Gather2 {
 };
 
 template <bool DERIV>
-MDN_DEV void gather_pair(const float* __restrict__ rf, int hw, int h, int w, float2 xs, float2 ys, float2 fx, float2 fy,
-                         const WarpGeom& G, Gather2& out) {
+MDN_DEV void gather_pair(const float* __restrict__ pl0, const float* __restrict__ pl1, const float* __restrict__ pl2, int h, int w,
+                         float2 xs, float2 ys, float2 fx, float2 fy, const WarpGeom& G, Gather2& out) {
   const float2 one = splat2(1.f), neg1 = splat2(-1.f), two = splat2(2.f);
+  // NOTE: fx / fy must come from SCALAR multiplies: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it
+  // honours .rn only for scalar ops), which would move x + sx * f by an ulp and flip bilinear cells
   const float2 px = add2(xs, fx), py = add2(ys, fy);
   float2 gx, gy;
   if (G.cuda_arith) { gx = mul2(px, splat2(G.inv_wm1)); gy = mul2(py, splat2(G.inv_hm1)); }
@@ -227,7 +239,7 @@ MDN_DEV void gather_pair(const float* __restrict__ rf, int hw, int h, int w, flo
   const float2 x0f = make_float2(floorf(ix.x), floorf(ix.y)), y0f = make_float2(floorf(iy.x), floorf(iy.y));
   float2 ax1 = fma2(x0f, neg1, ix), ax0 = fma2(ix, neg1, add2(x0f, one));
   float2 ay1 = fma2(y0f, neg1, iy), ay0 = fma2(iy, neg1, add2(y0f, one));
-  int o00[2], o01[2], o10[2], o11[2];
+  unsigned o00[2], o01[2], o10[2], o11[2];
   float mx0[2], mx1[2], my0[2], my1[2];
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
@@ -235,8 +247,8 @@ MDN_DEV void gather_pair(const float* __restrict__ rf, int hw, int h, int w, flo
     const int x1 = x0 + 1, y1 = y0 + 1;
     const bool bx0 = (unsigned)x0 < (unsigned)w, bx1 = (unsigned)x1 < (unsigned)w;
     const bool by0 = (unsigned)y0 < (unsigned)h, by1 = (unsigned)y1 < (unsigned)h;
-    const int cx0 = bx0 ? x0 : 0, cx1 = bx1 ? x1 : 0;
-    const int r0 = (by0 ? y0 : 0) * w, r1 = (by1 ? y1 : 0) * w;
+    const unsigned cx0 = bx0 ? x0 : 0, cx1 = bx1 ? x1 : 0;
+    const unsigned r0 = (by0 ? y0 : 0) * w, r1 = (by1 ? y1 : 0) * w;
     o00[e] = r0 + cx0; o01[e] = r0 + cx1; o10[e] = r1 + cx0; o11[e] = r1 + cx1;
     mx0[e] = bx0 ? 1.f : 0.f; mx1[e] = bx1 ? 1.f : 0.f; my0[e] = by0 ? 1.f : 0.f; my1[e] = by1 ? 1.f : 0.f;
   }
@@ -253,7 +265,7 @@ MDN_DEV void gather_pair(const float* __restrict__ rf, int hw, int h, int w, flo
   float2 v00[3], v01[3], v10[3], v11[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float* pl = rf + (size_t)c * hw;
+    const float* pl = c == 0 ? pl0 : (c == 1 ? pl1 : pl2);
     v00[c] = make_float2(__ldg(pl + o00[0]), __ldg(pl + o00[1]));
     v01[c] = make_float2(__ldg(pl + o01[0]), __ldg(pl + o01[1]));
     v10[c] = make_float2(__ldg(pl + o10[0]), __ldg(pl + o10[1]));
@@ -265,6 +277,88 @@ MDN_DEV void gather_pair(const float* __restrict__ rf, int hw, int h, int w, flo
     if (DERIV) {
       out.dx[c] = fma2(v11[c], cx11, fma2(v10[c], cx10, fma2(v01[c], cx01, mul2(v00[c], cx00))));
       out.dy[c] = fma2(v11[c], cy11, fma2(v10[c], cy10, fma2(v01[c], cy01, mul2(v00[c], cy00))));
+    }
+  }
+}
+
+// The same for a source image REPACKED to one float4 (r, g, b, -) per pixel (ref_pack_kernel): the four corners of
+// a pixel are four 16-byte loads that bring all three channels at once -- a third of the load instructions and of
+// the L1 wavefronts / L2 sector requests of the planar form, which is what bounds the gather when neighbouring
+// pixels sample unrelated places.  Coordinates, fractions and masks are packed over the two PIXELS as above; the
+// interpolation is packed over the (r, g) CHANNELS of one pixel with the weight as the broadcast scalar operand,
+// b is scalar.  Output: per pixel e (0 / 1) value and derivatives of the three channels.
+struct GatherPx {
+  float v[3], dx[3], dy[3];
+};
+
+MDN_DEV float4 ldg4(const float4* p) { return __ldg(p); }
+
+template <bool DERIV>
+MDN_DEV void gather_pair_packed(const float4* __restrict__ pk, int h, int w, float2 xs, float2 ys, float2 fx, float2 fy,
+                                const WarpGeom& G, GatherPx* out, bool& valid_a, bool& valid_b) {
+  const float2 one = splat2(1.f), neg1 = splat2(-1.f), two = splat2(2.f);
+  const float2 px = add2(xs, fx), py = add2(ys, fy);     // fx / fy from SCALAR multiplies (see gather_pair)
+  float2 gx, gy;
+  if (G.cuda_arith) { gx = mul2(px, splat2(G.inv_wm1)); gy = mul2(py, splat2(G.inv_hm1)); }
+  else {
+    gx = make_float2(__fdiv_rn(px.x, G.wm1), __fdiv_rn(px.y, G.wm1));
+    gy = make_float2(__fdiv_rn(py.x, G.hm1), __fdiv_rn(py.y, G.hm1));
+  }
+  gx = fma2(two, gx, neg1);                     // loss_utils.py:31
+  gy = fma2(two, gy, neg1);
+  valid_a = (fabsf(gx.x) <= 1.f) & (fabsf(gy.x) <= 1.f);
+  valid_b = (fabsf(gx.y) <= 1.f) & (fabsf(gy.y) <= 1.f);
+  const float2 ix = mul2(add2(gx, one), splat2(0.5f * G.wm1));   // grid_sample un-normalisation, align_corners=True
+  const float2 iy = mul2(add2(gy, one), splat2(0.5f * G.hm1));
+  const float2 x0f = make_float2(floorf(ix.x), floorf(ix.y)), y0f = make_float2(floorf(iy.x), floorf(iy.y));
+  float2 ax1 = fma2(x0f, neg1, ix), ax0 = fma2(ix, neg1, add2(x0f, one));
+  float2 ay1 = fma2(y0f, neg1, iy), ay0 = fma2(iy, neg1, add2(y0f, one));
+  unsigned o00[2], o01[2], o10[2], o11[2];
+  float mx0[2], mx1[2], my0[2], my1[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int x0 = min(max(__float2int_rd(e ? ix.y : ix.x), -2), w), y0 = min(max(__float2int_rd(e ? iy.y : iy.x), -2), h);
+    const int x1 = x0 + 1, y1 = y0 + 1;
+    const bool bx0 = (unsigned)x0 < (unsigned)w, bx1 = (unsigned)x1 < (unsigned)w;
+    const bool by0 = (unsigned)y0 < (unsigned)h, by1 = (unsigned)y1 < (unsigned)h;
+    const unsigned cx0 = bx0 ? x0 : 0, cx1 = bx1 ? x1 : 0;
+    const unsigned r0 = (by0 ? y0 : 0) * w, r1 = (by1 ? y1 : 0) * w;
+    o00[e] = r0 + cx0; o01[e] = r0 + cx1; o10[e] = r1 + cx0; o11[e] = r1 + cx1;
+    mx0[e] = bx0 ? 1.f : 0.f; mx1[e] = bx1 ? 1.f : 0.f; my0[e] = by0 ? 1.f : 0.f; my1[e] = by1 ? 1.f : 0.f;
+  }
+  const float2 fx0 = make_float2(mx0[0], mx0[1]), fx1 = make_float2(mx1[0], mx1[1]);
+  const float2 fy0 = make_float2(my0[0], my0[1]), fy1 = make_float2(my1[0], my1[1]);
+  ax0 = mul2(ax0, fx0); ax1 = mul2(ax1, fx1); ay0 = mul2(ay0, fy0); ay1 = mul2(ay1, fy1);
+  const float2 w00 = mul2(ax0, ay0), w01 = mul2(ax1, ay0), w10 = mul2(ax0, ay1), w11 = mul2(ax1, ay1);
+  float2 cx00, cx01, cx10, cx11, cy00, cy01, cy10, cy11;
+  if (DERIV) {
+    const float2 nfx0 = mul2(fx0, neg1), nfy0 = mul2(fy0, neg1);
+    cx00 = mul2(ay0, nfx0); cx01 = mul2(ay0, fx1); cx10 = mul2(ay1, nfx0); cx11 = mul2(ay1, fx1);
+    cy00 = mul2(ax0, nfy0); cy01 = mul2(ax1, nfy0); cy10 = mul2(ax0, fy1); cy11 = mul2(ax1, fy1);
+  }
+  float4 v00[2], v01[2], v10[2], v11[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    v00[e] = ldg4(pk + o00[e]); v01[e] = ldg4(pk + o01[e]); v10[e] = ldg4(pk + o10[e]); v11[e] = ldg4(pk + o11[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const float a00 = e ? w00.y : w00.x, a01 = e ? w01.y : w01.x, a10 = e ? w10.y : w10.x, a11 = e ? w11.y : w11.x;
+    const float2 rg = fma2(make_float2(v11[e].x, v11[e].y), splat2(a11), fma2(make_float2(v10[e].x, v10[e].y), splat2(a10),
+                      fma2(make_float2(v01[e].x, v01[e].y), splat2(a01), mul2(make_float2(v00[e].x, v00[e].y), splat2(a00)))));
+    out[e].v[0] = rg.x; out[e].v[1] = rg.y;
+    out[e].v[2] = fmaf(v11[e].z, a11, fmaf(v10[e].z, a10, fmaf(v01[e].z, a01, v00[e].z * a00)));
+    if (DERIV) {
+      const float b00 = e ? cx00.y : cx00.x, b01 = e ? cx01.y : cx01.x, b10 = e ? cx10.y : cx10.x, b11 = e ? cx11.y : cx11.x;
+      const float2 dxrg = fma2(make_float2(v11[e].x, v11[e].y), splat2(b11), fma2(make_float2(v10[e].x, v10[e].y), splat2(b10),
+                          fma2(make_float2(v01[e].x, v01[e].y), splat2(b01), mul2(make_float2(v00[e].x, v00[e].y), splat2(b00)))));
+      out[e].dx[0] = dxrg.x; out[e].dx[1] = dxrg.y;
+      out[e].dx[2] = fmaf(v11[e].z, b11, fmaf(v10[e].z, b10, fmaf(v01[e].z, b01, v00[e].z * b00)));
+      const float c00 = e ? cy00.y : cy00.x, c01 = e ? cy01.y : cy01.x, c10 = e ? cy10.y : cy10.x, c11 = e ? cy11.y : cy11.x;
+      const float2 dyrg = fma2(make_float2(v11[e].x, v11[e].y), splat2(c11), fma2(make_float2(v10[e].x, v10[e].y), splat2(c10),
+                          fma2(make_float2(v01[e].x, v01[e].y), splat2(c01), mul2(make_float2(v00[e].x, v00[e].y), splat2(c00)))));
+      out[e].dy[0] = dyrg.x; out[e].dy[1] = dyrg.y;
+      out[e].dy[2] = fmaf(v11[e].z, c11, fmaf(v10[e].z, c10, fmaf(v01[e].z, c01, v00[e].z * c00)));
     }
   }
 }

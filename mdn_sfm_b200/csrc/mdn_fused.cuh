@@ -63,6 +63,8 @@ MDN_DEV void ring_pair(int i, int& r, int& j) {
 
 MDN_DEV float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
+template <bool B> struct BoolTag { static constexpr bool value = B; };
+
 template <bool PHOTO, bool MAPS>
 __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(const __grid_constant__ KParams P) {
   MDN_DYN_SMEM(smem_raw);
@@ -99,6 +101,8 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
   const int ty = rem / S.tiles_x, tx = rem - ty * S.tiles_x;
   const int x0 = tx * TW, y0 = ty * TH;
   const int h = S.h, w = S.w, hw = h * w;
+  const float sx = S.sx, sy = S.sy;      // per-scale constants live in registers, not in indexed constant-bank loads
+  const WarpGeom geom = S.geom;
   // tile holds a pixel whose 3x3 adjoint gather sees a reflected tap (rows 1, h-2 / columns 1, w-2)
   const bool border = (y0 == 0) | (h - 2 >= y0 && h - 2 < y0 + TH) | (x0 == 0) | (w - 2 >= x0 && w - 2 < x0 + TW);
 
@@ -150,23 +154,24 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
 #pragma unroll
   for (int k = 0; k < PR; ++k) mbar[k] = make_float2(0.f, 0.f);
 
-  const float* mob0 = need_mask ? S.mob[0] + (size_t)b * hw : nullptr;
-  const float* mob1 = need_mask ? (shared_mask ? mob0 : S.mob[1] + (size_t)b * hw) : nullptr;
+  const float* mob0 = opaque_ptr(need_mask ? S.mob[0] + (size_t)b * hw : nullptr);
+  const float* mob1 = opaque_ptr(need_mask ? (shared_mask ? mob0 : S.mob[1] + (size_t)b * hw) : nullptr);
 
-  // the two horizontally adjacent values at (y, px0), (y, px1) of a plane; 0 outside the image
+  // the two horizontally adjacent values at (y, px0), (y, px1) of a plane; 0 outside the image.  Offsets are unsigned
+  // 32-bit (one IMAD.WIDE.U32 per address).
   auto load_pair = [&](const float* plane, int y) -> float2 {
     if (!(((unsigned)y < (unsigned)h) & in0)) return make_float2(0.f, 0.f);
-    const float* p = plane + y * w + px0;
+    const float* p = plane + (unsigned)(y * w + px0);
     if (vec) return ldg2(p);
     return make_float2(__ldg(p), in1 ? __ldg(p + 1) : 0.f);
   };
   auto store_pair = [&](float* plane, int y, float2 v) {   // caller guarantees y < h and in0
-    float* p = plane + y * w + px0;
+    float* p = plane + (unsigned)(y * w + px0);
     if (vec) *reinterpret_cast<float2*>(p) = v;
     else { p[0] = v.x; if (in1) p[1] = v.y; }
   };
   auto load_one = [&](const float* plane, int y, int x) -> float {
-    return (((unsigned)y < (unsigned)h) & ((unsigned)x < (unsigned)w)) ? __ldg(plane + y * w + x) : 0.f;
+    return (((unsigned)y < (unsigned)h) & ((unsigned)x < (unsigned)w)) ? __ldg(plane + (unsigned)(y * w + x)) : 0.f;
   };
 
   // ---- tail (per mask q): smoothness + consistency + routing of d/dmask to the mobile maps, rolled over the rows
@@ -177,108 +182,119 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
     for (int k = 0; k < TAIL_SLOTS; ++k) acc[k] = 0.f;
     // in MIN / SHARED mode the reference evaluates smooth_loss once per source frame with the SAME mask
     const float rep = own ? 1.f : (float)P.n_pairs;
-    const float cx = rep * S.c_smx, cy = rep * S.c_smy;
+    const float cx = rep * S.c_smx, cy = rep * S.c_smy, cc40 = S.c_consis * 40.f;
     const float third_l2e = (1.f / 3.f) * 1.4426950408889634f;
     const float* mq = (own && q) ? mob1 : mob0;     // first raw map the stencil reads
-    // raw maps of the row below the current one (the loop carries current / above), the stencil mask derived from them
+    // Software pipeline over rows: iteration k works on row py0 + k (mask / target rows above and below are carried
+    // in registers), turns the row loaded ONE iteration ago into "the row below", and issues the global loads of
+    // row py0 + k + 2 -- no load is consumed in the iteration that issues it.  k = -3 .. -1 only fill the pipeline.
     float2 a0c = make_float2(0.f, 0.f), a1c = a0c, mc = a0c, mu = a0c;
+    float2 a0p = a0c, a1p = a0c;                        // pending: raw maps of row py0 + k + 1
+    float mlp = 0.f, mrp = 0.f, mlc = 0.f, mrc = 0.f;   // stencil mask left / right of the patch: pending, current row
     float2 tc[3];
     float2 evu = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < 3; ++c) tc[c] = make_float2(0.f, 0.f);
-    // iteration k works on row py0 + k with the rows above / below carried in registers; it loads row py0 + k + 1,
-    // so k = -2 and -1 only fill the pipeline (rows py0 - 1 and py0)
 #pragma unroll 1
-    for (int k = -2; k < PR; ++k) {
-      const int y = py0 + k;                        // current row; this iteration loads row y + 1
-      const float2 a0n = load_pair(mq, y + 1);
-      const float2 a1n = minmode ? load_pair(mob1, y + 1) : a0n;
-      const float2 mn = minmode ? make_float2((a0n.x <= a1n.x) ? a0n.x : a1n.x, (a0n.y <= a1n.y) ? a0n.y : a1n.y) : a0n;
-      float2 tn[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) tn[c] = make_float2(0.f, 0.f);
-      float2 evd = make_float2(0.f, 0.f);           // vertical edge weights (y | y+1) of the two columns
-      if (smooth_on) {
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          tn[c] = ld2s(sm.T + c * R2P + o2own + (k + 1) * S2);
-          s0 += fabsf(tc[c].x - tn[c].x); s1 += fabsf(tc[c].y - tn[c].y);
-        }
-        const bool ok = (y >= 0) & (y + 1 < h);
-        evd.x = (ok & in0) ? ex2_fast(-s0 * third_l2e) : 0.f;
-        evd.y = (ok & in1) ? ex2_fast(-s1 * third_l2e) : 0.f;
+    for (int k = -3; k < PR; ++k) {
+      const int y = py0 + k;                        // current row
+      // (a) issue the loads of row y + 2
+      const float2 a0q = load_pair(mq, y + 2);
+      const float2 a1q = minmode ? load_pair(mob1, y + 2) : a0q;
+      float l0 = 0.f, l1 = 0.f, r0 = 0.f, r1 = 0.f;
+      if (smooth_on & (k + 2 >= 0) & (k + 2 < PR)) {
+        l0 = load_one(mq, y + 2, px0 - 1); r0 = load_one(mq, y + 2, px1 + 1);
+        if (minmode) { l1 = load_one(mob1, y + 2, px0 - 1); r1 = load_one(mob1, y + 2, px1 + 1); }
       }
-      if (k >= 0 && (y < h) & in0) {
-        float2 gm = mbar[0];
+      if (k >= -2) {
+        // (b) the row below the current one = what was pending
+        const float2 a0n = a0p, a1n = a1p;
+        const float2 mn = minmode ? make_float2((a0n.x <= a1n.x) ? a0n.x : a1n.x, (a0n.y <= a1n.y) ? a0n.y : a1n.y) : a0n;
+        float2 tn[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tn[c] = make_float2(0.f, 0.f);
+        float2 evd = make_float2(0.f, 0.f);           // vertical edge weights (y | y+1) of the two columns
         if (smooth_on) {
-          // horizontal edges (x-1|x), (x|x+1), (x+1|x+2) of this row
-          float sl = 0.f, smid = 0.f, sr = 0.f;
+          float s0 = 0.f, s1 = 0.f;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float* Tr = sm.T + c * R2P + o2own + k * S2;
-            const float tl = Tr[-1], tr = Tr[2];
-            sl += fabsf(tl - tc[c].x); smid += fabsf(tc[c].x - tc[c].y); sr += fabsf(tc[c].y - tr);
+            tn[c] = ld2s(sm.T + c * R2P + o2own + (k + 1) * S2);
+            s0 += fabsf(tc[c].x - tn[c].x); s1 += fabsf(tc[c].y - tn[c].y);
           }
-          const float e0 = (px0 > 0) ? ex2_fast(-sl * third_l2e) : 0.f;
-          const float e1 = in1 ? ex2_fast(-smid * third_l2e) : 0.f;
-          const float e2 = (px1 + 1 < w) ? ex2_fast(-sr * third_l2e) : 0.f;
-          float ml, mr;
-          if (minmode) {
-            const float l0 = load_one(mob0, y, px0 - 1), l1 = load_one(mob1, y, px0 - 1);
-            const float r0 = load_one(mob0, y, px1 + 1), r1 = load_one(mob1, y, px1 + 1);
-            ml = (l0 <= l1) ? l0 : l1; mr = (r0 <= r1) ? r0 : r1;
-          } else { ml = load_one(mq, y, px0 - 1); mr = load_one(mq, y, px1 + 1); }
-          // d0 = m(x-1) - m(x), d1 = m(x) - m(x+1), d2 = m(x+1) - m(x+2); each pixel counts its right / lower edge
-          const float d0 = ml - mc.x, d1 = mc.x - mc.y, d2 = mc.y - mr;
-          acc[SL_SMX + 2 * q] += fabsf(d1) * e1 + fabsf(d2) * e2;
-          const float s0 = signf_(d0) * e0, s1 = signf_(d1) * e1, s2 = signf_(d2) * e2;
-          const float u0 = mu.x - mc.x, u1 = mu.y - mc.y, n0 = mc.x - mn.x, n1 = mc.y - mn.y;
-          acc[SL_SMY + 2 * q] += fabsf(n0) * evd.x + fabsf(n1) * evd.y;
-          gm.x += cx * (s1 - s0) + cy * (signf_(n0) * evd.x - signf_(u0) * evu.x);
-          gm.y += cx * (s2 - s1) + cy * (signf_(n1) * evd.y - signf_(u1) * evu.y);
+          const bool ok = (y >= 0) & (y + 1 < h);
+          evd.x = (ok & in0) ? ex2_fast(-s0 * third_l2e) : 0.f;
+          evd.y = (ok & in1) ? ex2_fast(-s1 * third_l2e) : 0.f;
         }
-        float2 g0, g1;
-        if (own) { g0 = q ? make_float2(0.f, 0.f) : gm; g1 = q ? gm : make_float2(0.f, 0.f); }
-        else if (shared_mask) { g0 = gm; g1 = make_float2(0.f, 0.f); }
-        else {
-          const bool f0 = a0c.x <= a1c.x, f1 = a0c.y <= a1c.y;
-          g0 = make_float2(f0 ? gm.x : 0.f, f1 ? gm.y : 0.f);
-          g1 = make_float2(f0 ? 0.f : gm.x, f1 ? 0.f : gm.y);
-        }
-        // raw maps of this row: (a0c, a1c) are (first map read, second) = (map q, -) in OWN mode
-        const float2 r0 = (own && q) ? (consis_on ? load_pair(mob0, y) : a0c) : a0c;
-        const float2 r1 = own ? (q ? a0c : (consis_on ? load_pair(mob1, y) : a0c)) : a1c;
-        if (consis_on) {
-          // sigmoid(20 (m - 0.5)) = 1 / (1 + 2^(-20 log2(e) (m - 0.5)))
-          const float kk = -20.f * 1.4426950408889634f;
-          const float p0 = rcp_fast(1.f + ex2_fast(kk * (r0.x - 0.5f))), q0 = rcp_fast(1.f + ex2_fast(kk * (r1.x - 0.5f)));
-          const float p1 = rcp_fast(1.f + ex2_fast(kk * (r0.y - 0.5f))), q1 = rcp_fast(1.f + ex2_fast(kk * (r1.y - 0.5f)));
-          const float df0 = p0 - q0, df1 = in1 ? p1 - q1 : 0.f;
-          // OWN mode visits every pixel once per map: count the value once, and give each map its own gradient
-          if (!own || q == 0) {
-            acc[SL_CONSIS] += df0 * df0 + df1 * df1;
-            g0.x += S.c_consis * 40.f * df0 * p0 * (1.f - p0);
-            g0.y += S.c_consis * 40.f * df1 * p1 * (1.f - p1);
-          }
-          if (!own || q == 1 || P.n_pairs == 1) {
-            g1.x -= S.c_consis * 40.f * df0 * q0 * (1.f - q0);
-            g1.y -= S.c_consis * 40.f * df1 * q1 * (1.f - q1);
-          }
-        }
-        if (grads) {
-          if (S.g_mob[0] && (!own || q == 0)) store_pair(S.g_mob[0] + (size_t)b * hw, y, g0);
-          if (S.g_mob[1] && !shared_mask && (!own || q == 1 || P.n_pairs == 1)) store_pair(S.g_mob[1] + (size_t)b * hw, y, g1);
-        }
-      }
-      if (k >= 0) {   // rotate the gradient ring (and clear it for the next use)
+        if (k >= 0 && (y < h) & in0) {
+          float2 gm = mbar[0];
+          if (smooth_on) {
+            // horizontal edges (x-1|x), (x|x+1), (x+1|x+2) of this row
+            float sl = 0.f, smid = 0.f, sr = 0.f;
 #pragma unroll
-        for (int i = 0; i + 1 < PR; ++i) mbar[i] = mbar[i + 1];
-        mbar[PR - 1] = make_float2(0.f, 0.f);
-      }
-      mu = mc; mc = mn; a0c = a0n; a1c = a1n; evu = evd;
+            for (int c = 0; c < 3; ++c) {
+              const float* Tr = sm.T + c * R2P + o2own + k * S2;
+              const float tl = Tr[-1], tr = Tr[2];
+              sl += fabsf(tl - tc[c].x); smid += fabsf(tc[c].x - tc[c].y); sr += fabsf(tc[c].y - tr);
+            }
+            const float e0 = (px0 > 0) ? ex2_fast(-sl * third_l2e) : 0.f;
+            const float e1 = in1 ? ex2_fast(-smid * third_l2e) : 0.f;
+            const float e2 = (px1 + 1 < w) ? ex2_fast(-sr * third_l2e) : 0.f;
+            // d0 = m(x-1) - m(x), d1 = m(x) - m(x+1), d2 = m(x+1) - m(x+2); each pixel counts its right / lower edge
+            const float d0 = mlc - mc.x, d1 = mc.x - mc.y, d2 = mc.y - mrc;
+            acc[SL_SMX + 2 * q] += fabsf(d1) * e1 + fabsf(d2) * e2;
+            const float s0 = signf_(d0) * e0, s1 = signf_(d1) * e1, s2 = signf_(d2) * e2;
+            const float u0 = mu.x - mc.x, u1 = mu.y - mc.y, n0 = mc.x - mn.x, n1 = mc.y - mn.y;
+            acc[SL_SMY + 2 * q] += fabsf(n0) * evd.x + fabsf(n1) * evd.y;
+            gm.x += cx * (s1 - s0) + cy * (signf_(n0) * evd.x - signf_(u0) * evu.x);
+            gm.y += cx * (s2 - s1) + cy * (signf_(n1) * evd.y - signf_(u1) * evu.y);
+          }
+          float2 g0, g1;
+          if (own) { g0 = q ? make_float2(0.f, 0.f) : gm; g1 = q ? gm : make_float2(0.f, 0.f); }
+          else if (shared_mask) { g0 = gm; g1 = make_float2(0.f, 0.f); }
+          else {
+            const bool f0 = a0c.x <= a1c.x, f1 = a0c.y <= a1c.y;
+            g0 = make_float2(f0 ? gm.x : 0.f, f1 ? gm.y : 0.f);
+            g1 = make_float2(f0 ? 0.f : gm.x, f1 ? 0.f : gm.y);
+          }
+          if (consis_on) {
+            // raw maps of this row: (a0c, a1c) are (first map read, second) = (map q, -) in OWN mode
+            const float2 v0 = (own && q) ? load_pair(mob0, y) : a0c;
+            const float2 v1 = own ? (q ? a0c : load_pair(mob1, y)) : a1c;
+            // sigmoid(20 (m - 0.5)) = 1 / (1 + 2^(-20 log2(e) (m - 0.5)))
+            const float kk = -20.f * 1.4426950408889634f;
+            const float p0 = rcp_fast(1.f + ex2_fast(kk * (v0.x - 0.5f))), q0 = rcp_fast(1.f + ex2_fast(kk * (v1.x - 0.5f)));
+            const float p1 = rcp_fast(1.f + ex2_fast(kk * (v0.y - 0.5f))), q1 = rcp_fast(1.f + ex2_fast(kk * (v1.y - 0.5f)));
+            const float df0 = p0 - q0, df1 = in1 ? p1 - q1 : 0.f;
+            // OWN mode visits every pixel once per map: count the value once, and give each map its own gradient
+            if (!own || q == 0) {
+              acc[SL_CONSIS] += df0 * df0 + df1 * df1;
+              g0.x += cc40 * df0 * p0 * (1.f - p0);
+              g0.y += cc40 * df1 * p1 * (1.f - p1);
+            }
+            if (!own || q == 1 || P.n_pairs == 1) {
+              g1.x -= cc40 * df0 * q0 * (1.f - q0);
+              g1.y -= cc40 * df1 * q1 * (1.f - q1);
+            }
+          }
+          if (grads) {
+            if (S.g_mob[0] && (!own || q == 0)) store_pair(S.g_mob[0] + (size_t)b * hw, y, g0);
+            if (S.g_mob[1] && !shared_mask && (!own || q == 1 || P.n_pairs == 1)) store_pair(S.g_mob[1] + (size_t)b * hw, y, g1);
+          }
+        }
+        if (k >= 0) {   // rotate the gradient ring (and clear it for the next use)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) tc[c] = tn[c];
+          for (int i = 0; i + 1 < PR; ++i) mbar[i] = mbar[i + 1];
+          mbar[PR - 1] = make_float2(0.f, 0.f);
+        }
+        mu = mc; mc = mn; a0c = a0n; a1c = a1n; evu = evd;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tc[c] = tn[c];
+        mlc = mlp; mrc = mrp;
+      }
+      // (c) what was loaded in (a) becomes pending (its first use is one iteration away)
+      a0p = a0q; a1p = a1q;
+      mlp = minmode ? ((l0 <= l1) ? l0 : l1) : l0;
+      mrp = minmode ? ((r0 <= r1) ? r0 : r1) : r0;
     }
     flush_acc<TAIL_SLOTS>(acc, sm.red, TAIL_BASE);
   };
@@ -289,68 +305,108 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
     float acc[PAIR_SLOTS];
 #pragma unroll
     for (int k = 0; k < PAIR_SLOTS; ++k) acc[k] = 0.f;
-    const float* flx = S.flow[pair] + (size_t)b * 2 * hw;
-    const float* fly = flx + hw;
+    const float* flx = opaque_ptr(S.flow[pair] + (size_t)b * 2 * hw);
+    const float* fly = opaque_ptr(flx + hw);
     float2 gix[PR], giy[PR];         // d(loss)/d(ix), d(loss)/d(iy) of the own pixels
 #pragma unroll
     for (int k = 0; k < PR; ++k) { gix[k] = giy[k] = make_float2(0.f, 0.f); }
 
     if (PHOTO) {
-      const float* rf = S.ref[pair] + (size_t)b * 3 * hw;
+      const float4* rfp = opaque_ptr(S.refp[pair] + (size_t)b * hw);   // source image, (r, g, b, -) per pixel
       unsigned vbits = 0;            // validity of own pixel (k, e): bit 2k + e
-      // -- P1: own pairs (it < PR), then this thread's share of the halo ring
+      // -- P1: own pairs (it < PR), then this thread's share of the halo ring.  The flow of the NEXT slot is loaded
+      // before the gather of the current one, so the dependent load chain flow -> coordinates -> gather overlaps.
       constexpr int N_IT = PR + (RINGP + FT - 1) / FT;
-#pragma unroll 1
-      for (int it = 0; it < N_IT; ++it) {
-        int r, j;
-        const bool own_it = it < PR;
-        if (own_it) { r = PR * g + 2 + it; j = 2 * t + 2; }
-        else {
+      struct Slot { int r, j, ya, xa, xb; float2 fx, fy; bool live; };
+      auto prep = [&](int it, Slot& q) {
+        q.live = it < N_IT;
+        q.r = PR * g + 2 + it; q.j = 2 * t + 2;
+        if (it >= PR) {
           const int i = tid + (it - PR) * FT;
-          if (i >= RINGP) break;
-          ring_pair(i, r, j);
+          q.live = q.live & (i < RINGP);
+          ring_pair(q.live ? i : 0, q.r, q.j);
         }
         // source pixels of the two slots: real pixels inside the image, reflected copies on the padding ring
-        const int ya = stage_index(y0 - 2 + r, h);
-        const int xa = stage_index(x0 - 2 + j, w), xb = stage_index(x0 - 1 + j, w);
-        const bool oka = (ya | xa) >= 0, okb = (ya | xb) >= 0;
-        float2 fxr, fyr;
-        if (oka & okb & weven & (xb == xa + 1)) {
-          fxr = ldg2(flx + ya * w + xa); fyr = ldg2(fly + ya * w + xa);
-        } else {
-          const int oa = oka ? ya * w + xa : 0, ob = okb ? ya * w + xb : 0;
-          fxr = make_float2(__ldg(flx + oa), __ldg(flx + ob)); fyr = make_float2(__ldg(fly + oa), __ldg(fly + ob));
+        q.ya = stage_index(y0 - 2 + q.r, h);
+        q.xa = stage_index(x0 - 2 + q.j, w); q.xb = stage_index(x0 - 1 + q.j, w);
+        q.fx = q.fy = make_float2(0.f, 0.f);
+        if (q.live) {
+          const bool oka = (q.ya | q.xa) >= 0, okb = (q.ya | q.xb) >= 0;
+          if (oka & okb & weven & (q.xb == q.xa + 1)) {
+            const unsigned o = q.ya * w + q.xa;
+            q.fx = ldg2(flx + o); q.fy = ldg2(fly + o);
+          } else {
+            const unsigned oa = oka ? q.ya * w + q.xa : 0, ob = okb ? q.ya * w + q.xb : 0;
+            q.fx = make_float2(__ldg(flx + oa), __ldg(flx + ob)); q.fy = make_float2(__ldg(fly + oa), __ldg(fly + ob));
+          }
         }
-        Gather2 G2;
-        // flow -> pixels with SCALAR multiplies: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it honours
-        // .rn only for scalar ops), which would move x + sx * f by an ulp and flip bilinear cells
-        const float2 fxp = make_float2(__fmul_rn(S.sx, fxr.x), __fmul_rn(S.sx, fxr.y));
-        const float2 fyp = make_float2(__fmul_rn(S.sy, fyr.x), __fmul_rn(S.sy, fyr.y));
-        gather_pair<true>(rf, hw, h, w, make_float2((float)xa, (float)xb), splat2((float)ya), fxp, fyp, S.geom, G2);
-        const float2 okm = make_float2(oka ? 1.f : 0.f, okb ? 1.f : 0.f);
+      };
+      // stores one gathered pair: warped values -> sW, and for an own pair (k >= 0) derivatives -> sD, validity bits
+      auto put = [&](const GatherPx* G2, bool valid_a, bool valid_b, int r, int j, bool oka, bool okb, int k) {
         float* Wd = sm.W + OFF2 + r * S2 + j;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) st2s(Wd + c * R2P, mul2(G2.val[c], okm));
-        if (own_it) {
+        for (int c = 0; c < 3; ++c) st2s(Wd + c * R2P, make_float2(oka ? G2[0].v[c] : 0.f, okb ? G2[1].v[c] : 0.f));
+        if (k >= 0) {
           const int y = y0 - 2 + r;
           const bool ra = (y < h) & in0, rb = (y < h) & in1;     // real pixels (not padding)
-          vbits |= ((G2.valid_a & ra) ? 1u : 0u) << (2 * it);
-          vbits |= ((G2.valid_b & rb) ? 2u : 0u) << (2 * it);
-          float* Dd = sm.D + (it * FT + tid) * 2;
+          vbits |= ((valid_a & ra) ? 1u : 0u) << (2 * k);
+          vbits |= ((valid_b & rb) ? 2u : 0u) << (2 * k);
+          float* Dd = sm.D + (k * FT + tid) * 2;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) { st2s(Dd + (2 * c) * PR * FT * 2, G2.dx[c]); st2s(Dd + (2 * c + 1) * PR * FT * 2, G2.dy[c]); }
+          for (int c = 0; c < 3; ++c) {
+            st2s(Dd + (2 * c) * PR * FT * 2, make_float2(G2[0].dx[c], G2[1].dx[c]));
+            st2s(Dd + (2 * c + 1) * PR * FT * 2, make_float2(G2[0].dy[c], G2[1].dy[c]));
+          }
           if (MAPS && ra) {
             const size_t o = (size_t)y * w + px0;
-            if (S.valid[pair]) { S.valid[pair][(size_t)b * hw + o] = G2.valid_a ? 1 : 0; if (rb) S.valid[pair][(size_t)b * hw + o + 1] = G2.valid_b ? 1 : 0; }
+            if (S.valid[pair]) { S.valid[pair][(size_t)b * hw + o] = valid_a ? 1 : 0; if (rb) S.valid[pair][(size_t)b * hw + o + 1] = valid_b ? 1 : 0; }
             if (S.warped[pair]) {
 #pragma unroll
               for (int c = 0; c < 3; ++c) {
-                S.warped[pair][((size_t)b * 3 + c) * hw + o] = G2.val[c].x;
-                if (rb) S.warped[pair][((size_t)b * 3 + c) * hw + o + 1] = G2.val[c].y;
+                S.warped[pair][((size_t)b * 3 + c) * hw + o] = G2[0].v[c];
+                if (rb) S.warped[pair][((size_t)b * 3 + c) * hw + o + 1] = G2[1].v[c];
               }
             }
           }
         }
+      };
+      // tiles that lie fully inside an even-width image (the common case): the own pairs are real, 8-byte aligned
+      // pixels -- no reflection / slot arithmetic, one LDG.64 per flow plane, next row's flow loaded a row ahead
+      const bool tile_full = weven & (x0 + TW <= w) & (y0 + TH <= h);
+      if (tile_full) {
+        unsigned o = (unsigned)(py0 * w + px0);
+        float2 fxn = ldg2(flx + o), fyn = ldg2(fly + o);
+        const float2 xs = make_float2((float)px0, (float)px1);
+#pragma unroll 1
+        for (int k = 0; k < PR; ++k) {
+          const float2 fxc = fxn, fyc = fyn;
+          o += w;
+          if (k + 1 < PR) { fxn = ldg2(flx + o); fyn = ldg2(fly + o); }
+          const float2 fxp = make_float2(__fmul_rn(sx, fxc.x), __fmul_rn(sx, fxc.y));
+          const float2 fyp = make_float2(__fmul_rn(sy, fyc.x), __fmul_rn(sy, fyc.y));
+          GatherPx G2[2];
+          bool va, vb;
+          gather_pair_packed<true>(rfp, h, w, xs, splat2((float)(py0 + k)), fxp, fyp, geom, G2, va, vb);
+          put(G2, va, vb, PR * g + 2 + k, 2 * t + 2, true, true, k);
+        }
+      }
+      const int it0 = tile_full ? PR : 0;
+      Slot cur;
+      prep(it0, cur);
+#pragma unroll 1
+      for (int it = it0; it < N_IT; ++it) {
+        Slot nxt;
+        prep(it + 1, nxt);
+        if (!cur.live) break;
+        const bool oka = (cur.ya | cur.xa) >= 0, okb = (cur.ya | cur.xb) >= 0;
+        // flow -> pixels with SCALAR multiplies (see gather_pair)
+        const float2 fxp = make_float2(__fmul_rn(sx, cur.fx.x), __fmul_rn(sx, cur.fx.y));
+        const float2 fyp = make_float2(__fmul_rn(sy, cur.fy.x), __fmul_rn(sy, cur.fy.y));
+        GatherPx G2[2];
+        bool va, vb;
+        gather_pair_packed<true>(rfp, h, w, make_float2((float)cur.xa, (float)cur.xb), splat2((float)cur.ya), fxp, fyp, geom, G2, va, vb);
+        put(G2, va, vb, cur.r, cur.j, oka, okb, it < PR ? it : -1);
+        cur = nxt;
       }
       if (!staged) { cp_async_wait_all(); staged = true; }
       __syncthreads();
@@ -359,24 +415,81 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
 #pragma unroll
       for (int k = 0; k < PR; ++k) vmask[k] = make_float2((vbits >> (2 * k)) & 1u ? 1.f : 0.f, (vbits >> (2 * k + 1)) & 1u ? 1.f : 0.f);
 
-      // reflection multiplicities of the adjoint gather (border tiles only): pixel column 1 / w-2 and pixel row
-      // 1 / h-2 collect the out-of-image tap of the windows in column 0 / w-1 and row 0 / h-1 a second time
-      float2 fl = make_float2(0.f, 0.f), fr = fl;
-      float ft[PR], fb[PR];
+      const float kq = S.c_ssim * (1.f / 9.f), c_l1 = S.c_l1;
+
+      // -- P3: the own pixels of channel c.  BORDER adds the reflection multiplicities of the adjoint gather: pixel
+      // column 1 / w-2 and pixel row 1 / h-2 collect the out-of-image tap of the windows in column 0 / w-1 and row
+      // 0 / h-1 a second time.  Two instantiations, selected by a block-uniform branch.
+      auto p3 = [&](const int c, auto border_tag) {
+        constexpr bool BORDER = decltype(border_tag)::value;
+        float2 tv[PR], wv[PR];
 #pragma unroll
-      for (int k = 0; k < PR; ++k) ft[k] = fb[k] = 0.f;
-      if (border) {
-        fl = make_float2(px0 == 1 ? 1.f : 0.f, px1 == 1 ? 1.f : 0.f);
-        fr = make_float2(px0 == w - 2 ? 1.f : 0.f, px1 == w - 2 ? 1.f : 0.f);
+        for (int k = 0; k < PR; ++k) {
+          tv[k] = ld2s(sm.T + c * R2P + o2own + k * S2);
+          wv[k] = ld2s(sm.W + c * R2P + o2own + k * S2);
+        }
+        float2 wbar[PR];
 #pragma unroll
-        for (int k = 0; k < PR; ++k) { ft[k] = (py0 + k == 1) ? 1.f : 0.f; fb[k] = (py0 + k == h - 2) ? 1.f : 0.f; }
-      }
+        for (int k = 0; k < PR; ++k) wbar[k] = make_float2(0.f, 0.f);
+        if (use_ssim & grads) {
+          float2 fl = make_float2(0.f, 0.f), fr = fl;
+          if (BORDER) {
+            fl = make_float2(px0 == 1 ? 1.f : 0.f, px1 == 1 ? 1.f : 0.f);
+            fr = make_float2(px0 == w - 2 ? 1.f : 0.f, px1 == w - 2 ? 1.f : 0.f);
+          }
+          float2 Sg[3][PR];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const float* Qa = sm.Q + a * R1P + (PR * g) * S1 + 2 * t;
+            float2 Hq[PR + 2];
+#pragma unroll
+            for (int rr = 0; rr < PR + 2; ++rr) {
+              const float2 qa = ld2s(Qa + rr * S1), qb = ld2s(Qa + rr * S1 + 2);
+              const float m = qa.y + qb.x;
+              Hq[rr] = make_float2(qa.x + m, m + qb.y);
+              if (BORDER) Hq[rr] = fma2(fr, qb, fma2(fl, qa, Hq[rr]));
+            }
+#pragma unroll
+            for (int k = 0; k < PR; k += 2) {       // rows k, k+1 share Hq[k+1] + Hq[k+2]
+              const float2 m12 = add2(Hq[k + 1], Hq[k + 2]);
+              Sg[a][k] = add2(Hq[k], m12); Sg[a][k + 1] = add2(m12, Hq[k + 3]);
+            }
+            if (BORDER) {
+#pragma unroll
+              for (int k = 0; k < PR; ++k) {
+                const float ftk = (py0 + k == 1) ? 1.f : 0.f, fbk = (py0 + k == h - 2) ? 1.f : 0.f;
+                Sg[a][k] = fma2(splat2(fbk), Hq[k + 2], fma2(splat2(ftk), Hq[k], Sg[a][k]));
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < PR; ++k) wbar[k] = fma2(tv[k], Sg[2][k], fma2(wv[k], Sg[1][k], Sg[0][k]));
+        }
+        // L1 term: |tgt - warped| * valid  (loss_functions.py:109-110)
+#pragma unroll
+        for (int k = 0; k < PR; ++k) {
+          const float d0 = tv[k].x - wv[k].x, d1 = tv[k].y - wv[k].y;
+          const float a0 = fabsf(d0) * vmask[k].x, a1 = fabsf(d1) * vmask[k].y;
+          acc[SL_L1] += a0 + a1;
+          if (MAPS && S.diff[pair]) {
+            const int y = py0 + k;
+            if ((y < h) & in0) S.diff[pair][((size_t)b * 3 + c) * hw + (size_t)y * w + px0] = a0;
+            if ((y < h) & in1) S.diff[pair][((size_t)b * 3 + c) * hw + (size_t)y * w + px1] = a1;
+          }
+          if (grads) {
+            wbar[k].x -= c_l1 * signf_(d0) * vmask[k].x;
+            wbar[k].y -= c_l1 * signf_(d1) * vmask[k].y;
+            const float* Dd = sm.D + (k * FT + tid) * 2 + (2 * c) * PR * FT * 2;
+            gix[k] = fma2(wbar[k], ld2s(Dd), gix[k]);
+            giy[k] = fma2(wbar[k], ld2s(Dd + PR * FT * 2), giy[k]);
+          }
+        }
+      };
 
 #pragma unroll 1
       for (int c = 0; c < 3; ++c) {
         // -- P2: SSIM windows of channel c, 2 columns x WPR rows per patch
         if (use_ssim) {
-          const float kq = S.c_ssim * (1.f / 9.f);
 #pragma unroll 1
           for (int patch = tid; patch < NPATCH; patch += FT) {
             const int rg = patch / NCP, cp = patch - rg * NCP;
@@ -409,9 +522,9 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
 #pragma unroll
                 for (int m = 0; m < 5; ++m) V[m] = add2(add2(H[0][m], H[1][m]), H[2][m]);
                 const Ssim2 so = ssim_window2(V[0], V[1], V[2], V[3], V[4], ri ? kcol : make_float2(0.f, 0.f));
-                const float rit = (ri & (r1 >= 1) & (r1 <= TH)) ? 1.f : 0.f;
-                acc[SL_SSIM] += so.J.x * (rit * it0) + so.J.y * (rit * it1);
-                if (MAPS && S.ssim_map[pair] && rit != 0.f) {
+                const bool rit = ri & (r1 >= 1) & (r1 <= TH);
+                acc[SL_SSIM] += rit ? fmaf(so.J.x, it0, so.J.y * it1) : 0.f;
+                if (MAPS && S.ssim_map[pair] && rit) {
                   float* dst = S.ssim_map[pair] + ((size_t)b * 3 + c) * hw + (size_t)wy * w + wx0;
                   if (it0 != 0.f) dst[0] = so.J.x;
                   if (it1 != 0.f) dst[1] = so.J.y;
@@ -423,70 +536,15 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
           }
           __syncthreads();
         }
-        // -- P3: the own pixels of channel c
-        {
-          float2 tv[PR], wv[PR];
-#pragma unroll
-          for (int k = 0; k < PR; ++k) {
-            tv[k] = ld2s(sm.T + c * R2P + o2own + k * S2);
-            wv[k] = ld2s(sm.W + c * R2P + o2own + k * S2);
-          }
-          float2 wbar[PR];
-#pragma unroll
-          for (int k = 0; k < PR; ++k) wbar[k] = make_float2(0.f, 0.f);
-          if (use_ssim & grads) {
-            float2 Sg[3][PR];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-              const float* Qa = sm.Q + a * R1P + (PR * g) * S1 + 2 * t;
-              float2 Hq[PR + 2];
-#pragma unroll
-              for (int rr = 0; rr < PR + 2; ++rr) {
-                const float2 qa = ld2s(Qa + rr * S1), qb = ld2s(Qa + rr * S1 + 2);
-                const float m = qa.y + qb.x;
-                Hq[rr] = make_float2(qa.x + m, m + qb.y);
-                if (border) Hq[rr] = fma2(fr, qb, fma2(fl, qa, Hq[rr]));
-              }
-#pragma unroll
-              for (int k = 0; k < PR; k += 2) {       // rows k, k+1 share Hq[k+1] + Hq[k+2]
-                const float2 m12 = add2(Hq[k + 1], Hq[k + 2]);
-                Sg[a][k] = add2(Hq[k], m12); Sg[a][k + 1] = add2(m12, Hq[k + 3]);
-              }
-              if (border) {
-#pragma unroll
-                for (int k = 0; k < PR; ++k) Sg[a][k] = fma2(splat2(fb[k]), Hq[k + 2], fma2(splat2(ft[k]), Hq[k], Sg[a][k]));
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < PR; ++k) wbar[k] = fma2(tv[k], Sg[2][k], fma2(wv[k], Sg[1][k], Sg[0][k]));
-          }
-          // L1 term: |tgt - warped| * valid  (loss_functions.py:109-110)
-#pragma unroll
-          for (int k = 0; k < PR; ++k) {
-            const float d0 = tv[k].x - wv[k].x, d1 = tv[k].y - wv[k].y;
-            const float a0 = fabsf(d0) * vmask[k].x, a1 = fabsf(d1) * vmask[k].y;
-            acc[SL_L1] += a0 + a1;
-            if (MAPS && S.diff[pair]) {
-              const int y = py0 + k;
-              if ((y < h) & in0) S.diff[pair][((size_t)b * 3 + c) * hw + (size_t)y * w + px0] = a0;
-              if ((y < h) & in1) S.diff[pair][((size_t)b * 3 + c) * hw + (size_t)y * w + px1] = a1;
-            }
-            if (grads) {
-              wbar[k].x -= S.c_l1 * signf_(d0) * vmask[k].x;
-              wbar[k].y -= S.c_l1 * signf_(d1) * vmask[k].y;
-              const float* Dd = sm.D + (k * FT + tid) * 2 + (2 * c) * PR * FT * 2;
-              gix[k] = fma2(wbar[k], ld2s(Dd), gix[k]);
-              giy[k] = fma2(wbar[k], ld2s(Dd + PR * FT * 2), giy[k]);
-            }
-          }
-        }
+        if (border) p3(c, BoolTag<true>()); else p3(c, BoolTag<false>());
         if (use_ssim) __syncthreads();   // Q (and, after the last channel, W) is rewritten next
       }
     }
 
     if (!PHOTO && !staged) { cp_async_wait_all(); staged = true; __syncthreads(); }
 
-    // -- P4: epipolar forward + adjoint, d(loss)/d(flow); rolled over the rows of the patch (gix / giy / mbar rotate)
+    // -- P4: epipolar forward + adjoint, d(loss)/d(flow); rolled over the rows of the patch (gix / giy / mbar rotate),
+    // the global loads of row k + 1 are issued before row k is computed
     {
       float Fm[9];
       float snmax = 1.f;
@@ -498,58 +556,72 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
           snmax = __uint_as_float((unsigned)(key >> 32));
         }
       }
+      const float c_epi = S.c_epi, c_nt = S.c_nt, c_ce = S.c_ce;
+      float* gflx = opaque_ptr(S.g_flow[pair] ? S.g_flow[pair] + (size_t)b * 2 * hw : nullptr);
+      float* gfly = opaque_ptr(gflx ? gflx + hw : nullptr);
       const float* mq0 = (own && pair) ? mob1 : mob0;
+      const bool use_inst = (P.flags & (MDN_OPT_INST_MASK | MDN_OPT_CROSS_ENT)) != 0, use_wgt = P.post == MDN_POST_TG;
+      struct Row { float2 fx, fy, m0, m1, kin, wgt; };
+      auto fetch = [&](int k, Row& R) {
+        const int y = py0 + k;
+        R.kin = R.wgt = make_float2(1.f, 1.f);
+        R.fx = R.fy = R.m0 = R.m1 = make_float2(0.f, 0.f);
+        if (epi_on & (k < PR)) {
+          R.fx = load_pair(flx, y); R.fy = load_pair(fly, y);
+          R.m0 = load_pair(mq0, y);
+          R.m1 = minmode ? load_pair(mob1, y) : R.m0;
+          if (use_wgt) R.wgt = load_pair(S.weight, y);
+          if (use_inst & (y < h) & in0) {
+            const uint8_t* ip = S.inst + (size_t)b * hw + (unsigned)(y * w + px0);
+            R.kin = make_float2((float)__ldg(ip), in1 ? (float)__ldg(ip + 1) : 0.f);
+          }
+        }
+      };
+      Row cur;
+      fetch(0, cur);
 #pragma unroll 1
       for (int k = 0; k < PR; ++k) {
+        Row nxt;
+        fetch(k + 1, nxt);
         const int y = py0 + k;
         // (w-1)/2 [grid_sample] * 2 [2g-1] / (w-1) [/= w-1] * sx [scale factor]
-        float gfx[2] = {gix[0].x * S.sx, gix[0].y * S.sx}, gfy[2] = {giy[0].x * S.sy, giy[0].y * S.sy};
+        float gfx[2] = {gix[0].x * sx, gix[0].y * sx}, gfy[2] = {giy[0].x * sy, giy[0].y * sy};
         float mb[2] = {0.f, 0.f};
         if ((y < h) & in0) {
-          const int o = y * w + px0;
           if (epi_on) {
-            const float2 fxr = load_pair(flx, y), fyr = load_pair(fly, y);
-            const float2 m0 = load_pair(mq0, y);
-            const float2 m1 = minmode ? load_pair(mob1, y) : m0;
-            float kin[2] = {1.f, 1.f}, wgt[2] = {1.f, 1.f};
-            if ((P.flags & (MDN_OPT_INST_MASK | MDN_OPT_CROSS_ENT)) != 0) {
-              kin[0] = (float)__ldg(S.inst + (size_t)b * hw + o);
-              kin[1] = in1 ? (float)__ldg(S.inst + (size_t)b * hw + o + 1) : 0.f;
-            }
-            if (P.post == MDN_POST_TG) { wgt[0] = __ldg(S.weight + o); wgt[1] = in1 ? __ldg(S.weight + o + 1) : 1.f; }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               if (e && !in1) continue;
-              const float ma = e ? m0.y : m0.x, mbv = e ? m1.y : m1.x;
+              const float ma = e ? cur.m0.y : cur.m0.x, mbv = e ? cur.m1.y : cur.m1.x;
               const float m = (ma <= mbv) ? ma : mbv;
               const float xf = (float)(px0 + e), yf = (float)y;
-              const float u = __fadd_rn(xf, __fmul_rn(S.sx, e ? fxr.y : fxr.x)), v = __fadd_rn(yf, __fmul_rn(S.sy, e ? fyr.y : fyr.x));
+              const float u = __fadd_rn(xf, __fmul_rn(sx, e ? cur.fx.y : cur.fx.x)), v = __fadd_rn(yf, __fmul_rn(sy, e ? cur.fy.y : cur.fy.x));
               const Epi ep = epipolar_distance(Fm, xf, yf, u, v);
               const float ae = fabsf(ep.d);
               float dpost;
-              float post = post_process(P, ae, snmax, wgt[e], dpost);
-              const float kmask = kin[e];
+              float post = post_process(P, ae, snmax, e ? cur.wgt.y : cur.wgt.x, dpost);
+              const float kmask = e ? cur.kin.y : cur.kin.x;
               if (P.flags & MDN_OPT_INST_MASK) { post *= kmask; dpost *= kmask; }
               const float bg = 1.f - m;
-              const float lg = __logf(bg + 1e-5f);
+              const float lg = lg2_fast(bg + 1e-5f) * 0.6931471805599453f;
               const float ml = m * lg;
               acc[SL_EPI] += bg * post;
               acc[SL_NT] += fabsf(ml);
               if (P.flags & MDN_OPT_CROSS_ENT) {
                 const float l1 = __logf(m + 1e-10f), l0 = __logf(bg + 1e-10f);
                 acc[SL_CE] += -(kmask * l1 + (1.f - kmask) * l0);
-                mb[e] += S.c_ce * (__fdividef(1.f - kmask, bg + 1e-10f) - __fdividef(kmask, m + 1e-10f));
+                mb[e] += c_ce * (__fdividef(1.f - kmask, bg + 1e-10f) - __fdividef(kmask, m + 1e-10f));
               }
-              if (MAPS && S.post_map[pair]) S.post_map[pair][(size_t)b * hw + o + e] = post;
-              if (MAPS && S.ori_map[pair]) S.ori_map[pair][(size_t)b * hw + o + e] = (P.post == MDN_POST_SN) ? __fdiv_rn(ae, snmax) : ae;
+              if (MAPS && S.post_map[pair]) S.post_map[pair][(size_t)b * hw + (size_t)y * w + px0 + e] = post;
+              if (MAPS && S.ori_map[pair]) S.ori_map[pair][(size_t)b * hw + (size_t)y * w + px0 + e] = (P.post == MDN_POST_SN) ? __fdiv_rn(ae, snmax) : ae;
               if (grads) {
-                mb[e] += -S.c_epi * post + S.c_nt * signf_(ml) * (lg - __fdividef(m, bg + 1e-5f));
-                const float ebar = S.c_epi * bg * dpost;
+                mb[e] += -c_epi * post + c_nt * signf_(ml) * (lg - m * rcp_fast(bg + 1e-5f));
+                const float ebar = c_epi * bg * dpost;
                 const float dbar = signf_(ep.d) * ebar;
-                const float g2 = __fdividef(dbar, ep.den);
-                const float das = __fdividef(ep.d, ep.s);
-                gfx[e] += g2 * ep.a * S.sx;
-                gfy[e] += g2 * ep.b * S.sy;
+                const float g2 = dbar * rcp_fast(ep.den);
+                const float das = ep.d * rcp_fast(ep.s);
+                gfx[e] += g2 * ep.a * sx;
+                gfy[e] += g2 * ep.b * sy;
                 const float g0 = g2 * (u - das * ep.a), g1 = g2 * (v - das * ep.b);
                 acc[SL_GF + 0] += g0 * xf; acc[SL_GF + 1] += g0 * yf; acc[SL_GF + 2] += g0;
                 acc[SL_GF + 3] += g1 * xf; acc[SL_GF + 4] += g1 * yf; acc[SL_GF + 5] += g1;
@@ -557,10 +629,9 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
               }
             }
           }
-          if (grads && S.g_flow[pair]) {
-            float* gx = S.g_flow[pair] + (size_t)b * 2 * hw;
-            store_pair(gx, y, make_float2(gfx[0], gfx[1]));
-            store_pair(gx + hw, y, make_float2(gfy[0], gfy[1]));
+          if (grads && gflx) {
+            store_pair(gflx, y, make_float2(gfx[0], gfx[1]));
+            store_pair(gfly, y, make_float2(gfy[0], gfy[1]));
           }
         }
         // rotate the rings: row k + 1 moves to the front, the updated mask gradient to the back
@@ -568,6 +639,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
 #pragma unroll
         for (int i = 0; i + 1 < PR; ++i) { gix[i] = gix[i + 1]; giy[i] = giy[i + 1]; mbar[i] = mbar[i + 1]; }
         mbar[PR - 1] = mnew;
+        cur = nxt;
       }
     }
     flush_acc<PAIR_SLOTS>(acc, sm.red, pair * PAIR_SLOTS);

@@ -13,6 +13,7 @@
 #include "mdn_common.cuh"
 #include "../../include/mdn_loss.h"
 
+#include <algorithm>
 #include <stdio.h>
 #include <string.h>
 
@@ -58,6 +59,7 @@ struct KScale {
   WarpGeom geom;
   float c_epi, c_nt, c_ce, c_l1, c_ssim, c_smx, c_smy, c_consis;   // gradient coefficients (upstream 1)
   const float* tgt; const float* ref[2]; const float* flow[2]; const float* mob[2]; const float* fmat[2];
+  float4* refp[2];         // source images repacked to (r, g, b, -) per pixel (workspace; written by ref_pack_kernel)
   const float* weight; const uint8_t* inst;
   float* g_flow[2]; float* g_mob[2];
   float* post_map[2]; float* ori_map[2]; float* warped[2]; float* diff[2]; uint8_t* valid[2]; float* ssim_map[2];
@@ -126,6 +128,22 @@ __global__ void __launch_bounds__(NTHREADS) sn_max_kernel(const KParams P, unsig
     best = o > best ? o : best;
   }
   if ((threadIdx.x & 31) == 0 && best) atomicMax(keys + job, best);
+}
+
+// ----------------------------------------------------------------------------------------------- source repack
+// NCHW planes -> one float4 (r, g, b, 0) per pixel, so that the flow-warp gather of the fused kernel fetches the
+// three channels of a bilinear corner with ONE 16-byte load (see gather_pair_packed).  Coalesced both ways: three
+// 128-byte reads and one 512-byte write per warp.  grid.y = (scale * n_pairs + pair) * batch + b.
+__global__ void __launch_bounds__(NTHREADS) ref_pack_kernel(const __grid_constant__ KParams P) {
+  const int job = blockIdx.y;
+  const int b = job % P.batch, sp = job / P.batch;
+  const int pair = sp % P.n_pairs, s = sp / P.n_pairs;
+  const KScale& S = P.sc[s];
+  const int hw = S.h * S.w;
+  const float* src = S.ref[pair] + (size_t)b * 3 * hw;
+  float4* dst = S.refp[pair] + (size_t)b * hw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x)
+    dst[i] = make_float4(__ldg(src + i), __ldg(src + hw + i), __ldg(src + 2 * hw + i), 0.f);
 }
 
 #include "mdn_fused.cuh"
@@ -571,7 +589,7 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 extern "C" MDN_API int mdn_version(void) { return MDN_ABI_VERSION; }
 extern "C" MDN_API const char* mdn_last_error_string(void) { return g_err; }
 
-struct WsLayout { size_t partials, sample_sums, snkeys, ticket, total; int n_tiles; };
+struct WsLayout { size_t partials, sample_sums, refpack, snkeys, ticket, total; int n_tiles; };
 
 static int plan_tiles(const MdnLossDesc* d, KParams& K) {
   int t = 0;
@@ -634,6 +652,11 @@ static WsLayout ws_layout(const MdnLossDesc* d, int n_tiles) {
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
   L.partials = take((size_t)n_tiles * NSLOT * sizeof(float));
   L.sample_sums = take((size_t)d->n_scales * d->batch * NSLOT * sizeof(float));
+  size_t packed = 0;   // repacked source images: 16 bytes per pixel, per pair, per scale (photometric term only)
+  if (d->flags & MDN_TERM_PHOTO)
+    for (int s = 0; s < d->n_scales; ++s)
+      packed += (size_t)d->n_pairs * d->batch * d->scale[s].height * d->scale[s].width * sizeof(float4);
+  L.refpack = take(packed);
   L.snkeys = take((size_t)d->n_scales * d->n_pairs * d->batch * sizeof(unsigned long long));
   L.ticket = take(256);
   L.total = off;
@@ -696,6 +719,14 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
       Z.valid[p] = S.valid[p]; Z.ssim_map[p] = S.ssim_map[p];
     }
   }
+  {   // carve the repacked source images out of the workspace
+    float4* rp = (float4*)(ws + L.refpack);
+    for (int s = 0; s < d->n_scales; ++s)
+      for (int p = 0; p < d->n_pairs; ++p) {
+        K.sc[s].refp[p] = (d->flags & MDN_TERM_PHOTO) ? rp : nullptr;
+        if (d->flags & MDN_TERM_PHOTO) rp += (size_t)d->batch * K.sc[s].h * K.sc[s].w;
+      }
+  }
   // SN keys and the completion ticket are adjacent in the workspace: one memset node zeroes both
   if (cudaMemsetAsync(keys, 0, L.total - L.snkeys, stream) != cudaSuccess) return fail(MDN_ERR_CUDA, "memset failed");
   if ((d->flags & MDN_TERM_EPIPOLAR) && d->post == MDN_POST_SN) {
@@ -705,6 +736,11 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
     MDN_LAUNCH(sn_max_kernel, grid, dim3(NTHREADS), 0, stream, K, keys, chunks);
   }
   const bool photo = (d->flags & MDN_TERM_PHOTO) != 0;
+  if (photo) {
+    const int hw0 = K.sc[0].h * K.sc[0].w;
+    const dim3 pgrid((unsigned)std::min((hw0 + NTHREADS - 1) / NTHREADS, 1024), (unsigned)(d->n_scales * d->n_pairs * d->batch));
+    MDN_LAUNCH(ref_pack_kernel, pgrid, dim3(NTHREADS), 0, stream, K);
+  }
   const size_t smem = fused_smem_floats(photo) * sizeof(float);
   static_assert(fused_smem_floats(true) * sizeof(float) <= 75 * 1024, "three CTAs per SM");
   bool maps = false;

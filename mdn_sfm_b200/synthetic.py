@@ -81,9 +81,26 @@ def make_instances(batch, gen, n_inst=3):
     return out
 
 
+def smooth_flow(batch, h, w, flow_std, gen, cell=32):
+    """A network-like flow field: what a (random-init or trained) FlowNet decoder emits is spatially smooth, not
+    white noise.  Per-sample global motion + a smooth field (white noise on a coarse grid, one node per ``cell``
+    full-resolution pixels, bilinearly upsampled like the decoder's own upsampling) + 5 % pixel-level jitter; the
+    total standard deviation is ``flow_std`` in the nets' normalised units."""
+    import torch.nn.functional as F
+    gh, gw = max(2, -(-h // cell) + 1), max(2, -(-w // cell) + 1)
+    coarse = torch.randn(batch, 2, gh, gw, generator=gen)
+    field = F.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True)
+    glob = torch.randn(batch, 2, 1, 1, generator=gen)
+    jitter = torch.randn(batch, 2, h, w, generator=gen)
+    return flow_std * (0.6 * glob + 0.8 * field + 0.05 * jitter)
+
+
 def make_batch(batch, height, width, scales=(0, 1, 2, 3), frame_ids=(-1, 1), seed=42, flow_std=0.01,
-               pose_rot_std=0.01, pose_t_std=0.1, with_instances=True, device="cpu"):
-    """Returns ``(inputs, flows, mobiles, cam_T_cam, instances)`` laid out as trainer.py:256-281 hands them on."""
+               pose_rot_std=0.01, pose_t_std=0.1, with_instances=True, device="cpu", flow_kind="iid"):
+    """Returns ``(inputs, flows, mobiles, cam_T_cam, instances)`` laid out as trainer.py:256-281 hands them on.
+
+    ``flow_kind``: "iid" = white noise N(0, flow_std^2) per pixel (the stress case: every pixel gathers from an
+    unrelated place), "smooth" = a network-like field of the same magnitude (``smooth_flow``)."""
     from torchvision.transforms import Resize
 
     gen = torch.Generator().manual_seed(seed)
@@ -102,7 +119,10 @@ def make_batch(batch, height, width, scales=(0, 1, 2, 3), frame_ids=(-1, 1), see
     for i in frame_ids:
         for s in scales:
             h, w = height // 2 ** s, width // 2 ** s
-            flows[("flow", i, s)] = torch.randn(batch, 2, h, w, generator=gen) * flow_std
+            if flow_kind == "smooth":
+                flows[("flow", i, s)] = smooth_flow(batch, h, w, flow_std, gen, cell=max(2, 32 >> s))
+            else:
+                flows[("flow", i, s)] = torch.randn(batch, 2, h, w, generator=gen) * flow_std
             mobiles[("mobile", i, s)] = torch.rand(batch, 1, h, w, generator=gen) * 0.96 + 0.02
         aa = torch.randn(batch, 1, 1, 3, generator=gen) * pose_rot_std
         tt = torch.randn(batch, 1, 1, 3, generator=gen) * pose_t_std
