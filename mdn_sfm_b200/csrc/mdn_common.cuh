@@ -482,6 +482,12 @@ MDN_DEV void cp_async_f32x4(float* smem_dst, const float* gsrc, bool pred) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 #endif
 }
+// Pulls a 128-byte line into L2 (no register, no stall): used to fetch the NEXT wave's inputs from HBM ahead of time
+MDN_DEV void prefetch_l2(const void* p) {
+#ifndef MDN_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 MDN_DEV void cp_async_wait_all() {
 #ifndef MDN_EMU
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");

@@ -31,10 +31,11 @@ struct FusedSmem {
   float* Q;      // [3][R1P]
   float* D;      // [6][PR][FT] float2
   float* red;    // [FWARPS][NSLOT]
+  float* fm;     // [2][16] fundamental matrix + SN maximum of the (pair, sample)
 };
 
 __host__ __device__ constexpr size_t fused_smem_floats(bool photo) {
-  return 3 * R2P + (size_t)FWARPS * NSLOT + (photo ? 3 * R2P + 3 * R1P + 6 * PR * FT * 2 : 0);
+  return 3 * R2P + (size_t)FWARPS * NSLOT + 32 + (photo ? 3 * R2P + 3 * R1P + 6 * PR * FT * 2 : 0);
 }
 
 template <int NV>
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
   FusedSmem sm;
   sm.T = smem_raw;
   sm.red = sm.T + 3 * R2P;
-  sm.W = sm.red + FWARPS * NSLOT;
+  sm.fm = sm.red + FWARPS * NSLOT;
+  sm.W = sm.fm + 32;
   sm.Q = sm.W + 3 * R2P;
   sm.D = sm.Q + 3 * R1P;
 
@@ -115,6 +117,39 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
   const int o2own = OFF2 + (PR * g + 2) * S2 + 2 * t + 2;   // halo-2 slot of the patch's first pixel
 
   for (int i = tid; i < FWARPS * NSLOT; i += FT) sm.red[i] = 0.f;
+
+  // ---- L2 prefetch of the inputs of the tile that will run in this CTA slot one wave from now: every input byte is
+  // read from HBM exactly once, so without this each tile's first touches (target staging, flow, mobile maps) pay
+  // the full DRAM latency in front of dependent work.  One 128-byte line per thread and plane row segment.
+  {
+    const int nt = (int)blockIdx.x + P.prefetch_distance;
+    if (nt < P.n_tiles) {
+      int s2 = 0;
+#pragma unroll
+      for (int k = 1; k < MDN_MAX_SCALES; ++k)
+        if (k < P.n_scales && nt >= P.sc[k].tile_begin) s2 = k;
+      const KScale& Z = P.sc[s2];
+      int r2 = nt - Z.tile_begin;
+      const int tpi = Z.tiles_x * Z.tiles_y;
+      const int b2 = r2 / tpi;
+      r2 -= b2 * tpi;
+      const int ty2 = r2 / Z.tiles_x, tx2 = r2 - ty2 * Z.tiles_x;
+      const int hw2 = Z.h * Z.w;
+      // rows of the tile x (3 target + 2 x 2 flow + 2 mobile planes) x two 128-byte lines per 64-pixel row
+      constexpr int NPL = 9;
+      for (int i = tid; i < NPL * TH * 2; i += FT) {
+        const int pl = i / (TH * 2), rr = i - pl * (TH * 2);
+        const int y = ty2 * TH + (rr >> 1), x = tx2 * TW + (rr & 1) * 32;
+        if (y < Z.h && x < Z.w) {
+          const float* base;
+          if (pl < 3) base = need_tgt ? Z.tgt + ((size_t)b2 * 3 + pl) * hw2 : nullptr;
+          else if (pl < 7) { const int q = pl - 3; base = Z.flow[q >> 1] ? Z.flow[q >> 1] + ((size_t)b2 * 2 + (q & 1)) * hw2 : nullptr; }
+          else base = (need_mask && Z.mob[pl - 7]) ? Z.mob[pl - 7] + (size_t)b2 * hw2 : nullptr;
+          if (base) prefetch_l2(base + (size_t)y * Z.w + x);
+        }
+      }
+    }
+  }
 
   // ---- P0: stage the target image (halo 2, reflection padded) with cp.async; the copies land while P1 runs
   if (need_tgt) {
@@ -311,6 +346,12 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
 #pragma unroll
     for (int k = 0; k < PR; ++k) { gix[k] = giy[k] = make_float2(0.f, 0.f); }
 
+    if (epi_on && tid < 10) {   // fundamental matrix + SN maximum of this (pair, sample): staged now, read in P4
+      float v = 1.f;
+      if (tid < 9) v = __ldg(S.fmat[pair] + b * 9 + tid);
+      else if (P.post == MDN_POST_SN) v = __uint_as_float((unsigned)(P.snkey[(s * P.n_pairs + pair) * P.batch + b] >> 32));
+      sm.fm[(pair & 1) * 16 + tid] = v;   // double-buffered by pair: a fast warp may start pair 1 while others read pair 0's
+    }
     if (PHOTO) {
       const float4* rfp = opaque_ptr(S.refp[pair] + (size_t)b * hw);   // source image, (r, g, b, -) per pixel
       unsigned vbits = 0;            // validity of own pixel (k, e): bit 2k + e
@@ -373,7 +414,11 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
       // tiles that lie fully inside an even-width image (the common case): the own pairs are real, 8-byte aligned
       // pixels -- no reflection / slot arithmetic, one LDG.64 per flow plane, next row's flow loaded a row ahead
       const bool tile_full = weven & (x0 + TW <= w) & (y0 + TH <= h);
+#ifdef MDN_ABLATE_P1
+      if (false) {
+#else
       if (tile_full) {
+#endif
         unsigned o = (unsigned)(py0 * w + px0);
         float2 fxn = ldg2(flx + o), fyn = ldg2(fly + o);
         const float2 xs = make_float2((float)px0, (float)px1);
@@ -390,7 +435,11 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
           put(G2, va, vb, PR * g + 2 + k, 2 * t + 2, true, true, k);
         }
       }
+#ifdef MDN_ABLATE_P1
+      const int it0 = N_IT;
+#else
       const int it0 = tile_full ? PR : 0;
+#endif
       Slot cur;
       prep(it0, cur);
 #pragma unroll 1
@@ -489,7 +538,11 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
 #pragma unroll 1
       for (int c = 0; c < 3; ++c) {
         // -- P2: SSIM windows of channel c, 2 columns x WPR rows per patch
+#ifdef MDN_ABLATE_P2
+        if (false) {
+#else
         if (use_ssim) {
+#endif
 #pragma unroll 1
           for (int patch = tid; patch < NPATCH; patch += FT) {
             const int rg = patch / NCP, cp = patch - rg * NCP;
@@ -536,7 +589,9 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
           }
           __syncthreads();
         }
+#ifndef MDN_ABLATE_P3
         if (border) p3(c, BoolTag<true>()); else p3(c, BoolTag<false>());
+#endif
         if (use_ssim) __syncthreads();   // Q (and, after the last channel, W) is rewritten next
       }
     }
@@ -549,12 +604,10 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
       float Fm[9];
       float snmax = 1.f;
       if (epi_on) {
+        if (!PHOTO) __syncthreads();     // (the photometric path has synchronised since sm.fm was written)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) Fm[k] = __ldg(S.fmat[pair] + b * 9 + k);
-        if (P.post == MDN_POST_SN) {
-          const unsigned long long key = P.snkey[(s * P.n_pairs + pair) * P.batch + b];
-          snmax = __uint_as_float((unsigned)(key >> 32));
-        }
+        for (int k = 0; k < 9; ++k) Fm[k] = sm.fm[(pair & 1) * 16 + k];
+        snmax = sm.fm[(pair & 1) * 16 + 9];
       }
       const float c_epi = S.c_epi, c_nt = S.c_nt, c_ce = S.c_ce;
       float* gflx = opaque_ptr(S.g_flow[pair] ? S.g_flow[pair] + (size_t)b * 2 * hw : nullptr);
@@ -579,8 +632,13 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
       };
       Row cur;
       fetch(0, cur);
+#ifdef MDN_ABLATE_P4
+#pragma unroll 1
+      for (int k = 0; k < 0; ++k) {
+#else
 #pragma unroll 1
       for (int k = 0; k < PR; ++k) {
+#endif
         Row nxt;
         fetch(k + 1, nxt);
         const int y = py0 + k;
@@ -643,9 +701,13 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
       }
     }
     flush_acc<PAIR_SLOTS>(acc, sm.red, pair * PAIR_SLOTS);
+#ifndef MDN_ABLATE_TAIL
     if (need_mask && own) tail(pair);
+#endif
   }
+#ifndef MDN_ABLATE_TAIL
   if (need_mask && !own) tail(0);
+#endif
 
   __syncthreads();
   for (int k = tid; k < NSLOT; k += FT) {

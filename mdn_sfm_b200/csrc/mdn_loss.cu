@@ -24,7 +24,7 @@ constexpr int NTHREADS = 256;                         // block size of the small
 // fused kernel: TW x TH tile, one thread per 2-column x 4-row patch of pixels
 constexpr int TW = 64, TH = 16;
 #ifndef MDN_PATCH_ROWS
-#define MDN_PATCH_ROWS 4
+#define MDN_PATCH_ROWS 2      // measured: 2 rows (256 threads / CTA) beats 4 rows (128 threads) at every shape tried
 #endif
 constexpr int PR = MDN_PATCH_ROWS;                           // rows of the per-thread pixel patch (2 or 4)
 static_assert((PR == 2 || PR == 4) && TH % PR == 0, "patch rows");
@@ -41,7 +41,7 @@ static_assert((TH + 2) % WPR == 0, "SSIM patches tile the halo-1 region exactly"
 constexpr int NCP = (TW + 2) / 2, NPATCH = NCP * ((TH + 2) / WPR);
 constexpr int RING = S2 * R2H - TW * TH;              // halo slots of the halo-2 region
 #ifndef MDN_FUSED_MIN_CTAS
-#define MDN_FUSED_MIN_CTAS 3
+#define MDN_FUSED_MIN_CTAS 2  // 128 registers / thread, no spills; the larger L1 carve-out of 2 CTAs / SM helps the gather
 #endif
 
 // partial-sum slots per tile
@@ -68,6 +68,7 @@ struct KScale {
 struct KParams {
   int batch, n_scales, n_pairs, post, mask_mode, flags;
   int n_tiles;
+  int prefetch_distance;             // tiles between a CTA and the tile whose inputs it prefetches into L2
   float threshold, inv_threshold;
   float* partials;                   // [n_tiles][NSLOT]
   const unsigned long long* snkey;   // [n_scales][n_pairs][batch] packed (bits(max)<<32 | ~argmax)
@@ -142,8 +143,21 @@ __global__ void __launch_bounds__(NTHREADS) ref_pack_kernel(const __grid_constan
   const int hw = S.h * S.w;
   const float* src = S.ref[pair] + (size_t)b * 3 * hw;
   float4* dst = S.refp[pair] + (size_t)b * hw;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x)
-    dst[i] = make_float4(__ldg(src + i), __ldg(src + hw + i), __ldg(src + 2 * hw + i), 0.f);
+  if ((hw & 3) == 0) {
+    // four pixels per thread: three 16-byte loads, four 16-byte stores
+    const float4* s0 = reinterpret_cast<const float4*>(src);
+    const float4* s1 = reinterpret_cast<const float4*>(src + hw);
+    const float4* s2 = reinterpret_cast<const float4*>(src + 2 * hw);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw / 4; i += gridDim.x * blockDim.x) {
+      const float4 r = __ldg(s0 + i), g = __ldg(s1 + i), bl = __ldg(s2 + i);
+      float4* d4 = dst + 4 * i;
+      d4[0] = make_float4(r.x, g.x, bl.x, 0.f); d4[1] = make_float4(r.y, g.y, bl.y, 0.f);
+      d4[2] = make_float4(r.z, g.z, bl.z, 0.f); d4[3] = make_float4(r.w, g.w, bl.w, 0.f);
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x)
+      dst[i] = make_float4(__ldg(src + i), __ldg(src + hw + i), __ldg(src + 2 * hw + i), 0.f);
+  }
 }
 
 #include "mdn_fused.cuh"
@@ -157,9 +171,12 @@ struct FParams {
   float* g_fmat[MDN_MAX_SCALES][2];
   float alpha, w_d2, w_e, w_s, w_c, w_p, l1_coef, ssim_coef;
   float scale_div[MDN_MAX_SCALES];
+  // reciprocals of the mean denominators, precomputed on the host in double: the single-thread epilogue multiplies
+  // (a dependent chain of ~100 double DIVISIONS cost 14 us)
+  double inv_N[MDN_MAX_SCALES], inv_div[MDN_MAX_SCALES], inv_cx[MDN_MAX_SCALES], inv_cy[MDN_MAX_SCALES];
 };
 
-constexpr int FIN_ROWS = 6;   // FIN_ROWS * NSLOT = 240 threads
+constexpr int FIN_ROWS = 24;  // FIN_ROWS * NSLOT = 960 threads: at most ~5 tiles per thread at the headline shape
 
 __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_constant__ FParams Q) {
   const KParams& P = Q.K;
@@ -171,7 +188,8 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
   const int tiles = S.tiles_x * S.tiles_y;
   const float* src = P.partials + ((long long)S.tile_begin + (long long)b * tiles) * NSLOT;
   float t = 0.f;
-  for (int k = row; k < tiles; k += FIN_ROWS) t += src[(long long)k * NSLOT + slot];
+#pragma unroll 4
+  for (int k = row; k < tiles; k += FIN_ROWS) t += __ldcg(src + (long long)k * NSLOT + slot);
   part[row][slot] = t;
   __syncthreads();
   if (row == 0) {
@@ -241,23 +259,22 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
     for (int ss = 0; ss < P.n_scales; ++ss) {
       const KScale& Z = P.sc[ss];
       const double* tot = tots[ss];
-      const double N = (double)P.batch * Z.h * Z.w, div = Q.scale_div[ss];
-      const double cx = (double)P.batch * Z.h * (Z.w - 1), cy = (double)P.batch * (Z.h - 1) * Z.w;
+      const double iN = Q.inv_N[ss], idiv = Q.inv_div[ss], icx = Q.inv_cx[ss], icy = Q.inv_cy[ss];
       for (int p = 0; p < P.n_pairs; ++p) {
         const double* tp = tot + p * PAIR_SLOTS;
         if (P.flags & MDN_TERM_EPIPOLAR) {
-          double e = tp[SL_EPI] / N + (double)Q.alpha * (tp[SL_NT] / N);
-          if (P.flags & MDN_OPT_CROSS_ENT) e += (double)Q.w_d2 * (tp[SL_CE] / N);
-          epip += e / div;
+          double e = tp[SL_EPI] * iN + (double)Q.alpha * (tp[SL_NT] * iN);
+          if (P.flags & MDN_OPT_CROSS_ENT) e += (double)Q.w_d2 * (tp[SL_CE] * iN);
+          epip += e * idiv;
         }
         if (P.flags & MDN_TERM_PHOTO)
-          photo += ((double)Q.l1_coef * (tp[SL_L1] / (3 * N)) + (double)Q.ssim_coef * (tp[SL_SSIM] / (3 * N))) / div;
+          photo += ((double)Q.l1_coef * (tp[SL_L1] * (iN * (1.0 / 3.0))) + (double)Q.ssim_coef * (tp[SL_SSIM] * (iN * (1.0 / 3.0)))) * idiv;
         if (P.flags & MDN_TERM_SMOOTH) {
           const int k = own ? p : 0;
-          smooth += (tot[TAIL_BASE + SL_SMX + 2 * k] / cx + tot[TAIL_BASE + SL_SMY + 2 * k] / cy) / div;
+          smooth += (tot[TAIL_BASE + SL_SMX + 2 * k] * icx + tot[TAIL_BASE + SL_SMY + 2 * k] * icy) * idiv;
         }
       }
-      if (P.flags & MDN_TERM_CONSIS) consis += tot[TAIL_BASE + SL_CONSIS] / N / div;
+      if (P.flags & MDN_TERM_CONSIS) consis += tot[TAIL_BASE + SL_CONSIS] * iN * idiv;
     }
     Q.loss_out[MDN_OUT_EPIP] = (float)epip;
     Q.loss_out[MDN_OUT_SMOOTH] = (float)smooth;
@@ -702,6 +719,10 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
     Z.geom = make_geom(Z.h, Z.w, (d->flags & MDN_OPT_CUDA_ARITH) != 0, false);
     const double div = S.scale_div > 0.f ? (double)S.scale_div : 1.0;
     Q.scale_div[s] = (float)div;
+    Q.inv_N[s] = 1.0 / ((double)d->batch * Z.h * Z.w);
+    Q.inv_div[s] = 1.0 / div;
+    Q.inv_cx[s] = Z.w > 1 ? 1.0 / ((double)d->batch * Z.h * (Z.w - 1)) : 0.0;
+    Q.inv_cy[s] = Z.h > 1 ? 1.0 / ((double)d->batch * (Z.h - 1) * Z.w) : 0.0;
     const double N = (double)d->batch * Z.h * Z.w;
     Z.c_epi = (float)(d->w_e / (div * N));
     Z.c_nt = (float)((double)d->w_e * d->alpha / (div * N));
@@ -738,7 +759,7 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
   const bool photo = (d->flags & MDN_TERM_PHOTO) != 0;
   if (photo) {
     const int hw0 = K.sc[0].h * K.sc[0].w;
-    const dim3 pgrid((unsigned)std::min((hw0 + NTHREADS - 1) / NTHREADS, 1024), (unsigned)(d->n_scales * d->n_pairs * d->batch));
+    const dim3 pgrid((unsigned)std::min((hw0 / 4 + NTHREADS - 1) / NTHREADS, 1024), (unsigned)(d->n_scales * d->n_pairs * d->batch));
     MDN_LAUNCH(ref_pack_kernel, pgrid, dim3(NTHREADS), 0, stream, K);
   }
   const size_t smem = fused_smem_floats(photo) * sizeof(float);
@@ -749,6 +770,7 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
       const MdnScale& S = d->scale[s];
       maps |= S.post_map[p] || S.ori_map[p] || S.warped[p] || S.diff[p] || S.valid[p] || S.ssim_map[p];
     }
+  K.prefetch_distance = MDN_FUSED_MIN_CTAS * 148;   // one wave of resident CTAs (148 SMs on B200)
   const dim3 grid(K.n_tiles), block(FT);
   static bool smem_opt_in = false;   // > 48 KB of dynamic shared memory needs the opt-in attribute (idempotent; set once)
   if (!smem_opt_in) {
