@@ -182,6 +182,7 @@ MDN_DEV float2 fma2(float2 a, float2 b, float2 c) { return make_float2(__fmaf_rn
 MDN_DEV float rcp_fast(float x) { return 1.0f / x; }
 MDN_DEV float ex2_fast(float x) { return exp2f(x); }
 MDN_DEV float lg2_fast(float x) { return log2f(x); }
+MDN_DEV float sqrt_fast(float x) { return sqrtf(x); }
 #else
 MDN_DEV float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 MDN_DEV float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
@@ -189,6 +190,7 @@ MDN_DEV float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); 
 MDN_DEV float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 MDN_DEV float ex2_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 MDN_DEV float lg2_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+MDN_DEV float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #endif
 MDN_DEV float2 splat2(float a) { return make_float2(a, a); }
 // Makes a pointer opaque to the optimiser, so that it is kept as ONE 64-bit register pair and `p + u32_offset` is a

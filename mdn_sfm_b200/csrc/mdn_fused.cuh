@@ -630,6 +630,17 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
           }
         }
       };
+      // Both pixels of a row at once (packed).  Exactness is kept where the reference cancels: u, v and the
+      // numerator p2^T F p1 replay the reference's separate roundings with SCALAR ops (ptxas would contract packed
+      // mul + add); a^2 + b^2, the square root, the division and the post-processing are a few ulp off the reference
+      // (fast reciprocal / sqrt), far inside the 1e-5 budget.  post = (d k)^2 with k = 1/max (SN), 1/thr (T),
+      // 1/(thr w) (TG): no |d| / sign(d) needed, d(post)/dd = 2 (d k) k.
+      float2 accp[PAIR_SLOTS];     // packed partial sums of this phase (slot layout of acc[])
+#pragma unroll
+      for (int k = 0; k < PAIR_SLOTS; ++k) accp[k] = make_float2(0.f, 0.f);
+      const float2 xf2 = make_float2((float)px0, (float)px1);
+      const float kbase = (P.post == MDN_POST_SN) ? rcp_fast(snmax) : ((P.threshold > 0.f) ? P.inv_threshold : 1.f);
+      const float2 live = make_float2(1.f, in1 ? 1.f : 0.f);   // the second column may lie outside a ragged image
       Row cur;
       fetch(0, cur);
 #ifdef MDN_ABLATE_P4
@@ -643,62 +654,86 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
         fetch(k + 1, nxt);
         const int y = py0 + k;
         // (w-1)/2 [grid_sample] * 2 [2g-1] / (w-1) [/= w-1] * sx [scale factor]
-        float gfx[2] = {gix[0].x * sx, gix[0].y * sx}, gfy[2] = {giy[0].x * sy, giy[0].y * sy};
-        float mb[2] = {0.f, 0.f};
+        float2 gfx = mul2(gix[0], splat2(sx)), gfy = mul2(giy[0], splat2(sy));
+        float2 mb = make_float2(0.f, 0.f);
         if ((y < h) & in0) {
           if (epi_on) {
+            const float yf = (float)y;
+            const float2 m = make_float2((cur.m0.x <= cur.m1.x) ? cur.m0.x : cur.m1.x, (cur.m0.y <= cur.m1.y) ? cur.m0.y : cur.m1.y);
+            const float2 u = add2(xf2, make_float2(__fmul_rn(sx, cur.fx.x), __fmul_rn(sx, cur.fx.y)));
+            const float2 v = add2(splat2(yf), make_float2(__fmul_rn(sy, cur.fy.x), __fmul_rn(sy, cur.fy.y)));
+            // F p1 (loss_utils.py:64): k-ordered FMA chains, exactly as epipolar_distance()
+            const float2 ea = add2(fma2(splat2(Fm[1]), splat2(yf), mul2(splat2(Fm[0]), xf2)), splat2(Fm[2]));
+            const float2 eb = add2(fma2(splat2(Fm[4]), splat2(yf), mul2(splat2(Fm[3]), xf2)), splat2(Fm[5]));
+            const float2 ec = add2(fma2(splat2(Fm[7]), splat2(yf), mul2(splat2(Fm[6]), xf2)), splat2(Fm[8]));
+            const float2 num = make_float2(__fadd_rn(__fadd_rn(__fmul_rn(ea.x, u.x), __fmul_rn(eb.x, v.x)), ec.x),
+                                           __fadd_rn(__fadd_rn(__fmul_rn(ea.y, u.y), __fmul_rn(eb.y, v.y)), ec.y));
+            const float2 ss = add2(fma2(ea, ea, mul2(eb, eb)), splat2(1e-10f));
+            const float2 den = add2(make_float2(sqrt_fast(ss.x), sqrt_fast(ss.y)), splat2(1e-10f));
+            const float2 rden = make_float2(rcp_fast(den.x), rcp_fast(den.y));
+            const float2 dd = mul2(num, rden);                                 // signed epipolar distance
+            float2 kw = splat2(kbase);
+            if (use_wgt) kw = make_float2(kbase * rcp_fast(cur.wgt.x), kbase * rcp_fast(cur.wgt.y));
+            const float2 rs = mul2(dd, kw);
+            float2 post = mul2(rs, rs);
+            float2 kmask = cur.kin;
+            if (P.flags & MDN_OPT_INST_MASK) post = mul2(post, kmask); else kmask = make_float2(1.f, 1.f);
+            const float2 bg = add2(splat2(1.f), mul2(m, splat2(-1.f)));
+            const float2 bge = add2(bg, splat2(1e-5f));
+            const float2 lg = mul2(make_float2(lg2_fast(bge.x), lg2_fast(bge.y)), splat2(0.6931471805599453f));
+            const float2 ml = mul2(m, lg);
+            accp[SL_EPI] = fma2(mul2(bg, post), live, accp[SL_EPI]);
+            acc[SL_NT] += fabsf(ml.x) + (in1 ? fabsf(ml.y) : 0.f);
+            if (P.flags & MDN_OPT_CROSS_ENT) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              if (e && !in1) continue;
-              const float ma = e ? cur.m0.y : cur.m0.x, mbv = e ? cur.m1.y : cur.m1.x;
-              const float m = (ma <= mbv) ? ma : mbv;
-              const float xf = (float)(px0 + e), yf = (float)y;
-              const float u = __fadd_rn(xf, __fmul_rn(sx, e ? cur.fx.y : cur.fx.x)), v = __fadd_rn(yf, __fmul_rn(sy, e ? cur.fy.y : cur.fy.x));
-              const Epi ep = epipolar_distance(Fm, xf, yf, u, v);
-              const float ae = fabsf(ep.d);
-              float dpost;
-              float post = post_process(P, ae, snmax, e ? cur.wgt.y : cur.wgt.x, dpost);
-              const float kmask = e ? cur.kin.y : cur.kin.x;
-              if (P.flags & MDN_OPT_INST_MASK) { post *= kmask; dpost *= kmask; }
-              const float bg = 1.f - m;
-              const float lg = lg2_fast(bg + 1e-5f) * 0.6931471805599453f;
-              const float ml = m * lg;
-              acc[SL_EPI] += bg * post;
-              acc[SL_NT] += fabsf(ml);
-              if (P.flags & MDN_OPT_CROSS_ENT) {
-                const float l1 = __logf(m + 1e-10f), l0 = __logf(bg + 1e-10f);
-                acc[SL_CE] += -(kmask * l1 + (1.f - kmask) * l0);
-                mb[e] += c_ce * (__fdividef(1.f - kmask, bg + 1e-10f) - __fdividef(kmask, m + 1e-10f));
+              for (int e = 0; e < 2; ++e) {
+                if (e && !in1) continue;
+                const float me = e ? m.y : m.x, bge0 = e ? bg.y : bg.x, ke = e ? cur.kin.y : cur.kin.x;
+                const float l1 = __logf(me + 1e-10f), l0 = __logf(bge0 + 1e-10f);
+                acc[SL_CE] += -(ke * l1 + (1.f - ke) * l0);
+                const float t = c_ce * (__fdividef(1.f - ke, bge0 + 1e-10f) - __fdividef(ke, me + 1e-10f));
+                if (e) mb.y += t; else mb.x += t;
               }
-              if (MAPS && S.post_map[pair]) S.post_map[pair][(size_t)b * hw + (size_t)y * w + px0 + e] = post;
-              if (MAPS && S.ori_map[pair]) S.ori_map[pair][(size_t)b * hw + (size_t)y * w + px0 + e] = (P.post == MDN_POST_SN) ? __fdiv_rn(ae, snmax) : ae;
-              if (grads) {
-                mb[e] += -c_epi * post + c_nt * signf_(ml) * (lg - m * rcp_fast(bg + 1e-5f));
-                const float ebar = c_epi * bg * dpost;
-                const float dbar = signf_(ep.d) * ebar;
-                const float g2 = dbar * rcp_fast(ep.den);
-                const float das = ep.d * rcp_fast(ep.s);
-                gfx[e] += g2 * ep.a * sx;
-                gfy[e] += g2 * ep.b * sy;
-                const float g0 = g2 * (u - das * ep.a), g1 = g2 * (v - das * ep.b);
-                acc[SL_GF + 0] += g0 * xf; acc[SL_GF + 1] += g0 * yf; acc[SL_GF + 2] += g0;
-                acc[SL_GF + 3] += g1 * xf; acc[SL_GF + 4] += g1 * yf; acc[SL_GF + 5] += g1;
-                acc[SL_GF + 6] += g2 * xf; acc[SL_GF + 7] += g2 * yf; acc[SL_GF + 8] += g2;
+            }
+            if (MAPS) {
+              const size_t o = (size_t)b * hw + (size_t)y * w + px0;
+              if (S.post_map[pair]) { S.post_map[pair][o] = post.x; if (in1) S.post_map[pair][o + 1] = post.y; }
+              if (S.ori_map[pair]) {
+                const float s0 = (P.post == MDN_POST_SN) ? kbase : 1.f;
+                S.ori_map[pair][o] = fabsf(dd.x) * s0; if (in1) S.ori_map[pair][o + 1] = fabsf(dd.y) * s0;
               }
+            }
+            if (grads) {
+              const float2 rb = make_float2(rcp_fast(bge.x), rcp_fast(bge.y));
+              const float2 tnt = fma2(mul2(m, rb), splat2(-1.f), lg);            // lg - m / (bg + 1e-5)
+              mb = fma2(post, splat2(-c_epi), mb);
+              mb.x += c_nt * signf_(ml.x) * tnt.x; mb.y += c_nt * signf_(ml.y) * tnt.y;
+              // d(loss)/dd = c_epi bg kmask 2 (d k) k
+              const float2 dbar = mul2(mul2(mul2(bg, kmask), splat2(2.f * c_epi)), mul2(rs, kw));
+              const float2 g2 = mul2(mul2(dbar, rden), live);
+              const float2 das = mul2(dd, rden);                                 // d / s (s and s + 1e-10 agree to 1e-5)
+              gfx = fma2(mul2(g2, ea), splat2(sx), gfx);
+              gfy = fma2(mul2(g2, eb), splat2(sy), gfy);
+              const float2 g0 = mul2(g2, fma2(mul2(das, ea), splat2(-1.f), u)), g1 = mul2(g2, fma2(mul2(das, eb), splat2(-1.f), v));
+              accp[SL_GF + 0] = fma2(g0, xf2, accp[SL_GF + 0]); accp[SL_GF + 1] = fma2(g0, splat2(yf), accp[SL_GF + 1]); accp[SL_GF + 2] = add2(accp[SL_GF + 2], g0);
+              accp[SL_GF + 3] = fma2(g1, xf2, accp[SL_GF + 3]); accp[SL_GF + 4] = fma2(g1, splat2(yf), accp[SL_GF + 4]); accp[SL_GF + 5] = add2(accp[SL_GF + 5], g1);
+              accp[SL_GF + 6] = fma2(g2, xf2, accp[SL_GF + 6]); accp[SL_GF + 7] = fma2(g2, splat2(yf), accp[SL_GF + 7]); accp[SL_GF + 8] = add2(accp[SL_GF + 8], g2);
             }
           }
           if (grads && gflx) {
-            store_pair(gflx, y, make_float2(gfx[0], gfx[1]));
-            store_pair(gfly, y, make_float2(gfy[0], gfy[1]));
+            store_pair(gflx, y, gfx);
+            store_pair(gfly, y, gfy);
           }
         }
         // rotate the rings: row k + 1 moves to the front, the updated mask gradient to the back
-        const float2 mnew = make_float2(mbar[0].x + mb[0], mbar[0].y + mb[1]);
+        const float2 mnew = add2(mbar[0], mb);
 #pragma unroll
         for (int i = 0; i + 1 < PR; ++i) { gix[i] = gix[i + 1]; giy[i] = giy[i + 1]; mbar[i] = mbar[i + 1]; }
         mbar[PR - 1] = mnew;
         cur = nxt;
       }
+#pragma unroll
+      for (int k = 0; k < PAIR_SLOTS; ++k) acc[k] += accp[k].x + accp[k].y;
     }
     flush_acc<PAIR_SLOTS>(acc, sm.red, pair * PAIR_SLOTS);
 #ifndef MDN_ABLATE_TAIL
