@@ -46,7 +46,15 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 100)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flow", default="iid", choices=["iid", "smooth"],
+                    help="synthetic flow field: iid = white noise N(0, 0.05^2) per pixel (stress: every pixel gathers from an "
+                         "unrelated place), smooth = network-like field of the same magnitude")
+    ap.add_argument("--no-second-flow", action="store_true", help="skip the short extra measurement on the other flow kind")
     return ap.parse_args()
+
+
+FLOW_DESC = {"iid": "normalised flow ~ N(0, 0.05^2) i.i.d. per pixel (+-32 px at 640: stress case, no locality in the warp gather)",
+             "smooth": "network-like smooth flow field, total std 0.05 (mdn_sfm_b200.synthetic.smooth_flow)"}
 
 
 def workload(args):
@@ -67,7 +75,8 @@ def config_dict(args, H, W, scales, n_gpus):
                         "fwd+bwd, batch %d/GPU x %d GPU, 3x%dx%d, %d scales, 2 source frames" % (
                             args.mode, args.batch, n_gpus, H, W, len(scales)),
             "mode": args.mode, "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus, "height": H, "width": W,
-            "scales": list(scales), "frame_ids": [0, -1, 1], "photometric": True, "ssim": True}
+            "scales": list(scales), "frame_ids": [0, -1, 1], "photometric": True, "ssim": True,
+            "flow": FLOW_DESC[args.flow]}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -124,7 +133,7 @@ def cpu_reference_step_fn(args, H, W, scales, seed=42):
     torch.set_num_threads(threads)
     opt = synthetic.default_opt(args.batch, H, W)
     inputs, flows, mobiles, cams, inst = synthetic.make_batch(args.batch, H, W, scales=scales, seed=seed, flow_std=0.05,
-                                                              with_instances=args.mode in ("DS", "DC"))
+                                                              with_instances=args.mode in ("DS", "DC"), flow_kind=args.flow)
     weights = restate.gauss_distance_weight(4, H, W) if args.mode == "TG" else None
 
     def step():
@@ -187,17 +196,6 @@ def run_ours(args):
     loss_mod = Loss(opt, no_ssim=False, mode=args.mode, photometric=True)
     ids = [-1, 1]
 
-    # ---- input sets: pinned host masters + device-resident copies
-    host_sets, dev_sets = [], []
-    for k in range(args.sets):
-        inputs, flows, mobiles, cams, inst = synthetic.make_batch(B, H, W, scales=scales, seed=42 + rank + 1000 * k,
-                                                                  flow_std=0.05, with_instances=with_inst)
-        pin = lambda d: {kk: v.pin_memory() for kk, v in d.items()}
-        host_sets.append((pin(inputs), pin(flows), pin(mobiles), pin(cams), inst))
-        to = lambda d, g=False: {kk: v.to(dev).requires_grad_(g) for kk, v in d.items()}
-        inst_d = [{"instances": d["instances"].to(dev)} for d in inst] if inst is not None else None
-        dev_sets.append((to(inputs), to(flows, True), to(mobiles, True), to(cams, True), inst_d))
-
     def step_on(s):
         inputs, flows, mobiles, cams, inst = s
         for d in (flows, mobiles, cams):
@@ -207,62 +205,80 @@ def run_ours(args):
         losses["loss"].backward()
         return losses["loss"]
 
-    # ---- eager warm-up (also sets the kernel attributes outside any capture) + optional graph capture
-    for s in dev_sets:
-        step_on(s)
-    torch.cuda.synchronize()
-    graphs, graph_ok = [], not args.no_graph
-    if graph_ok:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for s in dev_sets:
-                    step_on(s)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            for s in dev_sets:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    out = step_on(s)
-                graphs.append((g, out))
-            torch.cuda.synchronize()
-        except Exception as e:   # keep measuring, but say so
-            graph_ok, graphs = False, []
-            print("bench: CUDA graph capture failed (%r); timing eager launches" % (e,), file=sys.stderr)
-            torch.cuda.synchronize()
+    def make_sets(flow_kind, n_sets):
+        # pinned host masters + device-resident copies
+        host_sets, dev_sets = [], []
+        for k in range(n_sets):
+            inputs, flows, mobiles, cams, inst = synthetic.make_batch(B, H, W, scales=scales, seed=42 + rank + 1000 * k, flow_std=0.05,
+                                                                      with_instances=with_inst, flow_kind=flow_kind)
+            pin = lambda d: {kk: v.pin_memory() for kk, v in d.items()}
+            host_sets.append((pin(inputs), pin(flows), pin(mobiles), pin(cams), inst))
+            to = lambda d, g=False: {kk: v.to(dev).requires_grad_(g) for kk, v in d.items()}
+            inst_d = [{"instances": d["instances"].to(dev)} for d in inst] if inst is not None else None
+            dev_sets.append((to(inputs), to(flows, True), to(mobiles, True), to(cams, True), inst_d))
+        return host_sets, dev_sets
 
-    def run_step(i):
+    def timed_steps(dev_sets, steps, warmup, ramp_s):
+        """fwd+bwd steps replayed from CUDA graphs over rotating input sets; returns (total ms, graph_ok)."""
+        for s in dev_sets:   # eager warm-up (also sets the kernel attributes outside any capture)
+            step_on(s)
+        torch.cuda.synchronize()
+        graphs, graph_ok = [], not args.no_graph
         if graph_ok:
-            graphs[i % len(graphs)][0].replay()
-        else:
-            step_on(dev_sets[i % len(dev_sets)])
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for s in dev_sets:
+                        step_on(s)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                for s in dev_sets:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        out = step_on(s)
+                    graphs.append((g, out))
+                torch.cuda.synchronize()
+            except Exception as e:   # keep measuring, but say so
+                graph_ok, graphs = False, []
+                print("bench: CUDA graph capture failed (%r); timing eager launches" % (e,), file=sys.stderr)
+                torch.cuda.synchronize()
 
+        def run_step(i):
+            if graph_ok:
+                graphs[i % len(graphs)][0].replay()
+            else:
+                step_on(dev_sets[i % len(dev_sets)])
+
+        # clock ramp (untimed) so a short timed region does not run at idle clocks
+        t_end = time.perf_counter() + ramp_s
+        i = 0
+        while time.perf_counter() < t_end:
+            run_step(i)
+            i += 1
+        for i in range(warmup):
+            run_step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            run_step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, graph_ok
+
+    host_sets, dev_sets = make_sets(args.flow, args.sets)
     sampler = ClockSampler(local)
     sampler.start()
-    # clock ramp (untimed) so a short timed region does not run at idle clocks
-    t_end = time.perf_counter() + 1.0
-    i = 0
-    while time.perf_counter() < t_end:
-        run_step(i)
-        i += 1
-    for i in range(args.warmup):
-        run_step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        run_step(i)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms, graph_ok = timed_steps(dev_sets, args.steps, args.warmup, 1.0)
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms * 1e-3)
 
@@ -300,7 +316,17 @@ def run_ours(args):
         c[0].keep = c[0].keep[:-2]
     k1.record()
     torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / n_k
+    call_ms = k0.elapsed_time(k1) / n_k          # whole mdn_loss_fused call: memset + repack + fused + finish, back to back
+    # the fused tile kernel ALONE: CUDA events recorded around its launch on the launching stream, inside the library
+    # (mdn_loss_fused_profile); rotating input sets, each call waits for completion, so the kernel runs by itself
+    parts = [0.0, 0.0, 0.0]
+    n_p = 200
+    for i in range(n_p):
+        c = calls[i % len(calls)]
+        pm = c[0].profile(lib, c[1], c[2], stream)
+        for j in range(3):
+            parts[j] += pm[j] / n_p
+    repack_ms, kernel_ms, finish_ms = parts
     alg_bytes = algorithmic_bytes_per_frame(H, W, scales, with_inst) * B
     peaks = {}
     try:
@@ -315,8 +341,10 @@ def run_ours(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "mdn::fused_tile_kernel (+ memset and finish_kernel nodes of the same mdn_loss_fused call)",
+                "kernel": "mdn::fused_tile_kernel, timed alone with CUDA events around its launch (mdn_loss_fused_profile), mean of %d launches on rotating input sets" % n_p,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "other_kernels_of_the_call_ms": {"mdn::ref_pack_kernel": repack_ms, "mdn::finish_kernel": finish_ms,
+                                                 "whole mdn_loss_fused call, back to back": call_ms},
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
 
     # ---- e2e: public API, host buffers in, loss out, every step
@@ -352,6 +380,16 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
+    # ---- the same workload on the other flow kind (short run, reported beside the headline, never instead of it)
+    second = None
+    if not args.no_second_flow and world == 1:
+        other = "smooth" if args.flow == "iid" else "iid"
+        del calls
+        _, dev2 = make_sets(other, 2)
+        n2 = max(50, args.steps // 4)
+        ms2, _ = timed_steps(dev2, n2, max(3, args.warmup // 4), 0.3)
+        second = {"flow": FLOW_DESC[other], "value": B * n2 / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2 / n2, "steps": n2}
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         step, threads = cpu_reference_step_fn(args, H, W, scales)
@@ -375,10 +413,11 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
                         "path": "mdn_sfm_b200.loss_functions.Loss.forward + backward (eager public API), pinned host inputs"},
-                "gpu_launches": 5 * args.steps,
-                "launches_per_step": "mdn::fundamental_fwd_kernel, mdn::fused_tile_kernel, mdn::finish_kernel, "
+                "gpu_launches": 6 * args.steps,
+                "launches_per_step": "mdn::fundamental_fwd_kernel, mdn::ref_pack_kernel, mdn::fused_tile_kernel, mdn::finish_kernel, "
                                      "mdn::scale_grads_kernel, mdn::fundamental_bwd_kernel (+1 memset node and torch's "
                                      "ones_like fill for the upstream gradient)",
+                "other_flow": second,
                 "roofline": roofline, "cpu_baseline": cpu_base}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -121,7 +121,8 @@ MDN_API int mdn_version(void);
 MDN_API const char* mdn_last_error_string(void);
 
 /* Bytes of device workspace mdn_loss_fused needs for this description (tile partial sums, per-sample
- * sums, SN max keys, a completion ticket). */
+ * sums, SN max keys, a completion ticket and -- with MDN_TERM_PHOTO -- the source images repacked to one
+ * float4 per pixel for the warp gather: 16 bytes x pixels x pairs x scales). */
 MDN_API size_t mdn_loss_workspace_bytes(const MdnLossDesc* desc);
 
 /*
@@ -142,6 +143,14 @@ MDN_API size_t mdn_loss_workspace_bytes(const MdnLossDesc* desc);
  *   loss_out[MDN_OUT_LOSS]   = w_e*EPIP + w_s*SMOOTH + w_c*CONSIS + w_p*PHOTO
  */
 MDN_API int mdn_loss_fused(const MdnLossDesc* desc, float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Measurement aid (bench.py's roofline line): the same call, bracketed by CUDA events on `stream`; BLOCKS until the
+ * work has finished and returns, in HOST memory, ms_out[0] = source-image repack kernel, ms_out[1] = the fused tile
+ * kernel alone (the dominant kernel of the path), ms_out[2] = the finish kernel.  Not for use inside a training step.
+ */
+MDN_API int mdn_loss_fused_profile(const MdnLossDesc* desc, float* loss_out, void* workspace, size_t workspace_bytes, void* stream,
+                                   float* ms_out);
 
 /*
  * Backward of the call above for an arbitrary upstream gradient: multiplies every gradient buffer named in

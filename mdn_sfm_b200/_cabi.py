@@ -40,7 +40,8 @@ class MdnLossDesc(C.Structure):
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmdn_loss.so")
 
-EXPORTS = ("mdn_version", "mdn_last_error_string", "mdn_loss_workspace_bytes", "mdn_loss_fused", "mdn_loss_scale_grads",
+EXPORTS = ("mdn_version", "mdn_last_error_string", "mdn_loss_workspace_bytes", "mdn_loss_fused", "mdn_loss_fused_profile",
+           "mdn_loss_scale_grads",
            "mdn_fundamental_fwd", "mdn_fundamental_bwd",
            "mdn_epipolar_points_fwd", "mdn_epipolar_points_bwd", "mdn_epipolar_points_workspace_bytes",
            "mdn_flow_warp_fwd", "mdn_flow_warp_bwd", "mdn_ssim_fwd", "mdn_ssim_bwd", "mdn_binary_image")
@@ -62,6 +63,7 @@ class Library:
             "mdn_last_error_string": (C.c_char_p, []),
             "mdn_loss_workspace_bytes": (sz, [D]),
             "mdn_loss_fused": (C.c_int, [D, _P, _P, sz, _P]),
+            "mdn_loss_fused_profile": (C.c_int, [D, _P, _P, sz, _P, C.POINTER(C.c_float)]),
             "mdn_loss_scale_grads": (C.c_int, [D, _P, _P, _P]),
             "mdn_fundamental_fwd": (C.c_int, [C.POINTER(_P), C.POINTER(_P), _P, i32, i32, i32, _P]),
             "mdn_fundamental_bwd": (C.c_int, [C.POINTER(_P), C.POINTER(_P), _P, C.POINTER(_P), i32, i32, i32, _P]),
@@ -167,6 +169,13 @@ class FusedCall:
         self.keep += [loss_out, workspace]
         library.call("mdn_loss_fused", C.byref(self.desc), loss_out.data_ptr(), workspace.data_ptr(),
                      workspace.numel() * workspace.element_size(), stream)
+
+    def profile(self, library, loss_out, workspace, stream):
+        """Blocking measurement aid: returns (repack_ms, fused_kernel_ms, finish_ms) of one call (mdn_loss_fused_profile)."""
+        ms = (C.c_float * 3)()
+        library.call("mdn_loss_fused_profile", C.byref(self.desc), loss_out.data_ptr(), workspace.data_ptr(),
+                     workspace.numel() * workspace.element_size(), stream, ms)
+        return float(ms[0]), float(ms[1]), float(ms[2])
 
     def scale_grads(self, library, g, applied, stream):
         library.call("mdn_loss_scale_grads", C.byref(self.desc), g.data_ptr(), applied.data_ptr(), stream)

@@ -688,7 +688,9 @@ extern "C" MDN_API size_t mdn_loss_workspace_bytes(const MdnLossDesc* d) {
   return ws_layout(d, plan_tiles(d, K)).total;
 }
 
-extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, void* workspace, size_t workspace_bytes, void* stream_) {
+// ev (optional): four events recorded on `stream` before the source repack, before the fused kernel, after it and
+// after the finish kernel (mdn_loss_fused_profile)
+static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, size_t workspace_bytes, void* stream_, cudaEvent_t* ev) {
   int rc = check_desc(d);
   if (rc != MDN_OK) return rc;
   if (!loss_out) return fail(MDN_ERR_NULL_POINTER, "loss_out is NULL");
@@ -757,6 +759,7 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
     MDN_LAUNCH(sn_max_kernel, grid, dim3(NTHREADS), 0, stream, K, keys, chunks);
   }
   const bool photo = (d->flags & MDN_TERM_PHOTO) != 0;
+  if (ev) cudaEventRecord(ev[0], stream);
   if (photo) {
     const int hw0 = K.sc[0].h * K.sc[0].w;
     const dim3 pgrid((unsigned)std::min((hw0 / 4 + NTHREADS - 1) / NTHREADS, 1024), (unsigned)(d->n_scales * d->n_pairs * d->batch));
@@ -771,6 +774,7 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
       maps |= S.post_map[p] || S.ori_map[p] || S.warped[p] || S.diff[p] || S.valid[p] || S.ssim_map[p];
     }
   K.prefetch_distance = MDN_FUSED_MIN_CTAS * 148;   // one wave of resident CTAs (148 SMs on B200)
+  if (ev) cudaEventRecord(ev[1], stream);
   const dim3 grid(K.n_tiles), block(FT);
   static bool smem_opt_in = false;   // > 48 KB of dynamic shared memory needs the opt-in attribute (idempotent; set once)
   if (!smem_opt_in) {
@@ -783,10 +787,32 @@ extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, voi
   else if (photo) { auto kfn = fused_tile_kernel<true, false>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
   else if (maps) { auto kfn = fused_tile_kernel<false, true>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
   else { auto kfn = fused_tile_kernel<false, false>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
+  if (ev) cudaEventRecord(ev[2], stream);
   MDN_LAUNCH(finish_kernel, dim3(d->n_scales * d->batch), dim3(FIN_ROWS * NSLOT), 0, stream, Q);
+  if (ev) cudaEventRecord(ev[3], stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return MDN_OK;
+}
+
+extern "C" MDN_API int mdn_loss_fused(const MdnLossDesc* d, float* loss_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return launch_fused(d, loss_out, workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" MDN_API int mdn_loss_fused_profile(const MdnLossDesc* d, float* loss_out, void* workspace, size_t workspace_bytes, void* stream,
+                                              float* ms_out) {
+  if (!ms_out) return fail(MDN_ERR_NULL_POINTER, "ms_out is NULL");
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; ++i)
+    if (cudaEventCreate(&ev[i]) != cudaSuccess) return fail(MDN_ERR_CUDA, "cudaEventCreate failed");
+  int rc = launch_fused(d, loss_out, workspace, workspace_bytes, stream, ev);
+  if (rc == MDN_OK && cudaEventSynchronize(ev[3]) != cudaSuccess) rc = fail(MDN_ERR_CUDA, "cudaEventSynchronize failed");
+  for (int i = 0; i < 3; ++i) {
+    ms_out[i] = 0.f;
+    if (rc == MDN_OK) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  }
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+  return rc;
 }
 
 extern "C" MDN_API int mdn_loss_scale_grads(const MdnLossDesc* d, const float* g, float* applied, void* stream_) {
