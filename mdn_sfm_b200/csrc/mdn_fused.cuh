@@ -220,117 +220,128 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
     const float cx = rep * S.c_smx, cy = rep * S.c_smy, cc40 = S.c_consis * 40.f;
     const float third_l2e = (1.f / 3.f) * 1.4426950408889634f;
     const float* mq = (own && q) ? mob1 : mob0;     // first raw map the stencil reads
-    // Software pipeline over rows: iteration k works on row py0 + k (mask / target rows above and below are carried
-    // in registers), turns the row loaded ONE iteration ago into "the row below", and issues the global loads of
-    // row py0 + k + 2 -- no load is consumed in the iteration that issues it.  k = -3 .. -1 only fill the pipeline.
-    float2 a0c = make_float2(0.f, 0.f), a1c = a0c, mc = a0c, mu = a0c;
-    float2 a0p = a0c, a1p = a0c;                        // pending: raw maps of row py0 + k + 1
-    float mlp = 0.f, mrp = 0.f, mlc = 0.f, mrc = 0.f;   // stencil mask left / right of the patch: pending, current row
-    float2 tc[3];
-    float2 evu = make_float2(0.f, 0.f);
+    // Straight-line over the PR rows of the patch (a rolled software pipeline spent 3 of its 5 iterations filling):
+    // all global loads first -- raw maps of rows py0-1 .. py0+PR, the stencil mask left / right of the patch -- then
+    // the target rows from shared memory, the PR+1 vertical and 3 PR horizontal edge weights, the stencil.
+    float2 a0[PR + 2], a1[PR + 2], mm[PR + 2];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) tc[c] = make_float2(0.f, 0.f);
-#pragma unroll 1
-    for (int k = -3; k < PR; ++k) {
-      const int y = py0 + k;                        // current row
-      // (a) issue the loads of row y + 2
-      const float2 a0q = load_pair(mq, y + 2);
-      const float2 a1q = minmode ? load_pair(mob1, y + 2) : a0q;
-      float l0 = 0.f, l1 = 0.f, r0 = 0.f, r1 = 0.f;
-      if (smooth_on & (k + 2 >= 0) & (k + 2 < PR)) {
-        l0 = load_one(mq, y + 2, px0 - 1); r0 = load_one(mq, y + 2, px1 + 1);
-        if (minmode) { l1 = load_one(mob1, y + 2, px0 - 1); r1 = load_one(mob1, y + 2, px1 + 1); }
-      }
-      if (k >= -2) {
-        // (b) the row below the current one = what was pending
-        const float2 a0n = a0p, a1n = a1p;
-        const float2 mn = minmode ? make_float2((a0n.x <= a1n.x) ? a0n.x : a1n.x, (a0n.y <= a1n.y) ? a0n.y : a1n.y) : a0n;
-        float2 tn[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) tn[c] = make_float2(0.f, 0.f);
-        float2 evd = make_float2(0.f, 0.f);           // vertical edge weights (y | y+1) of the two columns
-        if (smooth_on) {
-          float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            tn[c] = ld2s(sm.T + c * R2P + o2own + (k + 1) * S2);
-            s0 += fabsf(tc[c].x - tn[c].x); s1 += fabsf(tc[c].y - tn[c].y);
-          }
-          const bool ok = (y >= 0) & (y + 1 < h);
-          evd.x = (ok & in0) ? ex2_fast(-s0 * third_l2e) : 0.f;
-          evd.y = (ok & in1) ? ex2_fast(-s1 * third_l2e) : 0.f;
-        }
-        if (k >= 0 && (y < h) & in0) {
-          float2 gm = mbar[0];
-          if (smooth_on) {
-            // horizontal edges (x-1|x), (x|x+1), (x+1|x+2) of this row
-            float sl = 0.f, smid = 0.f, sr = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const float* Tr = sm.T + c * R2P + o2own + k * S2;
-              const float tl = Tr[-1], tr = Tr[2];
-              sl += fabsf(tl - tc[c].x); smid += fabsf(tc[c].x - tc[c].y); sr += fabsf(tc[c].y - tr);
-            }
-            const float e0 = (px0 > 0) ? ex2_fast(-sl * third_l2e) : 0.f;
-            const float e1 = in1 ? ex2_fast(-smid * third_l2e) : 0.f;
-            const float e2 = (px1 + 1 < w) ? ex2_fast(-sr * third_l2e) : 0.f;
-            // d0 = m(x-1) - m(x), d1 = m(x) - m(x+1), d2 = m(x+1) - m(x+2); each pixel counts its right / lower edge
-            const float d0 = mlc - mc.x, d1 = mc.x - mc.y, d2 = mc.y - mrc;
-            acc[SL_SMX + 2 * q] += fabsf(d1) * e1 + fabsf(d2) * e2;
-            const float s0 = signf_(d0) * e0, s1 = signf_(d1) * e1, s2 = signf_(d2) * e2;
-            const float u0 = mu.x - mc.x, u1 = mu.y - mc.y, n0 = mc.x - mn.x, n1 = mc.y - mn.y;
-            acc[SL_SMY + 2 * q] += fabsf(n0) * evd.x + fabsf(n1) * evd.y;
-            gm.x += cx * (s1 - s0) + cy * (signf_(n0) * evd.x - signf_(u0) * evu.x);
-            gm.y += cx * (s2 - s1) + cy * (signf_(n1) * evd.y - signf_(u1) * evu.y);
-          }
-          float2 g0, g1;
-          if (own) { g0 = q ? make_float2(0.f, 0.f) : gm; g1 = q ? gm : make_float2(0.f, 0.f); }
-          else if (shared_mask) { g0 = gm; g1 = make_float2(0.f, 0.f); }
-          else {
-            const bool f0 = a0c.x <= a1c.x, f1 = a0c.y <= a1c.y;
-            g0 = make_float2(f0 ? gm.x : 0.f, f1 ? gm.y : 0.f);
-            g1 = make_float2(f0 ? 0.f : gm.x, f1 ? 0.f : gm.y);
-          }
-          if (consis_on) {
-            // raw maps of this row: (a0c, a1c) are (first map read, second) = (map q, -) in OWN mode
-            const float2 v0 = (own && q) ? load_pair(mob0, y) : a0c;
-            const float2 v1 = own ? (q ? a0c : load_pair(mob1, y)) : a1c;
-            // sigmoid(20 (m - 0.5)) = 1 / (1 + 2^(-20 log2(e) (m - 0.5)))
-            const float kk = -20.f * 1.4426950408889634f;
-            const float p0 = rcp_fast(1.f + ex2_fast(kk * (v0.x - 0.5f))), q0 = rcp_fast(1.f + ex2_fast(kk * (v1.x - 0.5f)));
-            const float p1 = rcp_fast(1.f + ex2_fast(kk * (v0.y - 0.5f))), q1 = rcp_fast(1.f + ex2_fast(kk * (v1.y - 0.5f)));
-            const float df0 = p0 - q0, df1 = in1 ? p1 - q1 : 0.f;
-            // OWN mode visits every pixel once per map: count the value once, and give each map its own gradient
-            if (!own || q == 0) {
-              acc[SL_CONSIS] += df0 * df0 + df1 * df1;
-              g0.x += cc40 * df0 * p0 * (1.f - p0);
-              g0.y += cc40 * df1 * p1 * (1.f - p1);
-            }
-            if (!own || q == 1 || P.n_pairs == 1) {
-              g1.x -= cc40 * df0 * q0 * (1.f - q0);
-              g1.y -= cc40 * df1 * q1 * (1.f - q1);
-            }
-          }
-          if (grads) {
-            if (S.g_mob[0] && (!own || q == 0)) store_pair(S.g_mob[0] + (size_t)b * hw, y, g0);
-            if (S.g_mob[1] && !shared_mask && (!own || q == 1 || P.n_pairs == 1)) store_pair(S.g_mob[1] + (size_t)b * hw, y, g1);
-          }
-        }
-        if (k >= 0) {   // rotate the gradient ring (and clear it for the next use)
-#pragma unroll
-          for (int i = 0; i + 1 < PR; ++i) mbar[i] = mbar[i + 1];
-          mbar[PR - 1] = make_float2(0.f, 0.f);
-        }
-        mu = mc; mc = mn; a0c = a0n; a1c = a1n; evu = evd;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) tc[c] = tn[c];
-        mlc = mlp; mrc = mrp;
-      }
-      // (c) what was loaded in (a) becomes pending (its first use is one iteration away)
-      a0p = a0q; a1p = a1q;
-      mlp = minmode ? ((l0 <= l1) ? l0 : l1) : l0;
-      mrp = minmode ? ((r0 <= r1) ? r0 : r1) : r0;
+    for (int r = 0; r < PR + 2; ++r) {
+      a0[r] = load_pair(mq, py0 - 1 + r);
+      a1[r] = minmode ? load_pair(mob1, py0 - 1 + r) : a0[r];
     }
+    float ml[PR], mr[PR];
+#pragma unroll
+    for (int k = 0; k < PR; ++k) {
+      ml[k] = mr[k] = 0.f;
+      if (smooth_on) {
+        ml[k] = load_one(mq, py0 + k, px0 - 1); mr[k] = load_one(mq, py0 + k, px1 + 1);
+        if (minmode) {
+          const float l1 = load_one(mob1, py0 + k, px0 - 1), r1 = load_one(mob1, py0 + k, px1 + 1);
+          ml[k] = (ml[k] <= l1) ? ml[k] : l1; mr[k] = (mr[k] <= r1) ? mr[k] : r1;
+        }
+      }
+    }
+    // raw maps of the own rows for the consistency term: (a0, a1) are (first map read, second) = (map q, -) in OWN mode
+    float2 v0[PR], v1[PR];
+#pragma unroll
+    for (int k = 0; k < PR; ++k) {
+      v0[k] = (own && q) ? (consis_on ? load_pair(mob0, py0 + k) : a0[k + 1]) : a0[k + 1];
+      v1[k] = own ? (q ? a0[k + 1] : (consis_on ? load_pair(mob1, py0 + k) : a0[k + 1])) : a1[k + 1];
+    }
+#pragma unroll
+    for (int r = 0; r < PR + 2; ++r)
+      mm[r] = minmode ? make_float2((a0[r].x <= a1[r].x) ? a0[r].x : a1[r].x, (a0[r].y <= a1[r].y) ? a0[r].y : a1[r].y) : a0[r];
+    float2 ev[PR + 1];      // vertical edge weights: ev[r] between rows py0-1+r and py0+r, both columns
+    float eh[PR][3];        // horizontal edge weights of row k: (x-1|x), (x|x+1), (x+1|x+2)
+#pragma unroll
+    for (int r = 0; r < PR + 1; ++r) ev[r] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < PR; ++k) eh[k][0] = eh[k][1] = eh[k][2] = 0.f;
+    if (smooth_on) {
+      float2 sv[PR + 1];
+      float sl[PR], smid[PR], sr[PR];
+#pragma unroll
+      for (int r = 0; r < PR + 1; ++r) sv[r] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < PR; ++k) sl[k] = smid[k] = sr[k] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float2 tr[PR + 2];
+#pragma unroll
+        for (int r = 0; r < PR + 2; ++r) tr[r] = ld2s(sm.T + c * R2P + o2own + (r - 1) * S2);
+#pragma unroll
+        for (int r = 0; r < PR + 1; ++r) {
+          const float2 d = fma2(tr[r + 1], splat2(-1.f), tr[r]);
+          sv[r].x += fabsf(d.x); sv[r].y += fabsf(d.y);
+        }
+#pragma unroll
+        for (int k = 0; k < PR; ++k) {
+          const float* Tr = sm.T + c * R2P + o2own + k * S2;
+          sl[k] += fabsf(Tr[-1] - tr[k + 1].x); smid[k] += fabsf(tr[k + 1].x - tr[k + 1].y); sr[k] += fabsf(tr[k + 1].y - Tr[2]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < PR + 1; ++r) {
+        const int ya = py0 - 1 + r;      // edge between rows ya and ya + 1
+        const bool ok = (ya >= 0) & (ya + 1 < h);
+        ev[r].x = (ok & in0) ? ex2_fast(-sv[r].x * third_l2e) : 0.f;
+        ev[r].y = (ok & in1) ? ex2_fast(-sv[r].y * third_l2e) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < PR; ++k) {
+        const bool rowin = (py0 + k < h) & in0;
+        eh[k][0] = (rowin & (px0 > 0)) ? ex2_fast(-sl[k] * third_l2e) : 0.f;
+        eh[k][1] = (rowin & in1) ? ex2_fast(-smid[k] * third_l2e) : 0.f;
+        eh[k][2] = (rowin & (px1 + 1 < w)) ? ex2_fast(-sr[k] * third_l2e) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PR; ++k) {
+      const int y = py0 + k;
+      if (!((y < h) & in0)) continue;
+      float2 gm = mbar[k];
+      if (smooth_on) {
+        const float2 mc = mm[k + 1], mu = mm[k], mn = mm[k + 2];
+        // d0 = m(x-1) - m(x), d1 = m(x) - m(x+1), d2 = m(x+1) - m(x+2); each pixel counts its right / lower edge
+        const float d0 = ml[k] - mc.x, d1 = mc.x - mc.y, d2 = mc.y - mr[k];
+        acc[SL_SMX + 2 * q] += fabsf(d1) * eh[k][1] + fabsf(d2) * eh[k][2];
+        const float s0 = signf_(d0) * eh[k][0], s1 = signf_(d1) * eh[k][1], s2 = signf_(d2) * eh[k][2];
+        const float2 du = fma2(mc, splat2(-1.f), mu), dn = fma2(mn, splat2(-1.f), mc);   // m(y-1) - m(y), m(y) - m(y+1)
+        acc[SL_SMY + 2 * q] += fabsf(dn.x) * ev[k + 1].x + fabsf(dn.y) * ev[k + 1].y;
+        gm.x += cx * (s1 - s0) + cy * (signf_(dn.x) * ev[k + 1].x - signf_(du.x) * ev[k].x);
+        gm.y += cx * (s2 - s1) + cy * (signf_(dn.y) * ev[k + 1].y - signf_(du.y) * ev[k].y);
+      }
+      float2 g0, g1;
+      if (own) { g0 = q ? make_float2(0.f, 0.f) : gm; g1 = q ? gm : make_float2(0.f, 0.f); }
+      else if (shared_mask) { g0 = gm; g1 = make_float2(0.f, 0.f); }
+      else {
+        const bool f0 = a0[k + 1].x <= a1[k + 1].x, f1 = a0[k + 1].y <= a1[k + 1].y;
+        g0 = make_float2(f0 ? gm.x : 0.f, f1 ? gm.y : 0.f);
+        g1 = make_float2(f0 ? 0.f : gm.x, f1 ? 0.f : gm.y);
+      }
+      if (consis_on) {
+        // sigmoid(20 (m - 0.5)) = 1 / (1 + 2^(-20 log2(e) (m - 0.5)))
+        const float kk = -20.f * 1.4426950408889634f;
+        const float2 t0 = fma2(v0[k], splat2(kk), splat2(-0.5f * kk)), t1 = fma2(v1[k], splat2(kk), splat2(-0.5f * kk));
+        const float2 p = make_float2(rcp_fast(1.f + ex2_fast(t0.x)), rcp_fast(1.f + ex2_fast(t0.y)));
+        const float2 r = make_float2(rcp_fast(1.f + ex2_fast(t1.x)), rcp_fast(1.f + ex2_fast(t1.y)));
+        float2 df = fma2(r, splat2(-1.f), p);
+        if (!in1) df.y = 0.f;
+        // OWN mode visits every pixel once per map: count the value once, and give each map its own gradient
+        if (!own || q == 0) {
+          acc[SL_CONSIS] += df.x * df.x + df.y * df.y;
+          g0 = fma2(mul2(mul2(df, splat2(cc40)), p), fma2(p, splat2(-1.f), splat2(1.f)), g0);
+        }
+        if (!own || q == 1 || P.n_pairs == 1)
+          g1 = fma2(mul2(mul2(df, splat2(-cc40)), r), fma2(r, splat2(-1.f), splat2(1.f)), g1);
+      }
+      if (grads) {
+        if (S.g_mob[0] && (!own || q == 0)) store_pair(S.g_mob[0] + (size_t)b * hw, y, g0);
+        if (S.g_mob[1] && !shared_mask && (!own || q == 1 || P.n_pairs == 1)) store_pair(S.g_mob[1] + (size_t)b * hw, y, g1);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PR; ++k) mbar[k] = make_float2(0.f, 0.f);
     flush_acc<TAIL_SLOTS>(acc, sm.red, TAIL_BASE);
   };
 
@@ -598,8 +609,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
 
     if (!PHOTO && !staged) { cp_async_wait_all(); staged = true; __syncthreads(); }
 
-    // -- P4: epipolar forward + adjoint, d(loss)/d(flow); rolled over the rows of the patch (gix / giy / mbar rotate),
-    // the global loads of row k + 1 are issued before row k is computed
+    // -- P4: epipolar forward + adjoint, d(loss)/d(flow)
     {
       float Fm[9];
       float snmax = 1.f;
@@ -641,20 +651,22 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
       const float2 xf2 = make_float2((float)px0, (float)px1);
       const float kbase = (P.post == MDN_POST_SN) ? rcp_fast(snmax) : ((P.threshold > 0.f) ? P.inv_threshold : 1.f);
       const float2 live = make_float2(1.f, in1 ? 1.f : 0.f);   // the second column may lie outside a ragged image
-      Row cur;
-      fetch(0, cur);
+      // straight-line over the PR rows: all global loads of the patch are issued first (one round of latency instead
+      // of one per row), and the rows' dependent chains (sqrt -> rcp -> ... -> adjoint) interleave
+      Row rows[PR];
+#pragma unroll
+      for (int k = 0; k < PR; ++k) fetch(k, rows[k]);
 #ifdef MDN_ABLATE_P4
 #pragma unroll 1
       for (int k = 0; k < 0; ++k) {
 #else
-#pragma unroll 1
+#pragma unroll
       for (int k = 0; k < PR; ++k) {
 #endif
-        Row nxt;
-        fetch(k + 1, nxt);
+        const Row& cur = rows[k];
         const int y = py0 + k;
         // (w-1)/2 [grid_sample] * 2 [2g-1] / (w-1) [/= w-1] * sx [scale factor]
-        float2 gfx = mul2(gix[0], splat2(sx)), gfy = mul2(giy[0], splat2(sy));
+        float2 gfx = mul2(gix[k], splat2(sx)), gfy = mul2(giy[k], splat2(sy));
         float2 mb = make_float2(0.f, 0.f);
         if ((y < h) & in0) {
           if (epi_on) {
@@ -725,12 +737,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
             store_pair(gfly, y, gfy);
           }
         }
-        // rotate the rings: row k + 1 moves to the front, the updated mask gradient to the back
-        const float2 mnew = add2(mbar[0], mb);
-#pragma unroll
-        for (int i = 0; i + 1 < PR; ++i) { gix[i] = gix[i + 1]; giy[i] = giy[i + 1]; mbar[i] = mbar[i + 1]; }
-        mbar[PR - 1] = mnew;
-        cur = nxt;
+        mbar[k] = add2(mbar[k], mb);
       }
 #pragma unroll
       for (int k = 0; k < PAIR_SLOTS; ++k) acc[k] += accp[k].x + accp[k].y;
