@@ -31,7 +31,7 @@ extern "C" {
 #define MDN_API
 #endif
 
-#define MDN_ABI_VERSION 1
+#define MDN_ABI_VERSION 2
 #define MDN_MAX_SCALES 4
 #define MDN_MAX_PAIRS 2
 
@@ -110,6 +110,15 @@ typedef struct MdnLossDesc {
   float w_d2_sim;      /* DC cross-entropy weight (opt.w_d2_sim)                                              */
   float w_e, w_s, w_c, w_p;  /* loss_functions.py:191-194                                                    */
   MdnScale scale[MDN_MAX_SCALES];
+  /* Optional pose inputs (ABI 2).  When cam[p] is given for every pair, the fundamental matrices are built INSIDE the
+   * call -- F = K^-T ((t_x R) K^-1), loss_utils.py:50-62, with R = cam[:, :3, :3], t = cam[:, :3, 3]
+   * (loss_functions.py:45-46) and K^-1 = inv_K[s][:, :3, :3] (:123), products accumulated like mdn_fundamental_fwd --
+   * and scale[s].fmat[p] is ignored (may be NULL); inv_K[s] is then required for every scale.  With MDN_OPT_GRADS,
+   * g_cam[p] (may be NULL) receives d(loss)/d(cam[p]): d/dR in [:3,:3], d/dt in [:3,3], zeros elsewhere -- what
+   * mdn_fundamental_bwd would return for the call's d/dF, without the two extra launches. */
+  const float* cam[MDN_MAX_PAIRS];     /* (B,4,4) relative pose target -> source frame p                          */
+  float* g_cam[MDN_MAX_PAIRS];         /* (B,4,4)                                                                 */
+  const float* inv_K[MDN_MAX_SCALES];  /* (B,4,4) inverse intrinsics of pyramid level s                           */
 } MdnLossDesc;
 
 /* loss_out layout (MDN_OUT_COUNT = 8 device floats) written by mdn_loss_fused.  MDN_OUT_APPLIED is the upstream
@@ -121,8 +130,9 @@ MDN_API int mdn_version(void);
 MDN_API const char* mdn_last_error_string(void);
 
 /* Bytes of device workspace mdn_loss_fused needs for this description (tile partial sums, per-sample
- * sums, SN max keys, a completion ticket and -- with MDN_TERM_PHOTO -- the source images repacked to one
- * float4 per pixel for the warp gather: 16 bytes x pixels x pairs x scales). */
+ * sums, SN max keys, a completion ticket, in-call fundamental matrices and -- with MDN_TERM_PHOTO -- the source
+ * images repacked to one float4 per pixel for the warp gather: 16 bytes x pixels x pairs x scales).  The workspace
+ * needs no initialisation and may be shared by calls with different descriptions on the same stream. */
 MDN_API size_t mdn_loss_workspace_bytes(const MdnLossDesc* desc);
 
 /*

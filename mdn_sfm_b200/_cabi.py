@@ -17,6 +17,8 @@ OPT_SSIM, OPT_INST_MASK, OPT_CROSS_ENT, OPT_GRADS, OPT_CUDA_ARITH = 16, 32, 64, 
 WARP_FLOWWARP_NORM, WARP_CUDA_ARITH = 1, 2
 OUT_LOSS, OUT_EPIP, OUT_SMOOTH, OUT_CONSIS, OUT_PHOTO, OUT_APPLIED, OUT_COUNT = 0, 1, 2, 3, 4, 5, 8
 
+ABI_VERSION = 2
+
 _P = C.c_void_p
 _PAIR = _P * MAX_PAIRS
 
@@ -35,7 +37,8 @@ class MdnLossDesc(C.Structure):
     _fields_ = [("batch", C.c_int32), ("n_scales", C.c_int32), ("n_pairs", C.c_int32), ("post", C.c_int32),
                 ("mask_mode", C.c_int32), ("flags", C.c_int32), ("threshold", C.c_double), ("alpha", C.c_float),
                 ("w_d2_sim", C.c_float), ("w_e", C.c_float), ("w_s", C.c_float), ("w_c", C.c_float),
-                ("w_p", C.c_float), ("scale", MdnScale * MAX_SCALES)]
+                ("w_p", C.c_float), ("scale", MdnScale * MAX_SCALES),
+                ("cam", _PAIR), ("g_cam", _PAIR), ("inv_K", _P * MAX_SCALES)]
 
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmdn_loss.so")
@@ -79,7 +82,7 @@ class Library:
         for name, (res, args) in sig.items():
             fn = getattr(d, name)
             fn.restype, fn.argtypes = res, args
-        if d.mdn_version() != 1:
+        if d.mdn_version() != ABI_VERSION:
             raise RuntimeError("libmdn_loss ABI version mismatch")
 
     def call(self, name, *args):
@@ -157,6 +160,22 @@ class FusedCall:
                     self.keep.append(t)
         if tensors:
             raise TypeError("unknown scale tensors: %s" % sorted(tensors))
+        return self
+
+    def set_poses(self, cams, inv_Ks, g_cams=None):
+        """Poses instead of fundamental matrices (MdnLossDesc.cam / inv_K / g_cam): cams = one (B,4,4) tensor per pair,
+        inv_Ks = one (B,4,4) tensor per scale (in add_scale order), g_cams = gradient buffers or None."""
+        d = self.desc
+        for p, t in enumerate(cams):
+            d.cam[p] = t.data_ptr()
+        for k, t in enumerate(inv_Ks):
+            d.inv_K[k] = t.data_ptr()
+        self.keep += list(cams) + list(inv_Ks)
+        if g_cams is not None:
+            for p, t in enumerate(g_cams):
+                if t is not None:
+                    d.g_cam[p] = t.data_ptr()
+                    self.keep.append(t)
         return self
 
     def workspace_bytes(self, library):

@@ -69,8 +69,10 @@ template <bool B> struct BoolTag { static constexpr bool value = B; };
 template <bool PHOTO, bool MAPS>
 __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(const __grid_constant__ KParams P) {
   MDN_DYN_SMEM(smem_raw);
+  pdl_wait();
   const int tid = threadIdx.x;
   const int t = tid & 31, g = tid >> 5;    // column pair, row group (= warp)
+  if (blockIdx.x == 0 && tid == 0) *P.ticket = 0u;   // finish_kernel's completion ticket (it runs after this grid)
   const bool use_ssim = PHOTO && (P.flags & MDN_OPT_SSIM);
   const bool epi_on = (P.flags & MDN_TERM_EPIPOLAR) != 0;
   const bool smooth_on = (P.flags & MDN_TERM_SMOOTH) != 0;
@@ -359,7 +361,17 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
 
     if (epi_on && tid < 10) {   // fundamental matrix + SN maximum of this (pair, sample): staged now, read in P4
       float v = 1.f;
-      if (tid < 9) v = __ldg(S.fmat[pair] + b * 9 + tid);
+      if (tid < 9) {
+        if (P.cam[pair]) {
+          // poses given: every one of the nine threads builds F (81 FMAs) and keeps its own entry; the sample's first
+          // tile publishes it for finish_kernel's SN fix-up
+          float Fp[9];
+          tile_fmat(P, s, pair, b, Fp);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) if (k == tid) v = Fp[k];
+          if ((x0 | y0) == 0) P.fmat_ws[((size_t)(s * P.n_pairs + pair) * P.batch + b) * 9 + tid] = v;
+        } else v = __ldg(S.fmat[pair] + b * 9 + tid);
+      }
       else if (P.post == MDN_POST_SN) v = __uint_as_float((unsigned)(P.snkey[(s * P.n_pairs + pair) * P.batch + b] >> 32));
       sm.fm[(pair & 1) * 16 + tid] = v;   // double-buffered by pair: a fast warp may start pair 1 while others read pair 0's
     }

@@ -72,8 +72,110 @@ struct KParams {
   float threshold, inv_threshold;
   float* partials;                   // [n_tiles][NSLOT]
   const unsigned long long* snkey;   // [n_scales][n_pairs][batch] packed (bits(max)<<32 | ~argmax)
+  // poses given instead of fundamental matrices (MdnLossDesc.cam / inv_K): F is built by the kernels that need it
+  const float* cam[MDN_MAX_PAIRS];   // (B,4,4) or NULL
+  const float* inv_K[MDN_MAX_SCALES];
+  float* fmat_ws;                    // [n_scales][n_pairs][batch][9] F as the fused kernel used it (written when cam is given)
+  unsigned* ticket;                  // completion ticket of finish_kernel (zeroed by the fused kernel)
   KScale sc[MDN_MAX_SCALES];
 };
+
+// ----------------------------------------------------------------------------------------------- fundamental matrix
+struct FundArgs {
+  const float* inv_K[MDN_MAX_SCALES];
+  const float* cam[MDN_MAX_PAIRS];
+  float* g_cam[MDN_MAX_PAIRS];
+  int n_scales, n_pairs, batch;
+};
+
+MDN_DEV void mat3_mul(const float* A, const float* Bm, float* C) {   // C = A B, k-ordered FMA accumulation from 0
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float acc = __fmul_rn(A[i * 3], Bm[j]);
+      acc = __fmaf_rn(A[i * 3 + 1], Bm[3 + j], acc);
+      C[i * 3 + j] = __fmaf_rn(A[i * 3 + 2], Bm[6 + j], acc);
+    }
+}
+
+MDN_DEV void load_pose(const float* cam, float* R, float* tx) {   // (4,4) row-major -> R (3x3), [t]_x (3x3)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) R[i * 3 + j] = cam[i * 4 + j];
+  const float t0 = cam[3], t1 = cam[7], t2 = cam[11];
+  tx[0] = 0.f; tx[1] = -t2; tx[2] = t1; tx[3] = t2; tx[4] = 0.f; tx[5] = -t0; tx[6] = -t1; tx[7] = t0; tx[8] = 0.f;
+}
+
+// F = K^-T ((t_x R) K^-1) from M1 = t_x R and the (4,4) inverse intrinsics of one sample (loss_utils.py:61-62)
+MDN_DEV void fundamental_from_m1(const float* M1, const float* kp, float* F) {
+  float K[9], KT[9], M2[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { K[r * 3 + c] = kp[r * 4 + c]; KT[c * 3 + r] = kp[r * 4 + c]; }
+  mat3_mul(M1, K, M2);                                // loss_utils.py:62 (inner product first)
+  mat3_mul(KT, M2, F);
+}
+
+MDN_DEV void fundamental_from_pose(const float* cam, const float* kp, float* F) {
+  float R[9], tx[9], M1[9];
+  load_pose(cam, R, tx);
+  mat3_mul(tx, R, M1);                                // loss_utils.py:61
+  fundamental_from_m1(M1, kp, F);
+}
+
+// d(loss)/d(cam[p][b]) from d(loss)/dF of every scale; g_fmat is [n_scales][n_pairs][batch][9]
+MDN_DEV void fundamental_bwd_one(const FundArgs& A, const float* g_fmat, int p, int b) {
+  float R[9], tx[9], G1[9];
+  load_pose(A.cam[p] + b * 16, R, tx);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) G1[k] = 0.f;
+  for (int s = 0; s < A.n_scales; ++s) {                // dL/dM1 = sum_s K gF K^T   (K = K^-1 of scale s)
+    float K[9], KT[9], T1[9], T2[9];
+    const float* kp = A.inv_K[s] + b * 16;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { K[r * 3 + c] = kp[r * 4 + c]; KT[c * 3 + r] = kp[r * 4 + c]; }
+    const float* g = g_fmat + ((size_t)(s * A.n_pairs + p) * A.batch + b) * 9;
+    float gF[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) gF[k] = __ldcg(g + k);
+    mat3_mul(K, gF, T1);
+    mat3_mul(T1, KT, T2);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) G1[k] += T2[k];
+  }
+  float txT[9], RT[9], gR[9], gTx[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { txT[c * 3 + r] = tx[r * 3 + c]; RT[c * 3 + r] = R[r * 3 + c]; }
+  mat3_mul(txT, G1, gR);                                // M1 = t_x R
+  mat3_mul(G1, RT, gTx);
+  float* out = A.g_cam[p] + b * 16;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) out[k] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[r * 4 + c] = gR[r * 3 + c];
+  out[3] = gTx[7] - gTx[5];                             // t0: t_x[2][1] = t0, t_x[1][2] = -t0
+  out[7] = gTx[2] - gTx[6];                             // t1: t_x[0][2] = t1, t_x[2][0] = -t1
+  out[11] = gTx[3] - gTx[1];                            // t2: t_x[1][0] = t2, t_x[0][1] = -t2
+}
+
+// the fundamental matrix of (scale s, pair, sample b): built from the pose when one was given, else loaded
+MDN_DEV void tile_fmat(const KParams& P, int s, int pair, int b, float* F) {
+  if (P.cam[pair]) fundamental_from_pose(P.cam[pair] + b * 16, P.inv_K[s] + b * 16, F);
+  else {
+    const float* src = P.sc[s].fmat[pair] + b * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) F[k] = __ldg(src + k);
+  }
+}
 
 MDN_DEV float post_process(const KParams& P, float e, float snmax, float wgt, float& dpost_de) {
   // returns post (before the DS mask) and d(post)/d(e); wgt = Gaussian distance weight of the pixel (TG only)
@@ -101,10 +203,9 @@ __global__ void __launch_bounds__(NTHREADS) sn_max_kernel(const KParams P, unsig
   int pair = sp % P.n_pairs, s = sp / P.n_pairs;
   const KScale& S = P.sc[s];
   const int hw = S.h * S.w;
-  const float* F = S.fmat[pair] + b * 9;
+  pdl_wait();
   float Fm[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) Fm[k] = __ldg(F + k);
+  tile_fmat(P, s, pair, b, Fm);
   const float* fx = S.flow[pair] + (long long)b * 2 * hw;
   const float* fy = fx + hw;
   unsigned long long best = 0ull;
@@ -136,6 +237,7 @@ __global__ void __launch_bounds__(NTHREADS) sn_max_kernel(const KParams P, unsig
 // three channels of a bilinear corner with ONE 16-byte load (see gather_pair_packed).  Coalesced both ways: three
 // 128-byte reads and one 512-byte write per warp.  grid.y = (scale * n_pairs + pair) * batch + b.
 __global__ void __launch_bounds__(NTHREADS) ref_pack_kernel(const __grid_constant__ KParams P) {
+  pdl_wait();
   const int job = blockIdx.y;
   const int b = job % P.batch, sp = job / P.batch;
   const int pair = sp % P.n_pairs, s = sp / P.n_pairs;
@@ -166,9 +268,10 @@ __global__ void __launch_bounds__(NTHREADS) ref_pack_kernel(const __grid_constan
 struct FParams {
   KParams K;
   float* sample_sums;      // [n_scales][batch][NSLOT]
-  unsigned* ticket;
   float* loss_out;         // MDN_OUT_COUNT
   float* g_fmat[MDN_MAX_SCALES][2];
+  float* gf_ws;            // [n_scales][n_pairs][batch][9] d(loss)/dF, for the pose adjoint of the last block
+  float* g_cam[MDN_MAX_PAIRS];
   float alpha, w_d2, w_e, w_s, w_c, w_p, l1_coef, ssim_coef;
   float scale_div[MDN_MAX_SCALES];
   // reciprocals of the mean denominators, precomputed on the host in double: the single-thread epilogue multiplies
@@ -182,6 +285,7 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
   const KParams& P = Q.K;
   __shared__ float part[FIN_ROWS][NSLOT];
   __shared__ bool is_last;
+  pdl_wait();
   const int s = blockIdx.x / P.batch, b = blockIdx.x % P.batch;
   const KScale& S = P.sc[s];
   const int slot = threadIdx.x % NSLOT, row = threadIdx.x / NSLOT;
@@ -214,7 +318,8 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
         int y = idx / S.w, x = idx - y * S.w;
         const float* flx = S.flow[pair] + (long long)b * 2 * hw;
         float Fm[9];
-        for (int k = 0; k < 9; ++k) Fm[k] = S.fmat[pair][b * 9 + k];
+        const float* Fsrc = P.cam[pair] ? P.fmat_ws + ((size_t)(s * P.n_pairs + pair) * P.batch + b) * 9 : S.fmat[pair] + b * 9;
+        for (int k = 0; k < 9; ++k) Fm[k] = Fsrc[k];
         float u = __fadd_rn((float)x, __fmul_rn(S.sx, flx[idx]));
         float v = __fadd_rn((float)y, __fmul_rn(S.sy, flx[hw + idx]));
         Epi e = epipolar_distance(Fm, (float)x, (float)y, u, v);
@@ -234,17 +339,30 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
     }
     if (Q.g_fmat[s][pair])
       for (int k = 0; k < 9; ++k) Q.g_fmat[s][pair][b * 9 + k] = gF[k];
+    if (Q.gf_ws)
+      for (int k = 0; k < 9; ++k) Q.gf_ws[((size_t)(s * P.n_pairs + pair) * P.batch + b) * 9 + k] = gF[k];
   }
   // last block to arrive folds the per-sample sums into the loss scalars, in a fixed order
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned prev = atomicInc(Q.ticket, gridDim.x - 1);   // wraps to 0 after the last block: reusable across launches
+    unsigned prev = atomicInc(P.ticket, gridDim.x - 1);   // (the fused kernel zeroed the ticket)
     is_last = (prev == gridDim.x - 1);
   }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  // pose adjoint (what mdn_fundamental_bwd computes) from the d/dF every block has published
+  if (Q.gf_ws && threadIdx.x < (unsigned)(P.n_pairs * P.batch)) {
+    const int p = threadIdx.x / P.batch, bb = threadIdx.x - p * P.batch;
+    if (Q.g_cam[p]) {
+      FundArgs A;
+      for (int k = 0; k < MDN_MAX_SCALES; ++k) A.inv_K[k] = P.inv_K[k];
+      for (int k = 0; k < MDN_MAX_PAIRS; ++k) { A.cam[k] = P.cam[k]; A.g_cam[k] = Q.g_cam[k]; }
+      A.n_scales = P.n_scales; A.n_pairs = P.n_pairs; A.batch = P.batch;
+      fundamental_bwd_one(A, Q.gf_ws, p, bb);
+    }
+  }
   __shared__ double tots[MDN_MAX_SCALES][NSLOT];
   if (threadIdx.x < (unsigned)(P.n_scales * NSLOT)) {
     const int ss = threadIdx.x / NSLOT, k = threadIdx.x % NSLOT;
@@ -290,13 +408,14 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
 // ----------------------------------------------------------------------------------------------- scale grads
 struct GradList {
   int n;
-  float* ptr[MDN_MAX_SCALES * 6];
-  long long count[MDN_MAX_SCALES * 6];
+  float* ptr[MDN_MAX_SCALES * 6 + MDN_MAX_PAIRS];
+  long long count[MDN_MAX_SCALES * 6 + MDN_MAX_PAIRS];
 };
 
 __global__ void __launch_bounds__(NTHREADS) scale_grads_kernel(const __grid_constant__ GradList L, const float* g, float* applied,
                                                                unsigned* ticket) {
   __shared__ bool is_last;
+  pdl_wait();
   const float gv = __ldg(g), ap = *applied;
   if (gv == ap) return;                      // loss.backward() with the implicit upstream gradient of 1: nothing to do
   const float ratio = gv / ap;
@@ -388,33 +507,6 @@ __global__ void epipolar_points_bwd_finish_kernel(const float* __restrict__ part
   g_fmat[b * 9 + k] = t;
 }
 
-struct FundArgs {
-  const float* inv_K[MDN_MAX_SCALES];
-  const float* cam[MDN_MAX_PAIRS];
-  float* g_cam[MDN_MAX_PAIRS];
-  int n_scales, n_pairs, batch;
-};
-
-MDN_DEV void mat3_mul(const float* A, const float* Bm, float* C) {   // C = A B, k-ordered FMA accumulation from 0
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      float acc = __fmul_rn(A[i * 3], Bm[j]);
-      acc = __fmaf_rn(A[i * 3 + 1], Bm[3 + j], acc);
-      C[i * 3 + j] = __fmaf_rn(A[i * 3 + 2], Bm[6 + j], acc);
-    }
-}
-
-MDN_DEV void load_pose(const float* cam, float* R, float* tx) {   // (4,4) row-major -> R (3x3), [t]_x (3x3)
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) R[i * 3 + j] = cam[i * 4 + j];
-  const float t0 = cam[3], t1 = cam[7], t2 = cam[11];
-  tx[0] = 0.f; tx[1] = -t2; tx[2] = t1; tx[3] = t2; tx[4] = 0.f; tx[5] = -t0; tx[6] = -t1; tx[7] = t0; tx[8] = 0.f;
-}
-
 __global__ void fundamental_fwd_kernel(const __grid_constant__ FundArgs A, float* __restrict__ fmat) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n_pairs * A.batch) return;
@@ -423,14 +515,8 @@ __global__ void fundamental_fwd_kernel(const __grid_constant__ FundArgs A, float
   load_pose(A.cam[p] + b * 16, R, tx);
   mat3_mul(tx, R, M1);                                  // loss_utils.py:61
   for (int s = 0; s < A.n_scales; ++s) {
-    float K[9], KT[9], M2[9], F[9];
-    const float* kp = A.inv_K[s] + b * 16;
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { K[r * 3 + c] = kp[r * 4 + c]; KT[c * 3 + r] = kp[r * 4 + c]; }
-    mat3_mul(M1, K, M2);                                // loss_utils.py:62 (inner product first)
-    mat3_mul(KT, M2, F);
+    float F[9];
+    fundamental_from_m1(M1, A.inv_K[s] + b * 16, F);
     float* out = fmat + ((size_t)(s * A.n_pairs + p) * A.batch + b) * 9;
 #pragma unroll
     for (int k = 0; k < 9; ++k) out[k] = F[k];
@@ -440,44 +526,8 @@ __global__ void fundamental_fwd_kernel(const __grid_constant__ FundArgs A, float
 __global__ void fundamental_bwd_kernel(const __grid_constant__ FundArgs A, const float* __restrict__ g_fmat) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n_pairs * A.batch) return;
-  const int p = i / A.batch, b = i - p * A.batch;
-  float R[9], tx[9], G1[9];
-  load_pose(A.cam[p] + b * 16, R, tx);
-#pragma unroll
-  for (int k = 0; k < 9; ++k) G1[k] = 0.f;
-  for (int s = 0; s < A.n_scales; ++s) {                // dL/dM1 = sum_s K gF K^T   (K = K^-1 of scale s)
-    float K[9], KT[9], T1[9], T2[9];
-    const float* kp = A.inv_K[s] + b * 16;
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { K[r * 3 + c] = kp[r * 4 + c]; KT[c * 3 + r] = kp[r * 4 + c]; }
-    const float* g = g_fmat + ((size_t)(s * A.n_pairs + p) * A.batch + b) * 9;
-    float gF[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) gF[k] = g[k];
-    mat3_mul(K, gF, T1);
-    mat3_mul(T1, KT, T2);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) G1[k] += T2[k];
-  }
-  float txT[9], RT[9], gR[9], gTx[9];
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { txT[c * 3 + r] = tx[r * 3 + c]; RT[c * 3 + r] = R[r * 3 + c]; }
-  mat3_mul(txT, G1, gR);                                // M1 = t_x R
-  mat3_mul(G1, RT, gTx);
-  float* out = A.g_cam[p] + b * 16;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) out[k] = 0.f;
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) out[r * 4 + c] = gR[r * 3 + c];
-  out[3] = gTx[7] - gTx[5];                             // t0: t_x[2][1] = t0, t_x[1][2] = -t0
-  out[7] = gTx[2] - gTx[6];                             // t1: t_x[0][2] = t1, t_x[2][0] = -t1
-  out[11] = gTx[3] - gTx[1];                            // t2: t_x[1][0] = t2, t_x[0][1] = -t2
+  const int p = i / A.batch;
+  fundamental_bwd_one(A, g_fmat, p, i - p * A.batch);
 }
 
 __global__ void __launch_bounds__(NTHREADS) flow_warp_fwd_kernel(const float* __restrict__ ref, const float* __restrict__ flow,
@@ -606,7 +656,7 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 extern "C" MDN_API int mdn_version(void) { return MDN_ABI_VERSION; }
 extern "C" MDN_API const char* mdn_last_error_string(void) { return g_err; }
 
-struct WsLayout { size_t partials, sample_sums, refpack, snkeys, ticket, total; int n_tiles; };
+struct WsLayout { size_t partials, sample_sums, refpack, snkeys, ticket, fmat, gfmat, total; int n_tiles; };
 
 static int plan_tiles(const MdnLossDesc* d, KParams& K) {
   int t = 0;
@@ -630,6 +680,15 @@ static int check_desc(const MdnLossDesc* d) {
   if ((d->flags & MDN_TERM_CONSIS) && d->mask_mode == MDN_MASK_SHARED)
     return fail(MDN_ERR_UNSUPPORTED, "consistency term needs two mobile maps (not MDN_MASK_SHARED)");
   const int f = d->flags;
+  // poses instead of fundamental matrices: all pairs or none, and the inverse intrinsics of every scale
+  bool poses = d->cam[0] != nullptr;
+  for (int p = 0; p < d->n_pairs; ++p)
+    if ((d->cam[p] != nullptr) != poses) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "cam[p] (give every pair's pose or none)");
+  if (poses)
+    for (int s = 0; s < d->n_scales; ++s)
+      if (!d->inv_K[s]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "inv_K[s] (required with cam)");
+  for (int p = 0; p < d->n_pairs; ++p)
+    if (d->g_cam[p] && !poses) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "cam[p] (g_cam needs the poses)");
   for (int s = 0; s < d->n_scales; ++s) {
     const MdnScale& S = d->scale[s];
     if (S.height < 2 || S.width < 2 || (long long)S.height * S.width > (1ll << 30)) return fail(MDN_ERR_BAD_SHAPE, "height/width must be >= 2");
@@ -643,7 +702,7 @@ static int check_desc(const MdnLossDesc* d) {
     for (int p = 0; p < d->n_pairs; ++p) {
       if (f & MDN_TERM_PHOTO) NEED(S.ref[p], "ref");
       if (f & (MDN_TERM_PHOTO | MDN_TERM_EPIPOLAR)) NEED(S.flow[p], "flow");
-      if (f & MDN_TERM_EPIPOLAR) { if (!S.fmat[p]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "fmat"); }
+      if ((f & MDN_TERM_EPIPOLAR) && !poses) { if (!S.fmat[p]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "fmat"); }
       OPT(S.g_flow[p], "g_flow"); OPT(S.g_mob[p], "g_mob"); OPT(S.post_map[p], "post_map"); OPT(S.ori_map[p], "ori_map");
       OPT(S.warped[p], "warped"); OPT(S.diff[p], "diff"); OPT(S.ssim_map[p], "ssim_map");
     }
@@ -676,6 +735,9 @@ static WsLayout ws_layout(const MdnLossDesc* d, int n_tiles) {
   L.refpack = take(packed);
   L.snkeys = take((size_t)d->n_scales * d->n_pairs * d->batch * sizeof(unsigned long long));
   L.ticket = take(256);
+  const size_t nf = (size_t)d->n_scales * d->n_pairs * d->batch * 9 * sizeof(float);
+  L.fmat = take(d->cam[0] ? nf : 0);
+  L.gfmat = take(d->cam[0] ? nf : 0);
   L.total = off;
   L.n_tiles = n_tiles;
   return L;
@@ -709,8 +771,15 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
   unsigned long long* keys = (unsigned long long*)(ws + L.snkeys);
   K.snkey = keys;
   Q.sample_sums = (float*)(ws + L.sample_sums);
-  Q.ticket = (unsigned*)(ws + L.ticket);
+  K.ticket = (unsigned*)(ws + L.ticket);
   Q.loss_out = loss_out;
+  const bool poses = d->cam[0] != nullptr && (d->flags & MDN_TERM_EPIPOLAR);
+  if (poses) {
+    K.fmat_ws = (float*)(ws + L.fmat);
+    for (int p = 0; p < d->n_pairs; ++p) { K.cam[p] = d->cam[p]; Q.g_cam[p] = (d->flags & MDN_OPT_GRADS) ? d->g_cam[p] : nullptr; }
+    for (int s = 0; s < d->n_scales; ++s) K.inv_K[s] = d->inv_K[s];
+    if (d->flags & MDN_OPT_GRADS) Q.gf_ws = (float*)(ws + L.gfmat);
+  }
   const bool use_ssim = (d->flags & MDN_OPT_SSIM) != 0;
   Q.alpha = d->alpha; Q.w_d2 = d->w_d2_sim; Q.w_e = d->w_e; Q.w_s = d->w_s; Q.w_c = d->w_c; Q.w_p = d->w_p;
   Q.l1_coef = use_ssim ? 0.15f : 1.f; Q.ssim_coef = use_ssim ? 0.85f : 0.f;
@@ -750,10 +819,10 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
         if (d->flags & MDN_TERM_PHOTO) rp += (size_t)d->batch * K.sc[s].h * K.sc[s].w;
       }
   }
-  // SN keys and the completion ticket are adjacent in the workspace: one memset node zeroes both
-  if (cudaMemsetAsync(keys, 0, L.total - L.snkeys, stream) != cudaSuccess) return fail(MDN_ERR_CUDA, "memset failed");
+  // the completion ticket is zeroed by the fused kernel itself; only the SN pre-pass needs a cleared buffer
   if ((d->flags & MDN_TERM_EPIPOLAR) && d->post == MDN_POST_SN) {
     size_t nkeys = (size_t)d->n_scales * d->n_pairs * d->batch;
+    if (cudaMemsetAsync(keys, 0, nkeys * sizeof(unsigned long long), stream) != cudaSuccess) return fail(MDN_ERR_CUDA, "memset failed");
     const int chunks = 16;
     dim3 grid(chunks, (unsigned)nkeys);
     MDN_LAUNCH(sn_max_kernel, grid, dim3(NTHREADS), 0, stream, K, keys, chunks);
@@ -763,7 +832,7 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
   if (photo) {
     const int hw0 = K.sc[0].h * K.sc[0].w;
     const dim3 pgrid((unsigned)std::min((hw0 / 4 + NTHREADS - 1) / NTHREADS, 1024), (unsigned)(d->n_scales * d->n_pairs * d->batch));
-    MDN_LAUNCH(ref_pack_kernel, pgrid, dim3(NTHREADS), 0, stream, K);
+    MDN_LAUNCH_PDL(1, ref_pack_kernel, pgrid, dim3(NTHREADS), 0, stream, K);
   }
   const size_t smem = fused_smem_floats(photo) * sizeof(float);
   static_assert(fused_smem_floats(true) * sizeof(float) <= 75 * 1024, "three CTAs per SM");
@@ -781,14 +850,16 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
     const int bytes = (int)(fused_smem_floats(true) * sizeof(float));
     cudaFuncSetAttribute(fused_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(fused_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(fused_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(fused_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     smem_opt_in = true;
   }
-  if (photo && maps) { auto kfn = fused_tile_kernel<true, true>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
-  else if (photo) { auto kfn = fused_tile_kernel<true, false>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
-  else if (maps) { auto kfn = fused_tile_kernel<false, true>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
-  else { auto kfn = fused_tile_kernel<false, false>; MDN_LAUNCH(kfn, grid, block, smem, stream, K); }
+  if (photo && maps) { auto kfn = fused_tile_kernel<true, true>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
+  else if (photo) { auto kfn = fused_tile_kernel<true, false>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
+  else if (maps) { auto kfn = fused_tile_kernel<false, true>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
+  else { auto kfn = fused_tile_kernel<false, false>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
   if (ev) cudaEventRecord(ev[2], stream);
-  MDN_LAUNCH(finish_kernel, dim3(d->n_scales * d->batch), dim3(FIN_ROWS * NSLOT), 0, stream, Q);
+  MDN_LAUNCH_PDL(4, finish_kernel, dim3(d->n_scales * d->batch), dim3(FIN_ROWS * NSLOT), 0, stream, Q);
   if (ev) cudaEventRecord(ev[3], stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -830,9 +901,11 @@ extern "C" MDN_API int mdn_loss_scale_grads(const MdnLossDesc* d, const float* g
       if (S.g_fmat[p]) { L.ptr[L.n] = S.g_fmat[p]; L.count[L.n++] = 9ll * d->batch; }
     }
   }
+  for (int p = 0; p < MDN_MAX_PAIRS; ++p)
+    if (d->g_cam[p]) { L.ptr[L.n] = d->g_cam[p]; L.count[L.n++] = 16ll * d->batch; }
   if (L.n == 0) return MDN_OK;
   // applied[1] (MDN_OUT_APPLIED + 1) is the completion ticket, zeroed by mdn_loss_fused
-  MDN_LAUNCH(scale_grads_kernel, dim3(296), dim3(NTHREADS), 0, stream, L, g, applied, reinterpret_cast<unsigned*>(applied + 1));
+  MDN_LAUNCH_PDL(8, scale_grads_kernel, dim3(296), dim3(NTHREADS), 0, stream, L, g, applied, reinterpret_cast<unsigned*>(applied + 1));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return MDN_OK;

@@ -78,16 +78,20 @@ def _workspace(device, nbytes):
     return ws
 
 
-def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None, g_fmat_all=None):
+def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None, g_fmat_all=None, poses=None, g_cams=None):
     """Launches the fused kernel.
 
     need_grad: per scale a dict {"flow": [bool,bool], "mob": [bool,bool], "fmat": [bool,bool]}.
     g_fmat_all: optional (S,P,B,3,3) buffer whose [k,p] slices receive d/dF (one tensor for the whole pyramid).
+    poses: optional (cams, inv_Ks) -- one (B,4,4) pose per pair and one (B,4,4) inverse intrinsics per scale; the
+    kernels then build the fundamental matrices themselves (MdnLossDesc.cam / inv_K) and `fmat` entries are ignored.
+    g_cams: with poses, per pair a (B,4,4) buffer (or None) that receives d(loss)/d(pose).
     Returns (loss_out (8,), grads (same structure, tensors or None), maps (dict name -> [pair tensors]), call).
     """
     library = library or _cabi.lib()
     dev = None
-    any_grad = any(any(v) for ng in need_grad for v in ng.values()) or g_fmat_all is not None
+    any_grad = (any(any(v) for ng in need_grad for v in ng.values()) or g_fmat_all is not None
+                or (g_cams is not None and any(g is not None for g in g_cams)))
     flags = cfg.flags | (OPT_GRADS if any_grad else 0) | (OPT_CUDA_ARITH if cfg.cuda_arith else 0)
     call = _cabi.FusedCall(batch=cfg.batch, n_pairs=cfg.n_pairs, post=cfg.post, mask_mode=cfg.mask_mode, flags=flags,
                            threshold=cfg.threshold, alpha=cfg.alpha, w_d2_sim=cfg.w_d2_sim, w_e=cfg.w_e, w_s=cfg.w_s,
@@ -128,6 +132,8 @@ def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None
                        fmat=S.fmat, weight=S.weight, inst=S.inst, g_flow=g["flow"], g_mob=g["mob"], g_fmat=g["fmat"],
                        **extra)
         grads.append(g)
+    if poses is not None:
+        call.set_poses(poses[0], poses[1], g_cams)
     loss_out = torch.empty(OUT_COUNT, dtype=torch.float32, device=dev)
     ws = _workspace(dev, call.workspace_bytes(library))
     call.run(library, loss_out, ws, _cabi.stream_ptr(loss_out))
@@ -138,18 +144,21 @@ class _FusedLossFn(torch.autograd.Function):
     """total = fused(flows, mobs, fmats); the gradients were produced by the forward launch."""
 
     @staticmethod
-    def forward(ctx, cfg, scales, slots, library, *diff_inputs):
+    def forward(ctx, cfg, scales, slots, library, poses, *diff_inputs):
         # slots[i] = (scale index, kind, pair) for diff_inputs[i]
         need = [{"flow": [False, False], "mob": [False, False], "fmat": [False, False]} for _ in scales]
         g_fmat_all = None
+        g_cams = [None, None] if poses is not None else None
         for (k, kind, p), t in zip(slots, diff_inputs):
             if kind == "fmat_all":
                 g_fmat_all = torch.empty_like(t)
+            elif kind == "cam":
+                g_cams[p] = torch.empty_like(t)
             elif t.requires_grad:
                 need[k][kind][p] = True
-        loss_out, grads, maps, call = run_fused(cfg, scales, need, library, g_fmat_all)
+        loss_out, grads, maps, call = run_fused(cfg, scales, need, library, g_fmat_all, poses, g_cams)
         ctx.call, ctx.library, ctx.slots, ctx.grads, ctx.loss_out = call, library, slots, grads, loss_out
-        ctx.g_fmat_all = g_fmat_all
+        ctx.g_fmat_all, ctx.g_cams = g_fmat_all, g_cams
         ctx.maps = maps
         total = loss_out[0]
         terms = loss_out[1:5]
@@ -162,25 +171,34 @@ class _FusedLossFn(torch.autograd.Function):
         if g.dtype != torch.float32:
             g = g.float()
         ctx.call.scale_grads(ctx.library, g, ctx.loss_out[OUT_APPLIED:], _cabi.stream_ptr(g))
-        out = [None, None, None, None]
+        out = [None, None, None, None, None]
         for (k, kind, p) in ctx.slots:
-            out.append(ctx.g_fmat_all if kind == "fmat_all" else ctx.grads[k][kind][p])
+            out.append(ctx.g_fmat_all if kind == "fmat_all" else (ctx.g_cams[p] if kind == "cam" else ctx.grads[k][kind][p]))
         return tuple(out)
 
 
-def fused_loss(cfg: FusedConfig, scales: List[ScaleData], library=None, fmat_all=None):
+def fused_loss(cfg: FusedConfig, scales: List[ScaleData], library=None, fmat_all=None, cams=None, inv_Ks=None):
     """-> (total 0-d tensor with grad_fn, terms (4,) = [epip, smooth, consis, photo] detached, maps dict).
 
     fmat_all: the (S,P,B,3,3) tensor the per-scale `fmat` entries are slices of; when it requires grad its gradient
-    is returned as ONE tensor instead of S*P slice gradients."""
+    is returned as ONE tensor instead of S*P slice gradients.
+    cams / inv_Ks: poses (one (B,4,4) per pair) and inverse intrinsics (one (B,4,4) per scale) INSTEAD of fundamental
+    matrices: F is built inside the call and the pose gradients come back from the same launches."""
     library = library or _cabi.lib()
     slots, diff = [], []
     grad_on = torch.is_grad_enabled()
+    poses = None
+    if cams is not None:
+        poses = ([c.detach() for c in cams], [k.detach() for k in inv_Ks])
+        for p, c in enumerate(cams):
+            if c.requires_grad and grad_on:
+                slots.append((0, "cam", p))
+                diff.append(c)
     if fmat_all is not None and fmat_all.requires_grad and grad_on:
         slots.append((0, "fmat_all", 0))
         diff.append(fmat_all)
     for k, S in enumerate(scales):
-        for kind in ("flow", "mob") + (() if fmat_all is not None else ("fmat",)):
+        for kind in ("flow", "mob") + (() if (fmat_all is not None or cams is not None) else ("fmat",)):
             for p, t in enumerate(getattr(S, kind)):
                 if t is not None and t.requires_grad and torch.is_grad_enabled():
                     if kind == "mob" and cfg.mask_mode == MASK_SHARED and p == 1:
@@ -189,10 +207,10 @@ def fused_loss(cfg: FusedConfig, scales: List[ScaleData], library=None, fmat_all
                     diff.append(t)
     holder = {}
     if diff:
-        total, terms = _FusedLossFn.apply(cfg, scales, slots, library, *diff)
+        total, terms = _FusedLossFn.apply(cfg, scales, slots, library, poses, *diff)
         maps = total.grad_fn.maps if total.grad_fn is not None and hasattr(total.grad_fn, "maps") else holder
     else:
         need = [{"flow": [False, False], "mob": [False, False], "fmat": [False, False]} for _ in scales]
-        loss_out, _, maps, _ = run_fused(cfg, scales, need, library)
+        loss_out, _, maps, _ = run_fused(cfg, scales, need, library, poses=poses)
         total, terms = loss_out[0], loss_out[1:5]
     return total, terms, maps

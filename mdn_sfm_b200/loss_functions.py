@@ -238,6 +238,9 @@ class Loss(nn.Module):
         self._library = library
         self._arith = arith
         self._cuda_arith = _arith_flag(arith)
+        # arith="cuda": hand the poses to the fused call (F and the pose gradients are computed inside it) instead of
+        # running the fundamental-matrix prologue / epilogue kernels around it; False keeps the three-launch form
+        self.pose_in = True
         self._helper = None
 
     def _lm(self):
@@ -249,10 +252,21 @@ class Loss(nn.Module):
     def _scale_data(self, inputs, frame_id, flow, mobile, instances_info, scales, cam_T_cam, post, bits):
         lm = self._lm()
         ids = list(frame_id)
-        if self._cuda_arith:
-            # one prologue launch: F for every (scale, source frame, sample); gradients flow back to the poses.  Its
-            # 3x3 products accumulate like the batched SGEMM the reference runs on CUDA.
+        poses = None
+        if self._cuda_arith and not self.pose_in:
+            # one prologue launch (mdn_fundamental_fwd): F for every (scale, source frame, sample); autograd carries
+            # d/dF back to the poses through mdn_fundamental_bwd.  Same arithmetic as the in-kernel path below.
             F_all = fundamental_matrices([inputs[("inv_K", s)] for s in scales], [cam_T_cam[i] for i in ids], self._library)
+        elif self._cuda_arith:
+            # the kernels build F themselves from the poses (MdnLossDesc.cam / inv_K: 3x3 products accumulated like the
+            # batched SGEMM the reference runs on CUDA) and return the pose gradients: no prologue / epilogue launches
+            F_all = None
+            cams = [_c(cam_T_cam[i], "cam_T_cam") for i in ids]
+            inv_Ks = [_c(inputs[("inv_K", s)].detach(), "inv_K") for s in scales]
+            for t in cams + inv_Ks:
+                if t.dim() != 3 or tuple(t.shape[1:]) != (4, 4):
+                    raise ValueError("inv_K / cam_T_cam must be (B,4,4)")
+            poses = (cams, inv_Ks)
         else:
             # arith="cpu": the reference's own three torch.matmul calls (loss_utils.py:61-62), batched over scales / frames
             R = torch.stack([cam_T_cam[i][:, :3, :3] for i in ids], 0).unsqueeze(0)      # (1,P,B,3,3)
@@ -266,7 +280,8 @@ class Loss(nn.Module):
             S = fused.ScaleData(h, w, float(w), float(h), float(2 ** s), tgt=tgt)
             for p, i in enumerate(ids):
                 S.flow[p] = _c(flow[("flow", i, s)], "flow")
-                S.fmat[p] = F_all[k, p]
+                if F_all is not None:
+                    S.fmat[p] = F_all[k, p]
                 if self.photometric:
                     S.ref[p] = _c(inputs[("color", i, s)], "source image")
             if self.opt.disable_min and len(ids) == 2:   # pair p is masked with its own frame's map
@@ -277,7 +292,7 @@ class Loss(nn.Module):
                 S.mob[1] = _c(mobile[("mobile", 1, s)], "mobile mask")
             S.weight, S.inst = lm._epi_extras(post, bits, h, w, tgt.device, instances_info)
             data.append(S)
-        return data, F_all
+        return data, F_all, poses
 
     def forward(self, inputs, frame_id, flow, mobile, instances_info, scales, cam_T_cam):
         o = self.opt
@@ -292,13 +307,14 @@ class Loss(nn.Module):
             flags |= TERM_CONSIS
         if self.photometric:
             flags |= TERM_PHOTO | (OPT_SSIM if self.ssim is not None else 0)
-        data, F_all = self._scale_data(inputs, ids, flow, mobile, instances_info, scales, cam_T_cam, post, bits)
+        data, F_all, poses = self._scale_data(inputs, ids, flow, mobile, instances_info, scales, cam_T_cam, post, bits)
+        cams, inv_Ks = poses if poses is not None else (None, None)
         b = data[0].tgt.shape[0]
         cfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=len(ids), post=post, mask_mode=MASK_OWN if o.disable_min else MASK_MIN,
                                 flags=flags, threshold=getattr(o, "threshold", None) if post != fused.POST_SN else None,
                                 alpha=o.alpha, w_d2_sim=o.w_d2_sim, w_e=o.w_e, w_s=o.w_s, w_c=o.w_c,
                                 w_p=getattr(o, "w_p", 1.0) if self.photometric else 0.0)
-        total, terms, _ = fused.fused_loss(cfg, data, self._library, fmat_all=F_all)
+        total, terms, _ = fused.fused_loss(cfg, data, self._library, fmat_all=F_all, cams=cams, inv_Ks=inv_Ks)
         losses = {"consis": terms[OUT_CONSIS - 1] if not o.disable_consisloss else 0, "epip": terms[OUT_EPIP - 1],
                   "smooth": terms[OUT_SMOOTH - 1] if not o.disable_smoothloss else 0, "loss": total}
         if self.photometric:
@@ -321,7 +337,8 @@ class Loss(nn.Module):
                 mcfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=len(ids), post=post, mask_mode=cfg.mask_mode,
                                          flags=flags & ~(TERM_SMOOTH | TERM_CONSIS), threshold=cfg.threshold,
                                          alpha=o.alpha, w_d2_sim=o.w_d2_sim, want_maps=want)
-                _, _, maps = fused.fused_loss(mcfg, [S], self._library)
+                _, _, maps = fused.fused_loss(mcfg, [S], self._library, cams=None if cams is None else [c.detach() for c in cams],
+                                              inv_Ks=None if inv_Ks is None else inv_Ks[:1])
                 h, w = S0.height, S0.width
                 sf = get_scale_factor(b, h, w).to(S0.tgt.device)
                 cache["epipolars"] = {(i, 0): maps["post_map"][p].expand(b, 3, h, w) for p, i in enumerate(ids)}

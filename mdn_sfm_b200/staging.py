@@ -1,0 +1,80 @@
+"""Host -> device staging of one batch of loss inputs (the step in front of ``Loss.forward``).
+
+The reference uploads a batch key by key (``inputs[key] = ipt.to(self.device)``, trainer.py:226-227): ~30 small
+``cudaMemcpyAsync`` calls per step on the compute stream.  ``BatchStager`` keeps the whole batch in ONE pinned host
+slab and ONE device slab per buffer: the loader writes into the pinned views, ``upload()`` issues a single copy on a
+dedicated copy stream, and with two (or more) buffers the copy of batch i+1 overlaps the loss kernels of batch i.
+The tensors handed to the loss are views of the device slab, 256-byte aligned, contiguous fp32 NCHW as the C ABI wants.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def _layout(template):
+    """template: list of dicts {key: tensor}; -> ([(dict index, key, shape, dtype, offset, nbytes)], total bytes)."""
+    entries, off = [], 0
+    for di, d in enumerate(template):
+        for k, v in d.items():
+            nbytes = v.numel() * v.element_size()
+            entries.append((di, k, tuple(v.shape), v.dtype, off, nbytes))
+            off += (nbytes + 255) & ~255
+    return entries, off
+
+
+class BatchStager:
+    """Double-buffered single-copy upload of a batch given as a list of ``{key: tensor}`` dicts.
+
+    >>> st = BatchStager([inputs, flows, mobiles, cams], device)      # shapes / dtypes are taken from the template
+    >>> host = st.host_views(0)                                       # pinned views the loader fills in place
+    >>> dev_dicts = st.upload(0)                                      # one cudaMemcpyAsync on the copy stream
+    >>> st.wait(0)                                                    # the current stream waits for that copy
+    """
+
+    def __init__(self, template, device, n_buffers=2):
+        self.device = torch.device(device)
+        self.entries, self.nbytes = _layout(template)
+        self.n_dicts = len(template)
+        self.n_buffers = n_buffers
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.host = [torch.empty(self.nbytes, dtype=torch.uint8).pin_memory() for _ in range(n_buffers)]
+        self.dev = [torch.empty(self.nbytes, dtype=torch.uint8, device=self.device) for _ in range(n_buffers)]
+        self.ready = [torch.cuda.Event() for _ in range(n_buffers)]     # copy of buffer k has landed
+        self.free = [torch.cuda.Event() for _ in range(n_buffers)]      # consumers of buffer k have finished
+        self._host_views = [self._views(h) for h in self.host]
+        self._dev_views = [self._views(d) for d in self.dev]
+        for e in self.free:
+            e.record(torch.cuda.current_stream(self.device))
+
+    def _views(self, slab):
+        out = [dict() for _ in range(self.n_dicts)]
+        for di, k, shape, dtype, off, nbytes in self.entries:
+            out[di][k] = slab[off:off + nbytes].view(dtype).view(shape)
+        return out
+
+    def host_views(self, k):
+        """The pinned host tensors of buffer k (same keys / shapes as the template): write the next batch here."""
+        return self._host_views[k % self.n_buffers]
+
+    def fill(self, k, dicts):
+        """Convenience for loaders that already hold tensors: copies them into the pinned views of buffer k."""
+        for dst, src in zip(self.host_views(k), dicts):
+            for key, v in src.items():
+                dst[key].copy_(v)
+
+    def upload(self, k):
+        """Enqueues the copy of buffer k on the copy stream (after the previous consumers of that device buffer are
+        done) and returns the device views.  Call wait(k) on the consuming stream before using them."""
+        k %= self.n_buffers
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[k])
+            self.dev[k].copy_(self.host[k], non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        return self._dev_views[k]
+
+    def wait(self, k):
+        torch.cuda.current_stream(self.device).wait_event(self.ready[k % self.n_buffers])
+
+    def release(self, k):
+        """Marks the end of the work that reads device buffer k (recorded on the current stream)."""
+        self.free[k % self.n_buffers].record(torch.cuda.current_stream(self.device))

@@ -50,7 +50,7 @@ def oracle_run(opt, batch, mode, photo, ssim_on, device="cpu", pose_grad=False):
     return out, losses, f, m, cams
 
 
-def product_run(opt, batch, mode, photo, ssim_on, device, pose_grad=False, library=None, arith=None):
+def product_run(opt, batch, mode, photo, ssim_on, device, pose_grad=False, library=None, arith=None, pose_in=True):
     arith = arith or ("cuda" if str(device).startswith("cuda") else "cpu")
     from mdn_sfm_b200.loss_functions import Loss
     inputs, flows, mobiles, cams, inst = batch
@@ -63,6 +63,7 @@ def product_run(opt, batch, mode, photo, ssim_on, device, pose_grad=False, libra
         cams = leaf(cams)
     scales = sorted({k[2] for k in flows})
     loss = Loss(opt, no_ssim=not ssim_on, mode=mode, photometric=photo, library=library, arith=arith)
+    loss.pose_in = pose_in
     out, losses = loss(inputs, [-1, 1], f, m, inst, scales, cams)
     losses["loss"].backward()
     return out, losses, f, m, cams
@@ -100,3 +101,19 @@ def make(B, H, W, scales=(0, 1, 2, 3), seed=11, flow_std=0.05, **opt_over):
     opt = synthetic.default_opt(B, H, W, **opt_over)
     batch = synthetic.make_batch(B, H, W, scales=scales, seed=seed, flow_std=flow_std)
     return opt, batch
+
+
+def assert_identical_runs(a, b, maps=("epipolars", "epipolar_ori")):
+    """Two product runs agree BIT FOR BIT: loss scalars, every gradient, the listed per-pixel maps."""
+    _, l_a, f_a, m_a, c_a = a
+    _, l_b, f_b, m_b, c_b = b
+    for k in l_a:
+        if torch.is_tensor(l_a[k]):
+            assert torch.equal(l_a[k].detach().cpu(), l_b[k].detach().cpu()), k
+    for da, db, what in ((f_a, f_b, "d/dflow"), (m_a, m_b, "d/dmobile"), (c_a, c_b, "d/dpose")):
+        for k in da:
+            if da[k].grad is not None or db[k].grad is not None:
+                assert torch.equal(da[k].grad.cpu(), db[k].grad.cpu()), (what, k)
+    for name in maps:
+        for key in a[0][name]:
+            assert torch.equal(a[0][name][key].cpu(), b[0][name][key].cpu()), (name, key)

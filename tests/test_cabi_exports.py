@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_symbol():
     for name in declared_symbols():
         assert hasattr(dll, name), name
     lib = _cabi.Library(path)
-    assert lib.cdll.mdn_version() == 1
+    assert lib.cdll.mdn_version() == _cabi.ABI_VERSION
 
 
 def test_struct_layout_matches_header():

@@ -199,3 +199,19 @@ def test_multiple_tiles_in_x_and_vector_staging():
         with emulated():
             got = common.product_run(opt, batch, mode, True, True, "cpu")
             common.compare(ref, got, True)
+
+
+@pytest.mark.parametrize("mode", ["SN", "T"])
+def test_poses_inside_the_call_equal_the_prologue_kernels(mode):
+    """MdnLossDesc.cam / inv_K (F and the pose adjoint computed inside mdn_loss_fused) is bit-identical to
+    mdn_fundamental_fwd -> mdn_loss_fused(fmat) -> mdn_fundamental_bwd, two scales, ragged tiles, SN fix-up included."""
+    opt, batch = common.make(2, 24, 72, scales=(0, 1), seed=13, flow_std=0.08)
+    with emulated():
+        a = common.product_run(opt, batch, mode, True, True, "cpu", pose_grad=True, arith="cuda", pose_in=True)
+        b = common.product_run(opt, batch, mode, True, True, "cpu", pose_grad=True, arith="cuda", pose_in=False)
+        assert all(c.grad is not None and float(c.grad.abs().sum()) > 0 for c in a[4].values())
+        common.assert_identical_runs(a, b)   # (the per-pixel maps are evaluated lazily: inside the emulated block)
+    # and the CUDA-eager arithmetic stays within tolerance of the CPU oracle away from flipped bilinear cells (scalars only)
+    ref = common.oracle_run(opt, batch, mode, True, True, pose_grad=True)
+    for k in ("loss", "epip", "smooth", "consis", "photo"):
+        assert float(a[1][k]) == pytest.approx(float(ref[1][k]), rel=1e-4), k

@@ -149,3 +149,40 @@ def test_native_library_is_what_ran():
     _cabi.lib()
     maps = open("/proc/self/maps").read()
     assert "libmdn_loss.so" in maps
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["SN", "TG", "DC"])
+def test_poses_inside_the_call_equal_the_prologue_kernels_gpu(mode):
+    """MdnLossDesc.cam / inv_K (F built by the fused kernel, pose adjoint by the finish kernel, programmatic dependent
+    launches) == mdn_fundamental_fwd -> mdn_loss_fused(fmat) -> mdn_fundamental_bwd, bit for bit, at configs[0]'s shape."""
+    opt, batch = common.make(4, 192, 640, seed=21)
+    a = common.product_run(opt, batch, mode, True, True, DEV, pose_grad=True, arith="cuda", pose_in=True)
+    b = common.product_run(opt, batch, mode, True, True, DEV, pose_grad=True, arith="cuda", pose_in=False)
+    assert all(c.grad is not None and float(c.grad.abs().sum()) > 0 for c in a[4].values())
+    common.assert_identical_runs(a, b)
+
+
+@pytest.mark.gpu
+def test_batch_stager_uploads_what_the_loader_wrote():
+    """mdn_sfm_b200.staging.BatchStager: one pinned slab -> one copy; the device views equal the loader's tensors,
+    are 256-byte aligned and feed Loss.forward unchanged (same loss as the per-key .to(device) upload)."""
+    from mdn_sfm_b200.loss_functions import Loss
+    from mdn_sfm_b200.staging import BatchStager
+    opt, batch = common.make(2, 64, 96, seed=3)
+    inputs, flows, mobiles, cams, inst = batch
+    st = BatchStager([inputs, flows, mobiles, cams], DEV, n_buffers=2)
+    for k in range(3):   # buffer 0 is reused on the third round
+        st.fill(k, [inputs, flows, mobiles, cams])
+        views = st.upload(k)
+        st.wait(k)
+        for src, dst in zip([inputs, flows, mobiles, cams], views):
+            for key in src:
+                assert dst[key].data_ptr() % 256 == 0 and dst[key].is_contiguous()
+                assert torch.equal(dst[key].cpu(), src[key]), key
+        st.release(k)
+    loss = Loss(opt, no_ssim=False, mode="T", photometric=True)
+    _, a = loss(views[0], [-1, 1], views[1], views[2], None, [0, 1, 2, 3], views[3])
+    mv = lambda d: {k: v.to(DEV) for k, v in d.items()}
+    _, b = loss(mv(inputs), [-1, 1], mv(flows), mv(mobiles), None, [0, 1, 2, 3], mv(cams))
+    assert torch.equal(a["loss"], b["loss"])
