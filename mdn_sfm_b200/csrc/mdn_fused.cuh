@@ -30,12 +30,14 @@ struct FusedSmem {
   float* W;      // [3][R2P]
   float* Q;      // [3][R1P]
   float* D;      // [6][PR][FT] float2
+  float* M;      // [2][R2P] the two mobile maps, tile + halo, ZERO outside the image (halo-2 layout, 1 pixel used)
+  float* FL;     // [PR][2][FT] float2: flow (x, y planes) of the own pixels, stashed by P1 for P4
   float* red;    // [FWARPS][NSLOT]
   float* fm;     // [2][16] fundamental matrix + SN maximum of the (pair, sample)
 };
 
 __host__ __device__ constexpr size_t fused_smem_floats(bool photo) {
-  return 3 * R2P + (size_t)FWARPS * NSLOT + 32 + (photo ? 3 * R2P + 3 * R1P + 6 * PR * FT * 2 : 0);
+  return 3 * R2P + (size_t)FWARPS * NSLOT + 32 + 2 * R2P + (photo ? 3 * R2P + 3 * R1P + 6 * PR * FT * 2 + PR * 2 * FT * 2 : 0);
 }
 
 template <int NV>
@@ -88,9 +90,11 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
   sm.T = smem_raw;
   sm.red = sm.T + 3 * R2P;
   sm.fm = sm.red + FWARPS * NSLOT;
-  sm.W = sm.fm + 32;
+  sm.M = sm.fm + 32;
+  sm.W = sm.M + 2 * R2P;
   sm.Q = sm.W + 3 * R2P;
   sm.D = sm.Q + 3 * R1P;
+  sm.FL = sm.D + 6 * PR * FT * 2;
 
   // ---- which tile
   int s = 0;
@@ -153,46 +157,52 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
     }
   }
 
-  // ---- P0: stage the target image (halo 2, reflection padded) with cp.async; the copies land while P1 runs
-  if (need_tgt) {
-    const float* tg = S.tgt + (size_t)b * 3 * hw;
+  // ---- P0: stage the target image (planes 0-2: halo 2, reflection padded) and the two mobile maps (planes 3-4: zero
+  // outside the image) with cp.async; the copies land while P1 runs.  Nothing after this reads them from global memory.
+  const float* mob0 = opaque_ptr(need_mask ? S.mob[0] + (size_t)b * hw : nullptr);
+  const float* mob1 = opaque_ptr(need_mask ? (shared_mask ? mob0 : S.mob[1] + (size_t)b * hw) : nullptr);
+  {
+    const int pl0 = need_tgt ? 0 : 3, pl1 = need_mask ? (shared_mask ? 4 : 5) : 3;
+    const float* tg = need_tgt ? S.tgt + (size_t)b * 3 * hw : nullptr;
+    auto plane_src = [&](int pl) -> const float* { return pl < 3 ? tg + (size_t)pl * hw : (pl == 3 ? mob0 : mob1); };
+    auto plane_dst = [&](int pl) -> float* { return pl < 3 ? sm.T + pl * R2P : sm.M + (pl - 3) * R2P; };
+    // source coordinate of slot coordinate t: reflected for the image planes, none (-1 -> zero fill) for the maps
+    auto src_index = [&](int pl, int tt, int n) { return pl < 3 ? stage_index(tt, n) : ((unsigned)tt < (unsigned)n ? tt : -1); };
     if (((w & 3) == 0) & (x0 + TW <= w)) {
       // interior columns as 16-byte copies (global x0 + 4q and slot OFF2 + 2 + 4q are both 16-byte aligned)
-      for (int i = tid; i < 3 * R2H * (TW / 4); i += FT) {
+      for (int i = tid + pl0 * R2H * (TW / 4); i < pl1 * R2H * (TW / 4); i += FT) {
         const int c = i / (R2H * (TW / 4)), rr = i - c * (R2H * (TW / 4));
         const int r = rr / (TW / 4), q = rr - r * (TW / 4);
-        const int yy = stage_index(y0 - 2 + r, h);
+        const int yy = src_index(c, y0 - 2 + r, h);
         const bool ok = yy >= 0;
-        cp_async_f32x4(sm.T + c * R2P + OFF2 + r * S2 + 2 + 4 * q, tg + (size_t)c * hw + (ok ? yy * w : 0) + x0 + 4 * q, ok);
+        cp_async_f32x4(plane_dst(c) + OFF2 + r * S2 + 2 + 4 * q, plane_src(c) + (ok ? yy * w : 0) + x0 + 4 * q, ok);
       }
-      for (int i = tid; i < 3 * R2H * 4; i += FT) {
+      for (int i = tid + pl0 * R2H * 4; i < pl1 * R2H * 4; i += FT) {
         const int c = i / (R2H * 4), rr = i - c * (R2H * 4);
         const int r = rr >> 2, k = rr & 3;
         const int j = (k < 2) ? k : TW + k;
-        const int yy = stage_index(y0 - 2 + r, h), xx = stage_index(x0 - 2 + j, w);
+        const int yy = src_index(c, y0 - 2 + r, h), xx = src_index(c, x0 - 2 + j, w);
         const bool ok = (yy | xx) >= 0;
-        cp_async_f32(sm.T + c * R2P + OFF2 + r * S2 + j, tg + (size_t)c * hw + (ok ? yy * w + xx : 0), ok);
+        cp_async_f32(plane_dst(c) + OFF2 + r * S2 + j, plane_src(c) + (ok ? yy * w + xx : 0), ok);
       }
     } else {
-      for (int i = tid; i < R2H * S2; i += FT) {
-        const int r = i / S2, j = i - r * S2;
-        const int yy = stage_index(y0 - 2 + r, h), xx = stage_index(x0 - 2 + j, w);
+      for (int i = tid + pl0 * R2H * S2; i < pl1 * R2H * S2; i += FT) {
+        const int c = i / (R2H * S2), rr = i - c * (R2H * S2);
+        const int r = rr / S2, j = rr - r * S2;
+        const int yy = src_index(c, y0 - 2 + r, h), xx = src_index(c, x0 - 2 + j, w);
         const bool ok = (yy | xx) >= 0;
-        const float* src = tg + (ok ? yy * w + xx : 0);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) cp_async_f32(sm.T + c * R2P + OFF2 + i, src + (size_t)c * hw, ok);
+        cp_async_f32(plane_dst(c) + OFF2 + rr, plane_src(c) + (ok ? yy * w + xx : 0), ok);
       }
     }
   }
+  const float* sM0 = sm.M;
+  const float* sM1 = shared_mask ? sm.M : sm.M + R2P;
   bool staged = false;   // cp.async copies completed and the block synchronised
 
   // accumulated d(loss)/d(mask used by the pairs) of the own pixels; the rolled row loops rotate this ring
   float2 mbar[PR];
 #pragma unroll
   for (int k = 0; k < PR; ++k) mbar[k] = make_float2(0.f, 0.f);
-
-  const float* mob0 = opaque_ptr(need_mask ? S.mob[0] + (size_t)b * hw : nullptr);
-  const float* mob1 = opaque_ptr(need_mask ? (shared_mask ? mob0 : S.mob[1] + (size_t)b * hw) : nullptr);
 
   // the two horizontally adjacent values at (y, px0), (y, px1) of a plane; 0 outside the image.  Offsets are unsigned
   // 32-bit (one IMAD.WIDE.U32 per address).
@@ -221,24 +231,26 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
     const float rep = own ? 1.f : (float)P.n_pairs;
     const float cx = rep * S.c_smx, cy = rep * S.c_smy, cc40 = S.c_consis * 40.f;
     const float third_l2e = (1.f / 3.f) * 1.4426950408889634f;
-    const float* mq = (own && q) ? mob1 : mob0;     // first raw map the stencil reads
-    // Straight-line over the PR rows of the patch (a rolled software pipeline spent 3 of its 5 iterations filling):
-    // all global loads first -- raw maps of rows py0-1 .. py0+PR, the stencil mask left / right of the patch -- then
-    // the target rows from shared memory, the PR+1 vertical and 3 PR horizontal edge weights, the stencil.
+    const float* mq = ((own && q) ? sM1 : sM0) + o2own;     // first raw map the stencil reads (staged, 0 outside the image)
+    const float* m0s = sM0 + o2own;
+    const float* m1s = sM1 + o2own;
+    // Straight-line over the PR rows of the patch: raw maps of rows py0-1 .. py0+PR and the stencil mask left / right
+    // of the patch (shared memory, staged in P0), the target rows, the PR+1 vertical and 3 PR horizontal edge weights,
+    // the stencil.
     float2 a0[PR + 2], a1[PR + 2], mm[PR + 2];
 #pragma unroll
     for (int r = 0; r < PR + 2; ++r) {
-      a0[r] = load_pair(mq, py0 - 1 + r);
-      a1[r] = minmode ? load_pair(mob1, py0 - 1 + r) : a0[r];
+      a0[r] = ld2s(mq + (r - 1) * S2);
+      a1[r] = minmode ? ld2s(m1s + (r - 1) * S2) : a0[r];
     }
     float ml[PR], mr[PR];
 #pragma unroll
     for (int k = 0; k < PR; ++k) {
       ml[k] = mr[k] = 0.f;
       if (smooth_on) {
-        ml[k] = load_one(mq, py0 + k, px0 - 1); mr[k] = load_one(mq, py0 + k, px1 + 1);
+        ml[k] = mq[k * S2 - 1]; mr[k] = mq[k * S2 + 2];
         if (minmode) {
-          const float l1 = load_one(mob1, py0 + k, px0 - 1), r1 = load_one(mob1, py0 + k, px1 + 1);
+          const float l1 = m1s[k * S2 - 1], r1 = m1s[k * S2 + 2];
           ml[k] = (ml[k] <= l1) ? ml[k] : l1; mr[k] = (mr[k] <= r1) ? mr[k] : r1;
         }
       }
@@ -247,8 +259,8 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
     float2 v0[PR], v1[PR];
 #pragma unroll
     for (int k = 0; k < PR; ++k) {
-      v0[k] = (own && q) ? (consis_on ? load_pair(mob0, py0 + k) : a0[k + 1]) : a0[k + 1];
-      v1[k] = own ? (q ? a0[k + 1] : (consis_on ? load_pair(mob1, py0 + k) : a0[k + 1])) : a1[k + 1];
+      v0[k] = (own && q) ? (consis_on ? ld2s(m0s + k * S2) : a0[k + 1]) : a0[k + 1];
+      v1[k] = own ? (q ? a0[k + 1] : (consis_on ? ld2s(m1s + k * S2) : a0[k + 1])) : a1[k + 1];
     }
 #pragma unroll
     for (int r = 0; r < PR + 2; ++r)
@@ -406,7 +418,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
         }
       };
       // stores one gathered pair: warped values -> sW, and for an own pair (k >= 0) derivatives -> sD, validity bits
-      auto put = [&](const GatherPx* G2, bool valid_a, bool valid_b, int r, int j, bool oka, bool okb, int k) {
+      auto put = [&](const GatherPx* G2, bool valid_a, bool valid_b, int r, int j, bool oka, bool okb, int k, float2 fx, float2 fy) {
         float* Wd = sm.W + OFF2 + r * S2 + j;
 #pragma unroll
         for (int c = 0; c < 3; ++c) st2s(Wd + c * R2P, make_float2(oka ? G2[0].v[c] : 0.f, okb ? G2[1].v[c] : 0.f));
@@ -421,6 +433,9 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
             st2s(Dd + (2 * c) * PR * FT * 2, make_float2(G2[0].dx[c], G2[1].dx[c]));
             st2s(Dd + (2 * c + 1) * PR * FT * 2, make_float2(G2[0].dy[c], G2[1].dy[c]));
           }
+          // the flow of the own pixels, for P4 (0 for padding slots, like a masked global load)
+          st2s(sm.FL + ((2 * k) * FT + tid) * 2, make_float2(oka ? fx.x : 0.f, okb ? fx.y : 0.f));
+          st2s(sm.FL + ((2 * k + 1) * FT + tid) * 2, make_float2(oka ? fy.x : 0.f, okb ? fy.y : 0.f));
           if (MAPS && ra) {
             const size_t o = (size_t)y * w + px0;
             if (S.valid[pair]) { S.valid[pair][(size_t)b * hw + o] = valid_a ? 1 : 0; if (rb) S.valid[pair][(size_t)b * hw + o + 1] = valid_b ? 1 : 0; }
@@ -455,7 +470,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
           GatherPx G2[2];
           bool va, vb;
           gather_pair_packed<true>(rfp, h, w, xs, splat2((float)(py0 + k)), fxp, fyp, geom, G2, va, vb);
-          put(G2, va, vb, PR * g + 2 + k, 2 * t + 2, true, true, k);
+          put(G2, va, vb, PR * g + 2 + k, 2 * t + 2, true, true, k, fxc, fyc);
         }
       }
 #ifdef MDN_ABLATE_P1
@@ -477,7 +492,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
         GatherPx G2[2];
         bool va, vb;
         gather_pair_packed<true>(rfp, h, w, make_float2((float)cur.xa, (float)cur.xb), splat2((float)cur.ya), fxp, fyp, geom, G2, va, vb);
-        put(G2, va, vb, cur.r, cur.j, oka, okb, it < PR ? it : -1);
+        put(G2, va, vb, cur.r, cur.j, oka, okb, it < PR ? it : -1, cur.fx, cur.fy);
         cur = nxt;
       }
       if (!staged) { cp_async_wait_all(); staged = true; }
@@ -634,7 +649,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
       const float c_epi = S.c_epi, c_nt = S.c_nt, c_ce = S.c_ce;
       float* gflx = opaque_ptr(S.g_flow[pair] ? S.g_flow[pair] + (size_t)b * 2 * hw : nullptr);
       float* gfly = opaque_ptr(gflx ? gflx + hw : nullptr);
-      const float* mq0 = (own && pair) ? mob1 : mob0;
+      const float* mq0 = ((own && pair) ? sM1 : sM0) + o2own;
       const bool use_inst = (P.flags & (MDN_OPT_INST_MASK | MDN_OPT_CROSS_ENT)) != 0, use_wgt = P.post == MDN_POST_TG;
       struct Row { float2 fx, fy, m0, m1, kin, wgt; };
       auto fetch = [&](int k, Row& R) {
@@ -642,9 +657,11 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
         R.kin = R.wgt = make_float2(1.f, 1.f);
         R.fx = R.fy = R.m0 = R.m1 = make_float2(0.f, 0.f);
         if (epi_on & (k < PR)) {
-          R.fx = load_pair(flx, y); R.fy = load_pair(fly, y);
-          R.m0 = load_pair(mq0, y);
-          R.m1 = minmode ? load_pair(mob1, y) : R.m0;
+          if (PHOTO) {   // stashed by P1
+            R.fx = ld2s(sm.FL + ((2 * k) * FT + tid) * 2); R.fy = ld2s(sm.FL + ((2 * k + 1) * FT + tid) * 2);
+          } else { R.fx = load_pair(flx, y); R.fy = load_pair(fly, y); }
+          R.m0 = ld2s(mq0 + k * S2);
+          R.m1 = minmode ? ld2s(sM1 + o2own + k * S2) : R.m0;
           if (use_wgt) R.wgt = load_pair(S.weight, y);
           if (use_inst & (y < h) & in0) {
             const uint8_t* ip = S.inst + (size_t)b * hw + (unsigned)(y * w + px0);

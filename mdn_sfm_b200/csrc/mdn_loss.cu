@@ -835,7 +835,7 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
     MDN_LAUNCH_PDL(1, ref_pack_kernel, pgrid, dim3(NTHREADS), 0, stream, K);
   }
   const size_t smem = fused_smem_floats(photo) * sizeof(float);
-  static_assert(fused_smem_floats(true) * sizeof(float) <= 75 * 1024, "three CTAs per SM");
+  static_assert(fused_smem_floats(true) * sizeof(float) <= 113 * 1024, "two CTAs per SM");
   bool maps = false;
   for (int s = 0; s < d->n_scales; ++s)
     for (int p = 0; p < 2; ++p) {
