@@ -441,8 +441,8 @@ def run_ours(args):
                                 "mdn_sfm_b200.loss_functions.Loss.forward + backward (eager public API) + loss read back to pinned host memory" % len(host_sets)},
                 "gpu_launches": 4 * args.steps,
                 "launches_per_step": "mdn::ref_pack_kernel, mdn::fused_tile_kernel (builds the fundamental matrices from the poses), "
-                                     "mdn::finish_kernel (loss scalars, d/dF, pose adjoint), mdn::scale_grads_kernel; programmatic "
-                                     "dependent launches (+ torch's ones_like fill for the upstream gradient)",
+                                     "mdn::finish_kernel (loss scalars, d/dF, pose adjoint), mdn::scale_grads_kernel; "
+                                     "(+ torch's ones_like fill for the upstream gradient)",
                 "other_flow": second,
                 "roofline": roofline, "cpu_baseline": cpu_base}
         print(json.dumps(line), flush=True)

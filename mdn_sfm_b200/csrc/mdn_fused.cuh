@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
         unsigned o = (unsigned)(py0 * w + px0);
         float2 fxn = ldg2(flx + o), fyn = ldg2(fly + o);
         const float2 xs = make_float2((float)px0, (float)px1);
-#pragma unroll 1
+#pragma unroll      // (unrolled: the corner loads of row k + 1 are scheduled above the interpolation of row k)
         for (int k = 0; k < PR; ++k) {
           const float2 fxc = fxn, fyc = fyn;
           o += w;

@@ -163,6 +163,7 @@ class _FusedLossFn(torch.autograd.Function):
         total = loss_out[0]
         terms = loss_out[1:5]
         ctx.mark_non_differentiable(terms)
+        ctx.set_materialize_grads(False)   # no zero-filled gradient tensor (a fill launch) for `terms`
         return total, terms
 
     @staticmethod

@@ -24,6 +24,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __shared__ static

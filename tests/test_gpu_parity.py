@@ -154,8 +154,7 @@ def test_native_library_is_what_ran():
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["SN", "TG", "DC"])
 def test_poses_inside_the_call_equal_the_prologue_kernels_gpu(mode):
-    """MdnLossDesc.cam / inv_K (F built by the fused kernel, pose adjoint by the finish kernel, programmatic dependent
-    launches) == mdn_fundamental_fwd -> mdn_loss_fused(fmat) -> mdn_fundamental_bwd, bit for bit, at configs[0]'s shape."""
+    """MdnLossDesc.cam / inv_K (F built by the fused kernel, pose adjoint by the finish kernel) == mdn_fundamental_fwd -> mdn_loss_fused(fmat) -> mdn_fundamental_bwd, bit for bit, at configs[0]'s shape."""
     opt, batch = common.make(4, 192, 640, seed=21)
     a = common.product_run(opt, batch, mode, True, True, DEV, pose_grad=True, arith="cuda", pose_in=True)
     b = common.product_run(opt, batch, mode, True, True, DEV, pose_grad=True, arith="cuda", pose_in=False)
