@@ -218,6 +218,25 @@ MDN_API int mdn_ssim_fwd(const float* x, const float* y, float* out, int32_t pla
 MDN_API int mdn_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* g_y, int32_t planes,
                  int32_t height, int32_t width, void* stream);
 
+/*
+ * Instance-mask preparation for the DS / DC modes, once per step for every pyramid level.
+ *
+ * mdn_instance_mask_union: get_batch_instance_mask (loss_utils.py:102-124) -- `masks` is a HOST array of `batch` device
+ * pointers, masks[b] -> (counts[b], H, W) boolean (1 byte / element) instance masks of sample b (Detectron2
+ * `pred_masks`); `counts` is a HOST array; out (B, H, W) uint8 = (sum over instances != 0).  One channel instead of
+ * the reference's three identical int64 channels.
+ *
+ * mdn_instance_mask_resize: `Resize((h, w))(mask)` of loss_utils.py:73-75 / 135-137 for up to MDN_MAX_SCALES output
+ * sizes in one launch -- torchvision's bilinear + antialias resize of the integer mask (ATen _upsample_bilinear2d_aa:
+ * separable triangle filter of support in/out, fp32, horizontal then vertical) followed by round-half-to-even.
+ * src (B, in_h, in_w) uint8 {0,1}; dst is a HOST array of n_out device pointers, dst[k] -> (B, out_h[k], out_w[k]) uint8
+ * -- the `inst` tensors MdnScale wants.
+ */
+MDN_API int mdn_instance_mask_union(const uint8_t* const* masks, const int32_t* counts, uint8_t* out, int32_t batch,
+                                    int64_t hw, void* stream);
+MDN_API int mdn_instance_mask_resize(const uint8_t* src, int32_t batch, int32_t in_h, int32_t in_w, uint8_t* const* dst,
+                                     const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* stream);
+
 /* binary_image (utils.py:100-103): out = x >= threshold ? 1 : 0 */
 MDN_API int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream);
 

@@ -636,6 +636,106 @@ __global__ void __launch_bounds__(NTHREADS) ssim_bwd_kernel(const float* __restr
   }
 }
 
+// ----------------------------------------------------------------------------------------------- instance masks (DS / DC)
+// get_batch_instance_mask (loss_utils.py:102-124): union of the N boolean instance masks of a sample.
+constexpr int UNION_CHUNK = 32;   // samples per launch (pointer table passed by value)
+struct UnionArgs {
+  const uint8_t* masks[UNION_CHUNK];
+  int count[UNION_CHUNK];
+};
+
+__global__ void __launch_bounds__(NTHREADS) instance_union_kernel(const __grid_constant__ UnionArgs A, uint8_t* __restrict__ out, long long hw) {
+  const int b = blockIdx.y;
+  const uint8_t* src = A.masks[b];
+  const int n = A.count[b];
+  uint8_t* dst = out + (long long)b * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
+    unsigned v = 0;
+    for (int k = 0; k < n; ++k) v |= __ldg(src + (long long)k * hw + i);   // sum(pred_masks, 0) != 0
+    dst[i] = v ? 1 : 0;
+  }
+}
+
+// torchvision Resize (bilinear, antialias, align_corners=False) of a {0,1} mask followed by round-to-nearest-even, as
+// `Resize(size)(int64 mask)` does (loss_utils.py:73-75, 135-137): ATen's separable triangle filter
+// (_upsample_bilinear2d_aa: _compute_weights_span / _compute_weights / interpolate_aa_single_dim) in fp32 with the same
+// operation order -- weights w_j = f((j + xmin - center + 0.5) / scale) / sum, horizontal pass, then vertical.
+constexpr int AA_WFLOATS = 72 * 128;   // shared-memory floats for the per-column x weights: taps x columns per block
+struct ResizeArgs {
+  uint8_t* dst[MDN_MAX_SCALES];
+  int oh[MDN_MAX_SCALES], ow[MDN_MAX_SCALES];
+  int row_begin[MDN_MAX_SCALES + 1];   // first blockIdx.y of each output size
+  int n_out, batch, ih, iw;
+};
+
+MDN_DEV float aa_tri(float x) { x = x < 0.f ? -x : x; return x < 1.f ? __fsub_rn(1.f, x) : 0.f; }
+
+// Span and weights of output index i along one axis, with the operation order and precisions of ATen's CPU helper
+// (_compute_indices_min_size_weights_aa, the oracle's path): the `+ 0.5` literals are double there, so those sums --
+// and the product with 1/scale -- are formed in double and rounded to fp32 once.  (ATen's CUDA helper adds j to a
+// pre-rounded xmin - center in fp32: it can differ in the last bit of a weight, which shows only where a resized
+// value is an exact 0.5 tie.)
+struct AaSpan {
+  int xmin, xsize;
+  float center, invscale, total;
+  MDN_DEV float raw(int j) const {      // un-normalised triangle weight of tap j
+    return aa_tri((float)(((double)__fsub_rn((float)(j + xmin), center) + 0.5) * (double)invscale));
+  }
+  MDN_DEV float weight(int j) const { return total != 0.f ? __fdiv_rn(raw(j), total) : raw(j); }
+};
+
+MDN_DEV AaSpan aa_span(int i, int in_size, float scale) {
+  AaSpan sp;
+  const float support = (scale >= 1.f) ? scale : 1.f;                     // (interp_size * 0.5) * scale, interp_size = 2
+  sp.center = (float)((double)scale * ((double)i + 0.5));
+  sp.xmin = max((int)(long long)((double)__fsub_rn(sp.center, support) + 0.5), 0);
+  sp.xsize = min((int)(long long)((double)__fadd_rn(sp.center, support) + 0.5), in_size) - sp.xmin;
+  sp.xsize = min(max(sp.xsize, 0), (int)ceilf(support) * 2 + 1);
+  sp.invscale = (scale >= 1.f) ? (float)(1.0 / (double)scale) : 1.f;
+  sp.total = 0.f;
+  for (int j = 0; j < sp.xsize; ++j) sp.total = __fadd_rn(sp.total, sp.raw(j));
+  return sp;
+}
+
+// blockDim.x = output columns per block.  use_table: the normalised weights of this block's columns / row are staged in
+// shared memory (wx[tap][column], wy[tap]); otherwise (down-scaling factors beyond the table) they are re-evaluated per tap.
+__global__ void __launch_bounds__(128) instance_resize_kernel(const __grid_constant__ ResizeArgs A, const uint8_t* __restrict__ src,
+                                                              const int use_table) {
+  __shared__ float wx[AA_WFLOATS];
+  __shared__ float wy[AA_WFLOATS / 32];
+  const int cols = blockDim.x;
+  int k = 0;
+#pragma unroll
+  for (int q = 1; q < MDN_MAX_SCALES; ++q)
+    if (q < A.n_out && (int)blockIdx.y >= A.row_begin[q]) k = q;
+  const int oh = A.oh[k], ow = A.ow[k];
+  const int rem = blockIdx.y - A.row_begin[k];
+  const int b = rem / oh, oy = rem - b * oh;
+  const int ox = blockIdx.x * cols + threadIdx.x;
+  if ((int)(blockIdx.x * cols) >= ow) return;
+  const float sh = __fdiv_rn((float)A.ih, (float)oh), sw = __fdiv_rn((float)A.iw, (float)ow);   // area_pixel_compute_scale
+  const AaSpan sy = aa_span(oy, A.ih, sh);
+  const AaSpan sx = aa_span(min(ox, ow - 1), A.iw, sw);
+  if (use_table) {
+    for (int j = threadIdx.x; j < sy.xsize; j += cols) wy[j] = sy.weight(j);
+    for (int j = 0; j < sx.xsize; ++j) wx[j * cols + threadIdx.x] = sx.weight(j);
+    __syncthreads();
+  }
+  if (ox >= ow) return;
+  const uint8_t* base = src + ((long long)b * A.ih + sy.xmin) * A.iw + sx.xmin;
+  float out = 0.f;
+  for (int y = 0; y < sy.xsize; ++y) {
+    const uint8_t* row = base + (long long)y * A.iw;
+    // `output = src[0] * w[0]; output += src[j] * w[j]` (basic_loop_aa_horizontal / _vertical): the library builds
+    // contract the update into an FMA (GCC -ffp-contract=fast with FMA targets on the CPU, nvcc -fmad on CUDA)
+    float t = __fmul_rn((float)__ldg(row), use_table ? wx[threadIdx.x] : sx.weight(0));
+    for (int j = 1; j < sx.xsize; ++j) t = __fmaf_rn((float)__ldg(row + j), use_table ? wx[j * cols + threadIdx.x] : sx.weight(j), t);
+    const float wyv = use_table ? wy[y] : sy.weight(y);
+    out = (y == 0) ? __fmul_rn(t, wyv) : __fmaf_rn(t, wyv, out);
+  }
+  A.dst[k][((long long)b * oh + oy) * ow + ox] = (uint8_t)rintf(out);       // torch.round, then the cast back to integers
+}
+
 __global__ void __launch_bounds__(NTHREADS) binary_image_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, float thr) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = (x[i] >= thr) ? 1.f : 0.f;
@@ -1018,6 +1118,52 @@ extern "C" MDN_API int mdn_ssim_bwd(const float* x, const float* y, const float*
   if (planes < 1 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad SSIM shape (h,w >= 2)");
   MDN_LAUNCH(ssim_bwd_kernel, dim3(blocks_for((long long)height * width), planes), dim3(NTHREADS), 0, (cudaStream_t)stream, x, y, g_out, g_x, g_y,
              (int)height, (int)width);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" MDN_API int mdn_instance_mask_union(const uint8_t* const* masks, const int32_t* counts, uint8_t* out, int32_t batch,
+                                               int64_t hw, void* stream) {
+  if (!masks || !counts || !out) return fail(MDN_ERR_NULL_POINTER, "masks / counts / out is NULL");
+  if (batch < 1 || hw < 1) return fail(MDN_ERR_BAD_SHAPE, "batch / hw out of range");
+  for (int b0 = 0; b0 < batch; b0 += UNION_CHUNK) {
+    UnionArgs A;
+    memset(&A, 0, sizeof(A));
+    const int nb = std::min(UNION_CHUNK, batch - b0);
+    for (int b = 0; b < nb; ++b) {
+      if (counts[b0 + b] < 0 || (counts[b0 + b] > 0 && !masks[b0 + b])) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "masks[b]");
+      A.masks[b] = masks[b0 + b]; A.count[b] = counts[b0 + b];
+    }
+    MDN_LAUNCH(instance_union_kernel, dim3(blocks_for(hw, 296), nb), dim3(NTHREADS), 0, (cudaStream_t)stream, A, out + (long long)b0 * hw, (long long)hw);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" MDN_API int mdn_instance_mask_resize(const uint8_t* src, int32_t batch, int32_t in_h, int32_t in_w, uint8_t* const* dst,
+                                                const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* stream) {
+  if (!src || !dst || !out_h || !out_w) return fail(MDN_ERR_NULL_POINTER, "src / dst / out_h / out_w is NULL");
+  if (batch < 1 || in_h < 1 || in_w < 1 || n_out < 1 || n_out > MDN_MAX_SCALES) return fail(MDN_ERR_BAD_SHAPE, "batch / size / n_out out of range");
+  ResizeArgs A;
+  memset(&A, 0, sizeof(A));
+  A.n_out = n_out; A.batch = batch; A.ih = in_h; A.iw = in_w;
+  int rows = 0, max_w = 0, max_taps = 1;
+  for (int k = 0; k < n_out; ++k) {
+    if (!dst[k]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "dst[k]");
+    if (out_h[k] < 1 || out_w[k] < 1) return fail(MDN_ERR_BAD_SHAPE, "output size out of range");
+    // taps per axis: ceil(support) * 2 + 1 with support = max(scale, 1)
+    const float sh = (float)in_h / (float)out_h[k], sw = (float)in_w / (float)out_w[k];
+    const int th = (int)ceilf(sh >= 1.f ? sh : 1.f) * 2 + 1, tw = (int)ceilf(sw >= 1.f ? sw : 1.f) * 2 + 1;
+    max_taps = std::max(max_taps, std::max(th, tw));
+    A.dst[k] = dst[k]; A.oh[k] = out_h[k]; A.ow[k] = out_w[k];
+    A.row_begin[k] = rows;
+    rows += batch * out_h[k];
+    max_w = std::max(max_w, (int)out_w[k]);
+  }
+  A.row_begin[n_out] = rows;
+  const int use_table = max_taps <= AA_WFLOATS / 32;                      // else: weights re-evaluated per tap (factor > 143)
+  const int cols = max_taps <= 72 ? 128 : (max_taps <= 144 ? 64 : 32);    // taps x columns fit the weight table
+  MDN_LAUNCH(instance_resize_kernel, dim3((max_w + cols - 1) / cols, rows), dim3(cols), 0, (cudaStream_t)stream, A, src, use_table);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }

@@ -32,7 +32,7 @@ from ._cabi import (MASK_MIN, MASK_OWN, MASK_SHARED, OPT_CROSS_ENT, OPT_INST_MAS
 from .layers import SSIM, get_scale_factor  # noqa: F401  (re-exported like the reference module does)
 from .loss_utils import *  # noqa: F401,F403  (the reference does `from loss_utils import *`)
 from .loss_utils import create_coords as _create_coords
-from .loss_utils import _arith_flag, instance_mask_u8
+from .loss_utils import _arith_flag, instance_mask_u8, instance_masks_u8
 from .ops import fundamental_matrices
 from .utils import gauss_distance_weight
 
@@ -133,7 +133,7 @@ class LossModule(nn.Module):
 
     def _epi_extras(self, post, bits, h, w, device, instances_info):
         weight = self._tg_weight(h, w, device) if post == fused.POST_TG else None
-        inst = instance_mask_u8(instances_info, (h, w), device) if bits & (OPT_INST_MASK | OPT_CROSS_ENT) else None
+        inst = instance_mask_u8(instances_info, (h, w), device, self._library) if bits & (OPT_INST_MASK | OPT_CROSS_ENT) else None
         return weight, inst
 
     def _frames(self, inputs, frame_ids, flow, mobiles, instances_info, cam_T_cam, scale, mask_mode):
@@ -290,8 +290,12 @@ class Loss(nn.Module):
             else:                                         # torch.cat([m(-1), m(+1)]).min(1): this order breaks ties
                 S.mob[0] = _c(mobile[("mobile", -1, s)], "mobile mask")
                 S.mob[1] = _c(mobile[("mobile", 1, s)], "mobile mask")
-            S.weight, S.inst = lm._epi_extras(post, bits, h, w, tgt.device, instances_info)
+            S.weight, _ = lm._epi_extras(post, 0, h, w, tgt.device, None)
             data.append(S)
+        if bits & (OPT_INST_MASK | OPT_CROSS_ENT):   # DS / DC: the masks of every pyramid level from one pass (two launches)
+            insts = instance_masks_u8(instances_info, [(S.height, S.width) for S in data], data[0].tgt.device, self._library)
+            for S, m in zip(data, insts):
+                S.inst = m
         return data, F_all, poses
 
     def forward(self, inputs, frame_id, flow, mobile, instances_info, scales, cam_T_cam):

@@ -52,17 +52,48 @@ def get_batch_instance_mask(instances_info):
     return m.to(torch.int64).repeat(1, 3, 1, 1)
 
 
-def instance_mask_u8(instances_info, size, device):
-    """One-channel uint8 {0,1} instance mask at `size`, resized exactly as loss_utils.py:73-75 / :135-137 do
-    (torchvision Resize on the int64 mask, bilinear + antialias, rounded back to integers); the three
-    channels the reference carries are identical, so one is kept."""
-    from torchvision.transforms import Resize
+def _pred_masks(instances_info):
     if isinstance(instances_info, list):
-        m = torch.stack([(info["instances"].pred_masks.sum(0, keepdim=True) != 0) for info in instances_info], 0)
-    else:
-        m = (instances_info.pred_masks.sum(0, keepdim=True) != 0).unsqueeze(0)
-    m = Resize(tuple(size))(m.to(device=device, dtype=torch.int64))
-    return m[:, 0].to(torch.uint8).contiguous()
+        return [info["instances"].pred_masks for info in instances_info]
+    return [instances_info.pred_masks]
+
+
+def instance_masks_u8(instances_info, sizes, device, library=None):
+    """One-channel uint8 {0,1} instance masks at every size in `sizes` (a list of (h, w)), from ONE pass over the
+    Detectron2 masks: `get_batch_instance_mask` (loss_utils.py:102-124: union of the instances of each sample) and the
+    `Resize(size)` of loss_utils.py:73-75 / :135-137 (torchvision bilinear + antialias on the integer mask, rounded
+    back to integers) run as two kernels -- `mdn_instance_mask_union`, `mdn_instance_mask_resize` -- instead of the
+    reference's per-(frame, scale) int64 (B,3,375,1242) tensors.  The three channels upstream carries are identical;
+    one is kept.  -> list of (B, h, w) uint8 tensors."""
+    import ctypes as C
+    library = library or _cabi.lib()
+    masks = []
+    for m in _pred_masks(instances_info):
+        m = m.to(device)
+        if m.dtype != torch.bool and m.dtype != torch.uint8:
+            m = m != 0
+        m = m.contiguous()
+        masks.append(_cabi.check_tensor(m.view(torch.uint8) if m.dtype == torch.bool else m, dtype=torch.uint8, what="pred_masks"))
+    B = len(masks)
+    H, W = masks[0].shape[-2:]
+    if any(tuple(m.shape[-2:]) != (H, W) for m in masks):
+        raise ValueError("instance masks of one batch must share their size")
+    union = torch.empty((B, H, W), dtype=torch.uint8, device=masks[0].device)
+    stream = _cabi.stream_ptr(union)
+    counts = (C.c_int32 * B)(*[int(m.shape[0]) if m.dim() == 3 else 1 for m in masks])
+    library.call("mdn_instance_mask_union", _cabi.ptr_array(masks), counts, union.data_ptr(), B, H * W, stream)
+    outs = [torch.empty((B, int(h), int(w)), dtype=torch.uint8, device=union.device) for h, w in sizes]
+    for k0 in range(0, len(outs), _cabi.MAX_SCALES):
+        chunk = outs[k0:k0 + _cabi.MAX_SCALES]
+        oh = (C.c_int32 * len(chunk))(*[o.shape[1] for o in chunk])
+        ow = (C.c_int32 * len(chunk))(*[o.shape[2] for o in chunk])
+        library.call("mdn_instance_mask_resize", union.data_ptr(), B, H, W, _cabi.ptr_array(chunk), oh, ow, len(chunk), stream)
+    return outs
+
+
+def instance_mask_u8(instances_info, size, device, library=None):
+    """Single-size form of instance_masks_u8."""
+    return instance_masks_u8(instances_info, [tuple(size)], device, library)[0]
 
 
 def detectron2_similarity_loss(mobile_mask, instances_info):

@@ -185,3 +185,18 @@ def test_batch_stager_uploads_what_the_loader_wrote():
     mv = lambda d: {k: v.to(DEV) for k, v in d.items()}
     _, b = loss(mv(inputs), [-1, 1], mv(flows), mv(mobiles), None, [0, 1, 2, 3], mv(cams))
     assert torch.equal(a["loss"], b["loss"])
+
+
+@pytest.mark.gpu
+def test_instance_mask_prep_on_gpu_matches_torchvision():
+    """mdn_instance_mask_union + mdn_instance_mask_resize on the GPU == the reference's
+    Resize(size)(get_batch_instance_mask(.)) (torchvision on the CPU, int64), all four pyramid levels from one pass,
+    bit for bit except at exact 0.5 ties; B=12 KITTI-sized Detectron2-style masks (config 4's input)."""
+    from test_emu_kernels import assert_masks_equal_up_to_exact_ties
+    from mdn_sfm_b200 import loss_utils
+    g = torch.Generator().manual_seed(5)
+    inst = synthetic.make_instances(12, g)
+    sizes = [(192, 640), (96, 320), (48, 160), (24, 80)]
+    got = loss_utils.instance_masks_u8([{"instances": d["instances"].to(DEV)} for d in inst], sizes, DEV)
+    assert all(m.is_cuda for m in got)
+    assert_masks_equal_up_to_exact_ties(got, inst, sizes)
