@@ -50,6 +50,8 @@ def parse():
                     help="synthetic flow field: iid = white noise N(0, 0.05^2) per pixel (stress: every pixel gathers from an "
                          "unrelated place), smooth = network-like field of the same magnitude")
     ap.add_argument("--no-second-flow", action="store_true", help="skip the short extra measurement on the other flow kind")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the short whole-train-step measurement (configs[2])")
+    ap.add_argument("--train-steps", type=int, default=30)
     return ap.parse_args()
 
 
@@ -172,6 +174,65 @@ def run_reference_arm(args):
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ train step (configs[2])
+def measure_train_step(args, dev, world, rank, H, W, scales):
+    """TG-mode full train step, batch `--batch` per GPU: mdn_sfm_b200.train_step.TrainStep with the stand-in
+    nets (the reference's FlowNet / PoseNet / MobileDecoder are cuDNN consumers outside the path; random init either way),
+    frozen flow + pose nets, DDP on the mobile decoder when N > 1.  Eager launches, CUDA events, max over ranks."""
+    import torch.distributed as dist
+    from mdn_sfm_b200 import synthetic
+    from mdn_sfm_b200.train_step import TrainStep
+    B = args.batch
+    opt = synthetic.default_opt(B, H, W, threshold=0.8625, scales=list(scales))   # options_eval.py:55-58 (weighted 95 %)
+    torch.manual_seed(1234)     # identical initial weights on every rank, like DDP's broadcast would leave them
+    ts = TrainStep(opt, device=dev, mode="TG", photometric=True)
+    sets = []
+    for k in range(2):
+        inputs, _, _, _, _ = synthetic.make_batch(B, H, W, scales=scales, seed=4242 + rank + 1000 * k, with_instances=False)
+        sets.append({kk: v.to(dev) for kk, v in inputs.items()})
+    for i in range(5):
+        losses = ts.step(sets[i % 2])
+    torch.cuda.synchronize()
+    # loss path alone inside this step (forward + backward of Loss on the nets' outputs), for the share
+    flows, mobiles, cams, _, _ = ts.process_batch(sets[0])
+    fl = {k: v.detach().requires_grad_(True) for k, v in flows.items()}
+    mo = {k: v.detach().requires_grad_(True) for k, v in mobiles.items()}
+    ca = {k: v.detach().requires_grad_(True) for k, v in cams.items()}
+    ids = list(opt.frame_ids)[1:]
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(3):
+        ts.loss(sets[0], ids, fl, mo, None, list(scales), ca)[1]["loss"].backward()
+    torch.cuda.synchronize()
+    l0.record()
+    for i in range(10):
+        ts.loss(sets[0], ids, fl, mo, None, list(scales), ca)[1]["loss"].backward()
+    l1.record()
+    torch.cuda.synchronize()
+    loss_ms = l0.elapsed_time(l1) / 10
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n = args.train_steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        losses = ts.step(sets[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    logged = ts.log_losses(losses)
+    n_par = sum(p.numel() for p in ts.parameters_to_train)
+    return {"workload": "BASELINE configs[2]: TG-mode full train step (stand-in flow / pose / mobile-decoder CNNs on cuDNN, frozen flow + "
+                        "pose, %s on the mobile decoder, clip_grad_norm_, Adam), batch %d/GPU x %d GPU, eager launches" % (
+                            "DDP (NCCL all-reduce)" if world > 1 else "single process", B, world),
+            "value": world * B * n / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms / n, "steps": n,
+            "loss_path_ms_per_step_eager": loss_ms, "trainable_parameters": n_par, "loss": logged.get("loss")}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -414,6 +475,14 @@ def run_ours(args):
         ms2, _ = timed_steps(dev2, n2, max(3, args.warmup // 4), 0.3)
         second = {"flow": FLOW_DESC[other], "value": B * n2 / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2 / n2, "steps": n2}
 
+    # ---- BASELINE configs[2]: the whole train step (stand-in nets on cuDNN -> TG loss -> backward -> DDP -> clip -> Adam)
+    train = None
+    if not args.no_train_step:
+        try:
+            train = measure_train_step(args, dev, world, rank, H, W, scales)
+        except Exception as e:   # reported, never fatal for the headline line
+            train = {"error": repr(e)}
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         step, threads = cpu_reference_step_fn(args, H, W, scales)
@@ -443,7 +512,7 @@ def run_ours(args):
                 "launches_per_step": "mdn::ref_pack_kernel, mdn::fused_tile_kernel (builds the fundamental matrices from the poses), "
                                      "mdn::finish_kernel (loss scalars, d/dF, pose adjoint), mdn::scale_grads_kernel; "
                                      "(+ torch's ones_like fill for the upstream gradient)",
-                "other_flow": second,
+                "other_flow": second, "train_step": train,
                 "roofline": roofline, "cpu_baseline": cpu_base}
         print(json.dumps(line), flush=True)
     if world > 1:

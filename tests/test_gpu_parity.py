@@ -200,3 +200,21 @@ def test_instance_mask_prep_on_gpu_matches_torchvision():
     got = loss_utils.instance_masks_u8([{"instances": d["instances"].to(DEV)} for d in inst], sizes, DEV)
     assert all(m.is_cuda for m in got)
     assert_masks_equal_up_to_exact_ties(got, inst, sizes)
+
+
+@pytest.mark.gpu
+def test_train_step_harness_runs_on_the_cuda_loss():
+    """nets -> Loss (CUDA, TG mode) -> backward -> clip -> Adam; the loss falls over a few steps on a fixed
+    batch, only the mobile decoder moves, pose / flow nets stay frozen."""
+    from mdn_sfm_b200.train_step import StandInNets, TrainStep
+    opt = synthetic.default_opt(2, 64, 96, threshold=0.8625)
+    torch.manual_seed(0)
+    ts = TrainStep(opt, nets=StandInNets(width=8), device=DEV, mode="TG", photometric=True, lr=1e-3)
+    inputs, _, _, _, _ = synthetic.make_batch(2, 64, 96, seed=1, with_instances=False)
+    inputs = {k: v.to(DEV) for k, v in inputs.items()}
+    frozen = [p.detach().clone() for p in ts.nets.flownet.parameters()]
+    first = float(ts.step(inputs)["loss"].detach())
+    for _ in range(10):
+        last = float(ts.step(inputs)["loss"].detach())
+    assert last == last and last < first
+    assert all(torch.equal(a, b) for a, b in zip(frozen, ts.nets.flownet.parameters()))
