@@ -649,6 +649,27 @@ __global__ void __launch_bounds__(NTHREADS) instance_union_kernel(const __grid_c
   const uint8_t* src = A.masks[b];
   const int n = A.count[b];
   uint8_t* dst = out + (long long)b * hw;
+  const bool wide = (hw & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0;
+  if (wide) {   // four pixels per thread
+    const long long n4 = hw >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      unsigned v = 0;
+      for (int k = 0; k < n; ++k) v |= __ldg(reinterpret_cast<const unsigned*>(src + (long long)k * hw) + i);
+      const unsigned nz = ((v & 0x7f7f7f7fu) + 0x7f7f7f7fu | v) & 0x80808080u;    // 0x80 in every non-zero byte
+      reinterpret_cast<unsigned*>(dst)[i] = nz >> 7;
+    }
+    return;
+  }
+  const bool pair = (hw & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 1) == 0;
+  if (pair) {   // two pixels per thread (375 x 1242 is even, not a multiple of 4)
+    const long long n2 = hw >> 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+      unsigned v = 0;
+      for (int k = 0; k < n; ++k) v |= __ldg(reinterpret_cast<const unsigned short*>(src + (long long)k * hw) + i);
+      reinterpret_cast<unsigned short*>(dst)[i] = (unsigned short)(((v & 0xffu) ? 1u : 0u) | ((v & 0xff00u) ? 0x100u : 0u));
+    }
+    return;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
     unsigned v = 0;
     for (int k = 0; k < n; ++k) v |= __ldg(src + (long long)k * hw + i);   // sum(pred_masks, 0) != 0
@@ -663,8 +684,10 @@ __global__ void __launch_bounds__(NTHREADS) instance_union_kernel(const __grid_c
 constexpr int AA_WFLOATS = 72 * 128;   // shared-memory floats for the per-column x weights: taps x columns per block
 struct ResizeArgs {
   uint8_t* dst[MDN_MAX_SCALES];
+  float* tmp[MDN_MAX_SCALES];          // (B, in_h, out_w[k]) horizontally resized rows (workspace)
   int oh[MDN_MAX_SCALES], ow[MDN_MAX_SCALES];
-  int row_begin[MDN_MAX_SCALES + 1];   // first blockIdx.y of each output size
+  int row_begin[MDN_MAX_SCALES + 1];   // first blockIdx.y of each output size, horizontal pass (row groups)
+  int vrow_begin[MDN_MAX_SCALES + 1];  // ... vertical pass (output rows)
   int n_out, batch, ih, iw;
 };
 
@@ -697,42 +720,66 @@ MDN_DEV AaSpan aa_span(int i, int in_size, float scale) {
   return sp;
 }
 
-// blockDim.x = output columns per block.  use_table: the normalised weights of this block's columns / row are staged in
-// shared memory (wx[tap][column], wy[tap]); otherwise (down-scaling factors beyond the table) they are re-evaluated per tap.
-__global__ void __launch_bounds__(128) instance_resize_kernel(const __grid_constant__ ResizeArgs A, const uint8_t* __restrict__ src,
-                                                              const int use_table) {
+// Two separable passes, as the library does it (the intermediate is rounded to fp32 exactly like ATen's temporary tensor):
+//   H: tmp_k[b][y][ox] = sum_j src[b][y][xmin + j] * wx[j]   for every source row y and every output size k
+//   V: dst_k[b][oy][ox] = round(sum_y tmp_k[b][ymin + y][ox] * wy[y])
+// `output = src[0] * w[0]; output += src[j] * w[j]` (basic_loop_aa_horizontal / _vertical): the library builds contract
+// the update into an FMA (GCC -ffp-contract=fast with FMA targets on the CPU, nvcc -fmad on CUDA).
+constexpr int AA_HROWS = 16;     // source rows per block of the horizontal pass (the block's weights are computed once)
+
+// grid.x = 128-column chunk, grid.y = (k, b, row group); use_table: weights staged in shared memory, else re-evaluated
+__global__ void __launch_bounds__(128) instance_resize_h_kernel(const __grid_constant__ ResizeArgs A, const uint8_t* __restrict__ src,
+                                                                const int use_table) {
   __shared__ float wx[AA_WFLOATS];
-  __shared__ float wy[AA_WFLOATS / 32];
   const int cols = blockDim.x;
   int k = 0;
 #pragma unroll
   for (int q = 1; q < MDN_MAX_SCALES; ++q)
     if (q < A.n_out && (int)blockIdx.y >= A.row_begin[q]) k = q;
-  const int oh = A.oh[k], ow = A.ow[k];
-  const int rem = blockIdx.y - A.row_begin[k];
-  const int b = rem / oh, oy = rem - b * oh;
-  const int ox = blockIdx.x * cols + threadIdx.x;
+  const int ow = A.ow[k];
   if ((int)(blockIdx.x * cols) >= ow) return;
-  const float sh = __fdiv_rn((float)A.ih, (float)oh), sw = __fdiv_rn((float)A.iw, (float)ow);   // area_pixel_compute_scale
-  const AaSpan sy = aa_span(oy, A.ih, sh);
+  const int groups = (A.ih + AA_HROWS - 1) / AA_HROWS;
+  const int rem = blockIdx.y - A.row_begin[k];
+  const int b = rem / groups, y0 = (rem - b * groups) * AA_HROWS;
+  const int ox = blockIdx.x * cols + threadIdx.x;
+  const float sw = __fdiv_rn((float)A.iw, (float)ow);                     // area_pixel_compute_scale
   const AaSpan sx = aa_span(min(ox, ow - 1), A.iw, sw);
-  if (use_table) {
-    for (int j = threadIdx.x; j < sy.xsize; j += cols) wy[j] = sy.weight(j);
-    for (int j = 0; j < sx.xsize; ++j) wx[j * cols + threadIdx.x] = sx.weight(j);
+  if (use_table)
+    for (int j = 0; j < sx.xsize; ++j) wx[j * cols + threadIdx.x] = sx.weight(j);   // thread-private column of the table
+  if (ox >= ow) return;
+  float* tmp = A.tmp[k] + ((long long)b * A.ih + y0) * ow + ox;
+  const uint8_t* row = src + ((long long)b * A.ih + y0) * A.iw + sx.xmin;
+  const int ny = min(AA_HROWS, A.ih - y0);
+  for (int y = 0; y < ny; ++y, row += A.iw, tmp += ow) {
+    float t = __fmul_rn((float)__ldg(row), use_table ? wx[threadIdx.x] : sx.weight(0));
+    for (int j = 1; j < sx.xsize; ++j) t = __fmaf_rn((float)__ldg(row + j), use_table ? wx[j * cols + threadIdx.x] : sx.weight(j), t);
+    *tmp = t;
+  }
+}
+
+// grid.x = 128-column chunk, grid.y = (k, b, oy)
+__global__ void __launch_bounds__(128) instance_resize_v_kernel(const __grid_constant__ ResizeArgs A) {
+  __shared__ float wy[AA_WFLOATS / 32];
+  int k = 0;
+#pragma unroll
+  for (int q = 1; q < MDN_MAX_SCALES; ++q)
+    if (q < A.n_out && (int)blockIdx.y >= A.vrow_begin[q]) k = q;
+  const int oh = A.oh[k], ow = A.ow[k];
+  if ((int)(blockIdx.x * blockDim.x) >= ow) return;
+  const int rem = blockIdx.y - A.vrow_begin[k];
+  const int b = rem / oh, oy = rem - b * oh;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const float sh = __fdiv_rn((float)A.ih, (float)oh);
+  const AaSpan sy = aa_span(oy, A.ih, sh);
+  const bool table = sy.xsize <= AA_WFLOATS / 32;
+  if (table) {
+    for (int j = threadIdx.x; j < sy.xsize; j += blockDim.x) wy[j] = sy.weight(j);
     __syncthreads();
   }
   if (ox >= ow) return;
-  const uint8_t* base = src + ((long long)b * A.ih + sy.xmin) * A.iw + sx.xmin;
-  float out = 0.f;
-  for (int y = 0; y < sy.xsize; ++y) {
-    const uint8_t* row = base + (long long)y * A.iw;
-    // `output = src[0] * w[0]; output += src[j] * w[j]` (basic_loop_aa_horizontal / _vertical): the library builds
-    // contract the update into an FMA (GCC -ffp-contract=fast with FMA targets on the CPU, nvcc -fmad on CUDA)
-    float t = __fmul_rn((float)__ldg(row), use_table ? wx[threadIdx.x] : sx.weight(0));
-    for (int j = 1; j < sx.xsize; ++j) t = __fmaf_rn((float)__ldg(row + j), use_table ? wx[j * cols + threadIdx.x] : sx.weight(j), t);
-    const float wyv = use_table ? wy[y] : sy.weight(y);
-    out = (y == 0) ? __fmul_rn(t, wyv) : __fmaf_rn(t, wyv, out);
-  }
+  const float* col = A.tmp[k] + ((long long)b * A.ih + sy.xmin) * ow + ox;
+  float out = __fmul_rn(col[0], table ? wy[0] : sy.weight(0));
+  for (int y = 1; y < sy.xsize; ++y) out = __fmaf_rn(col[(long long)y * ow], table ? wy[y] : sy.weight(y), out);
   A.dst[k][((long long)b * oh + oy) * ow + ox] = (uint8_t)rintf(out);       // torch.round, then the cast back to integers
 }
 
@@ -1140,30 +1187,52 @@ extern "C" MDN_API int mdn_instance_mask_union(const uint8_t* const* masks, cons
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }
 
+static size_t resize_ws_layout(int batch, int in_h, const int32_t* out_w, int n_out, size_t* offs) {
+  size_t off = 0;
+  for (int k = 0; k < n_out; ++k) {
+    if (offs) offs[k] = off;
+    off += (((size_t)batch * in_h * out_w[k] * sizeof(float)) + 255) & ~size_t(255);
+  }
+  return off;
+}
+
+extern "C" MDN_API size_t mdn_instance_mask_resize_workspace_bytes(int32_t batch, int32_t in_h, const int32_t* out_w, int32_t n_out) {
+  if (batch < 1 || in_h < 1 || !out_w || n_out < 1 || n_out > MDN_MAX_SCALES) { fail(MDN_ERR_BAD_SHAPE, "batch / size / n_out out of range"); return 0; }
+  return resize_ws_layout(batch, in_h, out_w, n_out, nullptr);
+}
+
 extern "C" MDN_API int mdn_instance_mask_resize(const uint8_t* src, int32_t batch, int32_t in_h, int32_t in_w, uint8_t* const* dst,
-                                                const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* stream) {
+                                                const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* workspace,
+                                                size_t workspace_bytes, void* stream) {
   if (!src || !dst || !out_h || !out_w) return fail(MDN_ERR_NULL_POINTER, "src / dst / out_h / out_w is NULL");
   if (batch < 1 || in_h < 1 || in_w < 1 || n_out < 1 || n_out > MDN_MAX_SCALES) return fail(MDN_ERR_BAD_SHAPE, "batch / size / n_out out of range");
   ResizeArgs A;
   memset(&A, 0, sizeof(A));
   A.n_out = n_out; A.batch = batch; A.ih = in_h; A.iw = in_w;
-  int rows = 0, max_w = 0, max_taps = 1;
+  size_t offs[MDN_MAX_SCALES];
+  const size_t need = resize_ws_layout(batch, in_h, out_w, n_out, offs);
+  if (!workspace || workspace_bytes < need) return fail(MDN_ERR_WORKSPACE, "workspace too small");
+  if (!aligned16(workspace)) return fail(MDN_ERR_MISALIGNED, "%s is not 16-byte aligned", "workspace");
+  int hrows = 0, vrows = 0, max_w = 0, max_taps = 1;
+  const int groups = (in_h + AA_HROWS - 1) / AA_HROWS;
   for (int k = 0; k < n_out; ++k) {
     if (!dst[k]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "dst[k]");
     if (out_h[k] < 1 || out_w[k] < 1) return fail(MDN_ERR_BAD_SHAPE, "output size out of range");
     // taps per axis: ceil(support) * 2 + 1 with support = max(scale, 1)
-    const float sh = (float)in_h / (float)out_h[k], sw = (float)in_w / (float)out_w[k];
-    const int th = (int)ceilf(sh >= 1.f ? sh : 1.f) * 2 + 1, tw = (int)ceilf(sw >= 1.f ? sw : 1.f) * 2 + 1;
-    max_taps = std::max(max_taps, std::max(th, tw));
+    const float sw = (float)in_w / (float)out_w[k];
+    max_taps = std::max(max_taps, (int)ceilf(sw >= 1.f ? sw : 1.f) * 2 + 1);
     A.dst[k] = dst[k]; A.oh[k] = out_h[k]; A.ow[k] = out_w[k];
-    A.row_begin[k] = rows;
-    rows += batch * out_h[k];
+    A.tmp[k] = (float*)((char*)workspace + offs[k]);
+    A.row_begin[k] = hrows; A.vrow_begin[k] = vrows;
+    hrows += batch * groups;
+    vrows += batch * out_h[k];
     max_w = std::max(max_w, (int)out_w[k]);
   }
-  A.row_begin[n_out] = rows;
+  A.row_begin[n_out] = hrows; A.vrow_begin[n_out] = vrows;
   const int use_table = max_taps <= AA_WFLOATS / 32;                      // else: weights re-evaluated per tap (factor > 143)
   const int cols = max_taps <= 72 ? 128 : (max_taps <= 144 ? 64 : 32);    // taps x columns fit the weight table
-  MDN_LAUNCH(instance_resize_kernel, dim3((max_w + cols - 1) / cols, rows), dim3(cols), 0, (cudaStream_t)stream, A, src, use_table);
+  MDN_LAUNCH(instance_resize_h_kernel, dim3((max_w + cols - 1) / cols, hrows), dim3(cols), 0, (cudaStream_t)stream, A, src, use_table);
+  MDN_LAUNCH(instance_resize_v_kernel, dim3((max_w + 127) / 128, vrows), dim3(128), 0, (cudaStream_t)stream, A);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }

@@ -32,6 +32,23 @@ def rel_max(a, b):
     return ((a - b).abs().max() / a.abs().max().clamp_min(1e-30)).item()
 
 
+TIE_PX = 3   # per-pixel maps of the DS / DC modes: pixels exempted from a comparison (see rel_max_but)
+
+
+def rel_max_but(a, b, k):
+    """rel_max over (B,C,h,w) maps ignoring the k worst PIXELS.  DS / DC only: the instance mask the reference resizes
+    with torchvision sits on an exact 0.5 tie at about one pixel per million, where its own CPU and CUDA kernels round
+    to different sides (tests/test_emu_kernels.py::test_instance_mask_union_and_resize_match_torchvision pins that every
+    disagreement IS such a tie); a flipped mask pixel changes the gradients of that one pixel by O(1)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    err = (a - b).abs().amax(dim=1).reshape(-1)
+    if k and err.numel() > k:
+        err = err.topk(k + 1).values[-1]
+    else:
+        err = err.max()
+    return (err / a.abs().max().clamp_min(1e-30)).item()
+
+
 def oracle_run(opt, batch, mode, photo, ssim_on, device="cpu", pose_grad=False):
     inputs, flows, mobiles, cams, inst = batch
     mv = lambda d: {k: v.to(device) for k, v in d.items()}
@@ -69,16 +86,17 @@ def product_run(opt, batch, mode, photo, ssim_on, device, pose_grad=False, libra
     return out, losses, f, m, cams
 
 
-def compare(ref, got, photo, check_maps=True, fwd_tol=FWD_TOL, grad_tol=GRAD_TOL):
+def compare(ref, got, photo, check_maps=True, fwd_tol=FWD_TOL, grad_tol=GRAD_TOL, tie_px=0):
+    """tie_px: pixels per gradient map exempted from the comparison -- TIE_PX for the DS / DC modes (rel_max_but), else 0."""
     o_r, l_r, f_r, m_r, c_r = ref
     o_g, l_g, f_g, m_g, c_g = got
     for k in ("loss", "epip", "smooth", "consis") + (("photo",) if photo else ()):
         a, b = float(l_r[k]), float(l_g[k])
         assert abs(a - b) <= fwd_tol * max(abs(a), 1e-12), (k, a, b)
     for k in f_r:
-        assert rel_max(f_r[k].grad, f_g[k].grad) <= grad_tol, ("d/dflow", k, rel_max(f_r[k].grad, f_g[k].grad))
+        assert rel_max_but(f_r[k].grad, f_g[k].grad, tie_px) <= grad_tol, ("d/dflow", k, rel_max(f_r[k].grad, f_g[k].grad))
     for k in m_r:
-        assert rel_max(m_r[k].grad, m_g[k].grad) <= grad_tol, ("d/dmobile", k, rel_max(m_r[k].grad, m_g[k].grad))
+        assert rel_max_but(m_r[k].grad, m_g[k].grad, tie_px) <= grad_tol, ("d/dmobile", k, rel_max(m_r[k].grad, m_g[k].grad))
     for k in c_r:
         if c_r[k].grad is not None:
             assert rel_max(c_r[k].grad, c_g[k].grad) <= grad_tol, ("d/dpose", k, rel_max(c_r[k].grad, c_g[k].grad))
@@ -88,7 +106,7 @@ def compare(ref, got, photo, check_maps=True, fwd_tol=FWD_TOL, grad_tol=GRAD_TOL
             assert set(o_r[name].keys()) == set(o_g[name].keys()), name
             for key in o_r[name]:
                 assert o_r[name][key].shape == o_g[name][key].shape, (name, key)
-                assert rel_max(o_r[name][key], o_g[name][key]) <= fwd_tol, (name, key, rel_max(o_r[name][key], o_g[name][key]))
+                assert rel_max_but(o_r[name][key], o_g[name][key], tie_px) <= fwd_tol, (name, key, rel_max(o_r[name][key], o_g[name][key]))
         if photo:
             for key in o_r["valids"]:
                 assert o_g["valids"][key].dtype == torch.bool

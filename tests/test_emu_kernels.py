@@ -244,7 +244,7 @@ def assert_masks_equal_up_to_exact_ties(got, inst, sizes):
 
 
 @pytest.mark.parametrize("src_hw,sizes", [((375, 1242), [(192, 640), (96, 320), (48, 160), (24, 80)]),
-                                          ((61, 97), [(64, 128), (61, 97), (17, 200)]), ((375, 1242), [(8, 12), (3, 640)])])
+                                          ((61, 97), [(64, 128), (61, 97), (17, 200)]), ((375, 1242), [(8, 12), (3, 640)]), ((64, 96), [(32, 48), (64, 96)])])
 def test_instance_mask_union_and_resize_match_torchvision(src_hw, sizes):
     """mdn_instance_mask_union + mdn_instance_mask_resize == Resize(size)(get_batch_instance_mask(.)) of the reference
     (loss_utils.py:73-75,102-124,135-137; torchvision bilinear + antialias on int64, rounded), bit for bit except at
