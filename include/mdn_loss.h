@@ -230,15 +230,17 @@ MDN_API int mdn_ssim_bwd(const float* x, const float* y, const float* g_out, flo
  * sizes in one launch -- torchvision's bilinear + antialias resize of the integer mask (ATen _upsample_bilinear2d_aa:
  * separable triangle filter of support in/out, fp32, horizontal then vertical) followed by round-half-to-even.
  * src (B, in_h, in_w) uint8 {0,1}; dst is a HOST array of n_out device pointers, dst[k] -> (B, out_h[k], out_w[k]) uint8
- * -- the `inst` tensors MdnScale wants.  Two launches (horizontal pass into `workspace`, vertical pass).
+ * -- the `inst` tensors MdnScale wants.  Three launches (weight tables, horizontal pass into `workspace`, vertical pass).
  */
 MDN_API int mdn_instance_mask_union(const uint8_t* const* masks, const int32_t* counts, uint8_t* out, int32_t batch,
                                     int64_t hw, void* stream);
 MDN_API int mdn_instance_mask_resize(const uint8_t* src, int32_t batch, int32_t in_h, int32_t in_w, uint8_t* const* dst,
                                      const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* workspace,
                                      size_t workspace_bytes, void* stream);
-/* workspace of the call above: the horizontally resized fp32 rows, batch * in_h * sum(out_w) floats (256-byte padded) */
-MDN_API size_t mdn_instance_mask_resize_workspace_bytes(int32_t batch, int32_t in_h, const int32_t* out_w, int32_t n_out);
+/* workspace of the call above: the horizontally resized fp32 rows, batch * in_h * sum(out_w) floats, plus the per-axis
+ * weight tables (256-byte padded) */
+MDN_API size_t mdn_instance_mask_resize_workspace_bytes(int32_t batch, int32_t in_h, int32_t in_w, const int32_t* out_h,
+                                                        const int32_t* out_w, int32_t n_out);
 
 /* binary_image (utils.py:100-103): out = x >= threshold ? 1 : 0 */
 MDN_API int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream);

@@ -81,7 +81,7 @@ class Library:
             "mdn_binary_image": (C.c_int, [_P, _P, i64, f32, _P]),
             "mdn_instance_mask_union": (C.c_int, [C.POINTER(_P), C.POINTER(i32), _P, i32, i64, _P]),
             "mdn_instance_mask_resize": (C.c_int, [_P, i32, i32, i32, C.POINTER(_P), C.POINTER(i32), C.POINTER(i32), i32, _P, sz, _P]),
-            "mdn_instance_mask_resize_workspace_bytes": (sz, [i32, i32, C.POINTER(i32), i32]),
+            "mdn_instance_mask_resize_workspace_bytes": (sz, [i32, i32, i32, C.POINTER(i32), C.POINTER(i32), i32]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(d, name)

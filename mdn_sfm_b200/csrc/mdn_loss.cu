@@ -681,10 +681,14 @@ __global__ void __launch_bounds__(NTHREADS) instance_union_kernel(const __grid_c
 // `Resize(size)(int64 mask)` does (loss_utils.py:73-75, 135-137): ATen's separable triangle filter
 // (_upsample_bilinear2d_aa: _compute_weights_span / _compute_weights / interpolate_aa_single_dim) in fp32 with the same
 // operation order -- weights w_j = f((j + xmin - center + 0.5) / scale) / sum, horizontal pass, then vertical.
-constexpr int AA_WFLOATS = 72 * 128;   // shared-memory floats for the per-column x weights: taps x columns per block
 struct ResizeArgs {
   uint8_t* dst[MDN_MAX_SCALES];
   float* tmp[MDN_MAX_SCALES];          // (B, in_h, out_w[k]) horizontally resized rows (workspace)
+  float* wxt[MDN_MAX_SCALES];          // [taps_x][out_w[k]] normalised x weights (workspace)
+  float* wyt[MDN_MAX_SCALES];          // [out_h[k]][ty[k]] normalised y weights (workspace)
+  int2* xspan[MDN_MAX_SCALES];         // [out_w[k]] (first source column, taps)
+  int2* yspan[MDN_MAX_SCALES];         // [out_h[k]]
+  int ty[MDN_MAX_SCALES];              // row stride of wyt = taps per output row (upper bound)
   int oh[MDN_MAX_SCALES], ow[MDN_MAX_SCALES];
   int row_begin[MDN_MAX_SCALES + 1];   // first blockIdx.y of each output size, horizontal pass (row groups)
   int vrow_begin[MDN_MAX_SCALES + 1];  // ... vertical pass (output rows)
@@ -720,67 +724,91 @@ MDN_DEV AaSpan aa_span(int i, int in_size, float scale) {
   return sp;
 }
 
-// Two separable passes, as the library does it (the intermediate is rounded to fp32 exactly like ATen's temporary tensor):
+// Three launches: the per-axis spans / normalised weights of every output index (a few thousand floats, the only place
+// that needs the double-precision steps of aa_span), then two separable passes as the library does them (the
+// intermediate is rounded to fp32 exactly like ATen's temporary tensor):
 //   H: tmp_k[b][y][ox] = sum_j src[b][y][xmin + j] * wx[j]   for every source row y and every output size k
 //   V: dst_k[b][oy][ox] = round(sum_y tmp_k[b][ymin + y][ox] * wy[y])
 // `output = src[0] * w[0]; output += src[j] * w[j]` (basic_loop_aa_horizontal / _vertical): the library builds contract
 // the update into an FMA (GCC -ffp-contract=fast with FMA targets on the CPU, nvcc -fmad on CUDA).
-constexpr int AA_HROWS = 16;     // source rows per block of the horizontal pass (the block's weights are computed once)
+constexpr int AA_HROWS = 8;      // source rows per block of the horizontal pass
+constexpr int AA_VROWS = 4;      // output rows per block of the vertical pass
 
-// grid.x = 128-column chunk, grid.y = (k, b, row group); use_table: weights staged in shared memory, else re-evaluated
-__global__ void __launch_bounds__(128) instance_resize_h_kernel(const __grid_constant__ ResizeArgs A, const uint8_t* __restrict__ src,
-                                                                const int use_table) {
-  __shared__ float wx[AA_WFLOATS];
-  const int cols = blockDim.x;
+// one thread per (output size k, axis, output index): span -> A.xspan / A.yspan, weights -> A.wxt[k][tap][ox] / A.wyt[k][oy][tap]
+__global__ void __launch_bounds__(NTHREADS) instance_resize_weights_kernel(const __grid_constant__ ResizeArgs A) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k = 0; k < A.n_out; ++k) {
+    if (i < A.ow[k]) {
+      const AaSpan sp = aa_span(i, A.iw, __fdiv_rn((float)A.iw, (float)A.ow[k]));   // area_pixel_compute_scale
+      A.xspan[k][i] = make_int2(sp.xmin, sp.xsize);
+      for (int j = 0; j < sp.xsize; ++j) A.wxt[k][(long long)j * A.ow[k] + i] = sp.weight(j);
+      return;
+    }
+    i -= A.ow[k];
+    if (i < A.oh[k]) {
+      const AaSpan sp = aa_span(i, A.ih, __fdiv_rn((float)A.ih, (float)A.oh[k]));
+      A.yspan[k][i] = make_int2(sp.xmin, sp.xsize);
+      for (int j = 0; j < sp.xsize; ++j) A.wyt[k][(long long)i * A.ty[k] + j] = sp.weight(j);
+      return;
+    }
+    i -= A.oh[k];
+  }
+}
+
+// grid.x = 128-column chunk, grid.y = (k, b, group of AA_HROWS source rows)
+__global__ void __launch_bounds__(128) instance_resize_h_kernel(const __grid_constant__ ResizeArgs A, const uint8_t* __restrict__ src) {
   int k = 0;
 #pragma unroll
   for (int q = 1; q < MDN_MAX_SCALES; ++q)
     if (q < A.n_out && (int)blockIdx.y >= A.row_begin[q]) k = q;
   const int ow = A.ow[k];
-  if ((int)(blockIdx.x * cols) >= ow) return;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= ow) return;
   const int groups = (A.ih + AA_HROWS - 1) / AA_HROWS;
   const int rem = blockIdx.y - A.row_begin[k];
   const int b = rem / groups, y0 = (rem - b * groups) * AA_HROWS;
-  const int ox = blockIdx.x * cols + threadIdx.x;
-  const float sw = __fdiv_rn((float)A.iw, (float)ow);                     // area_pixel_compute_scale
-  const AaSpan sx = aa_span(min(ox, ow - 1), A.iw, sw);
-  if (use_table)
-    for (int j = 0; j < sx.xsize; ++j) wx[j * cols + threadIdx.x] = sx.weight(j);   // thread-private column of the table
-  if (ox >= ow) return;
+  const int2 sp = __ldg(A.xspan[k] + ox);
+  const float* wcol = A.wxt[k] + ox;
+  const uint8_t* row = src + ((long long)b * A.ih + y0) * A.iw + sp.x;
   float* tmp = A.tmp[k] + ((long long)b * A.ih + y0) * ow + ox;
-  const uint8_t* row = src + ((long long)b * A.ih + y0) * A.iw + sx.xmin;
   const int ny = min(AA_HROWS, A.ih - y0);
-  for (int y = 0; y < ny; ++y, row += A.iw, tmp += ow) {
-    float t = __fmul_rn((float)__ldg(row), use_table ? wx[threadIdx.x] : sx.weight(0));
-    for (int j = 1; j < sx.xsize; ++j) t = __fmaf_rn((float)__ldg(row + j), use_table ? wx[j * cols + threadIdx.x] : sx.weight(j), t);
-    *tmp = t;
+  float t[AA_HROWS];
+#pragma unroll
+  for (int y = 0; y < AA_HROWS; ++y) t[y] = 0.f;
+  for (int j = 0; j < sp.y; ++j) {            // the AA_HROWS rows are independent FMA chains sharing the weight
+    const float wj = __ldg(wcol + (long long)j * ow);
+#pragma unroll
+    for (int y = 0; y < AA_HROWS; ++y)
+      if (y < ny) {
+        const float v = (float)__ldg(row + (long long)y * A.iw + j);
+        t[y] = (j == 0) ? __fmul_rn(v, wj) : __fmaf_rn(v, wj, t[y]);
+      }
   }
+#pragma unroll
+  for (int y = 0; y < AA_HROWS; ++y)
+    if (y < ny) tmp[(long long)y * ow] = t[y];
 }
 
-// grid.x = 128-column chunk, grid.y = (k, b, oy)
+// grid.x = 128-column chunk, grid.y = (k, b, group of AA_VROWS output rows)
 __global__ void __launch_bounds__(128) instance_resize_v_kernel(const __grid_constant__ ResizeArgs A) {
-  __shared__ float wy[AA_WFLOATS / 32];
   int k = 0;
 #pragma unroll
   for (int q = 1; q < MDN_MAX_SCALES; ++q)
     if (q < A.n_out && (int)blockIdx.y >= A.vrow_begin[q]) k = q;
   const int oh = A.oh[k], ow = A.ow[k];
-  if ((int)(blockIdx.x * blockDim.x) >= ow) return;
-  const int rem = blockIdx.y - A.vrow_begin[k];
-  const int b = rem / oh, oy = rem - b * oh;
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-  const float sh = __fdiv_rn((float)A.ih, (float)oh);
-  const AaSpan sy = aa_span(oy, A.ih, sh);
-  const bool table = sy.xsize <= AA_WFLOATS / 32;
-  if (table) {
-    for (int j = threadIdx.x; j < sy.xsize; j += blockDim.x) wy[j] = sy.weight(j);
-    __syncthreads();
-  }
   if (ox >= ow) return;
-  const float* col = A.tmp[k] + ((long long)b * A.ih + sy.xmin) * ow + ox;
-  float out = __fmul_rn(col[0], table ? wy[0] : sy.weight(0));
-  for (int y = 1; y < sy.xsize; ++y) out = __fmaf_rn(col[(long long)y * ow], table ? wy[y] : sy.weight(y), out);
-  A.dst[k][((long long)b * oh + oy) * ow + ox] = (uint8_t)rintf(out);       // torch.round, then the cast back to integers
+  const int groups = (oh + AA_VROWS - 1) / AA_VROWS;
+  const int rem = blockIdx.y - A.vrow_begin[k];
+  const int b = rem / groups, oy0 = (rem - b * groups) * AA_VROWS;
+  for (int oy = oy0; oy < min(oy0 + AA_VROWS, oh); ++oy) {
+    const int2 sp = __ldg(A.yspan[k] + oy);
+    const float* wrow = A.wyt[k] + (long long)oy * A.ty[k];
+    const float* col = A.tmp[k] + ((long long)b * A.ih + sp.x) * ow + ox;
+    float out = __fmul_rn(col[0], __ldg(wrow));
+    for (int y = 1; y < sp.y; ++y) out = __fmaf_rn(col[(long long)y * ow], __ldg(wrow + y), out);
+    A.dst[k][((long long)b * oh + oy) * ow + ox] = (uint8_t)rintf(out);     // torch.round, then the cast back to integers
+  }
 }
 
 __global__ void __launch_bounds__(NTHREADS) binary_image_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, float thr) {
@@ -1187,52 +1215,74 @@ extern "C" MDN_API int mdn_instance_mask_union(const uint8_t* const* masks, cons
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }
 
-static size_t resize_ws_layout(int batch, int in_h, const int32_t* out_w, int n_out, size_t* offs) {
-  size_t off = 0;
-  for (int k = 0; k < n_out; ++k) {
-    if (offs) offs[k] = off;
-    off += (((size_t)batch * in_h * out_w[k] * sizeof(float)) + 255) & ~size_t(255);
-  }
-  return off;
+static inline int aa_taps(int in_size, int out_size) {   // ceil(support) * 2 + 1 with support = max(in / out, 1)
+  const float sc = (float)in_size / (float)out_size;
+  return (int)ceilf(sc >= 1.f ? sc : 1.f) * 2 + 1;
 }
 
-extern "C" MDN_API size_t mdn_instance_mask_resize_workspace_bytes(int32_t batch, int32_t in_h, const int32_t* out_w, int32_t n_out) {
-  if (batch < 1 || in_h < 1 || !out_w || n_out < 1 || n_out > MDN_MAX_SCALES) { fail(MDN_ERR_BAD_SHAPE, "batch / size / n_out out of range"); return 0; }
-  return resize_ws_layout(batch, in_h, out_w, n_out, nullptr);
+struct ResizeWs { size_t tmp[MDN_MAX_SCALES], wxt[MDN_MAX_SCALES], wyt[MDN_MAX_SCALES], xspan[MDN_MAX_SCALES], yspan[MDN_MAX_SCALES], total; };
+
+static ResizeWs resize_ws_layout(int batch, int in_h, int in_w, const int32_t* out_h, const int32_t* out_w, int n_out) {
+  ResizeWs L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+  for (int k = 0; k < n_out; ++k) {
+    L.tmp[k] = take((size_t)batch * in_h * out_w[k] * sizeof(float));
+    L.wxt[k] = take((size_t)aa_taps(in_w, out_w[k]) * out_w[k] * sizeof(float));
+    L.wyt[k] = take((size_t)aa_taps(in_h, out_h[k]) * out_h[k] * sizeof(float));
+    L.xspan[k] = take((size_t)out_w[k] * sizeof(int2));
+    L.yspan[k] = take((size_t)out_h[k] * sizeof(int2));
+  }
+  L.total = off;
+  return L;
+}
+
+static int check_resize_sizes(int32_t batch, int32_t in_h, int32_t in_w, const int32_t* out_h, const int32_t* out_w, int32_t n_out) {
+  if (!out_h || !out_w) return fail(MDN_ERR_NULL_POINTER, "out_h / out_w is NULL");
+  if (batch < 1 || in_h < 1 || in_w < 1 || n_out < 1 || n_out > MDN_MAX_SCALES) return fail(MDN_ERR_BAD_SHAPE, "batch / size / n_out out of range");
+  for (int k = 0; k < n_out; ++k)
+    if (out_h[k] < 1 || out_w[k] < 1) return fail(MDN_ERR_BAD_SHAPE, "output size out of range");
+  return MDN_OK;
+}
+
+extern "C" MDN_API size_t mdn_instance_mask_resize_workspace_bytes(int32_t batch, int32_t in_h, int32_t in_w, const int32_t* out_h,
+                                                                   const int32_t* out_w, int32_t n_out) {
+  if (check_resize_sizes(batch, in_h, in_w, out_h, out_w, n_out) != MDN_OK) return 0;
+  return resize_ws_layout(batch, in_h, in_w, out_h, out_w, n_out).total;
 }
 
 extern "C" MDN_API int mdn_instance_mask_resize(const uint8_t* src, int32_t batch, int32_t in_h, int32_t in_w, uint8_t* const* dst,
                                                 const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* workspace,
                                                 size_t workspace_bytes, void* stream) {
-  if (!src || !dst || !out_h || !out_w) return fail(MDN_ERR_NULL_POINTER, "src / dst / out_h / out_w is NULL");
-  if (batch < 1 || in_h < 1 || in_w < 1 || n_out < 1 || n_out > MDN_MAX_SCALES) return fail(MDN_ERR_BAD_SHAPE, "batch / size / n_out out of range");
+  if (!src || !dst) return fail(MDN_ERR_NULL_POINTER, "src / dst is NULL");
+  int rc = check_resize_sizes(batch, in_h, in_w, out_h, out_w, n_out);
+  if (rc != MDN_OK) return rc;
   ResizeArgs A;
   memset(&A, 0, sizeof(A));
   A.n_out = n_out; A.batch = batch; A.ih = in_h; A.iw = in_w;
-  size_t offs[MDN_MAX_SCALES];
-  const size_t need = resize_ws_layout(batch, in_h, out_w, n_out, offs);
-  if (!workspace || workspace_bytes < need) return fail(MDN_ERR_WORKSPACE, "workspace too small");
+  const ResizeWs L = resize_ws_layout(batch, in_h, in_w, out_h, out_w, n_out);
+  if (!workspace || workspace_bytes < L.total) return fail(MDN_ERR_WORKSPACE, "workspace too small");
   if (!aligned16(workspace)) return fail(MDN_ERR_MISALIGNED, "%s is not 16-byte aligned", "workspace");
-  int hrows = 0, vrows = 0, max_w = 0, max_taps = 1;
-  const int groups = (in_h + AA_HROWS - 1) / AA_HROWS;
+  char* ws = (char*)workspace;
+  int hrows = 0, vrows = 0, max_w = 0, n_idx = 0;
+  const int hgroups = (in_h + AA_HROWS - 1) / AA_HROWS;
   for (int k = 0; k < n_out; ++k) {
     if (!dst[k]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "dst[k]");
-    if (out_h[k] < 1 || out_w[k] < 1) return fail(MDN_ERR_BAD_SHAPE, "output size out of range");
-    // taps per axis: ceil(support) * 2 + 1 with support = max(scale, 1)
-    const float sw = (float)in_w / (float)out_w[k];
-    max_taps = std::max(max_taps, (int)ceilf(sw >= 1.f ? sw : 1.f) * 2 + 1);
     A.dst[k] = dst[k]; A.oh[k] = out_h[k]; A.ow[k] = out_w[k];
-    A.tmp[k] = (float*)((char*)workspace + offs[k]);
+    A.tmp[k] = (float*)(ws + L.tmp[k]); A.wxt[k] = (float*)(ws + L.wxt[k]); A.wyt[k] = (float*)(ws + L.wyt[k]);
+    A.xspan[k] = (int2*)(ws + L.xspan[k]); A.yspan[k] = (int2*)(ws + L.yspan[k]);
+    A.ty[k] = aa_taps(in_h, out_h[k]);
     A.row_begin[k] = hrows; A.vrow_begin[k] = vrows;
-    hrows += batch * groups;
-    vrows += batch * out_h[k];
+    hrows += batch * hgroups;
+    vrows += batch * ((out_h[k] + AA_VROWS - 1) / AA_VROWS);
     max_w = std::max(max_w, (int)out_w[k]);
+    n_idx += out_w[k] + out_h[k];
   }
   A.row_begin[n_out] = hrows; A.vrow_begin[n_out] = vrows;
-  const int use_table = max_taps <= AA_WFLOATS / 32;                      // else: weights re-evaluated per tap (factor > 143)
-  const int cols = max_taps <= 72 ? 128 : (max_taps <= 144 ? 64 : 32);    // taps x columns fit the weight table
-  MDN_LAUNCH(instance_resize_h_kernel, dim3((max_w + cols - 1) / cols, hrows), dim3(cols), 0, (cudaStream_t)stream, A, src, use_table);
-  MDN_LAUNCH(instance_resize_v_kernel, dim3((max_w + 127) / 128, vrows), dim3(128), 0, (cudaStream_t)stream, A);
+  cudaStream_t st = (cudaStream_t)stream;
+  MDN_LAUNCH(instance_resize_weights_kernel, dim3((n_idx + NTHREADS - 1) / NTHREADS), dim3(NTHREADS), 0, st, A);
+  MDN_LAUNCH(instance_resize_h_kernel, dim3((max_w + 127) / 128, hrows), dim3(128), 0, st, A, src);
+  MDN_LAUNCH(instance_resize_v_kernel, dim3((max_w + 127) / 128, vrows), dim3(128), 0, st, A);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }

@@ -87,7 +87,7 @@ def instance_masks_u8(instances_info, sizes, device, library=None):
         chunk = outs[k0:k0 + _cabi.MAX_SCALES]
         oh = (C.c_int32 * len(chunk))(*[o.shape[1] for o in chunk])
         ow = (C.c_int32 * len(chunk))(*[o.shape[2] for o in chunk])
-        nbytes = library.cdll.mdn_instance_mask_resize_workspace_bytes(B, H, ow, len(chunk))
+        nbytes = library.cdll.mdn_instance_mask_resize_workspace_bytes(B, H, W, oh, ow, len(chunk))
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=union.device)
         library.call("mdn_instance_mask_resize", union.data_ptr(), B, H, W, _cabi.ptr_array(chunk), oh, ow, len(chunk),
                      ws.data_ptr(), nbytes, stream)

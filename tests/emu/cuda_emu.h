@@ -38,6 +38,8 @@ struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+struct int2 { int x, y; };
+static inline int2 make_int2(int a, int b) { return int2{a, b}; }
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;
