@@ -21,6 +21,7 @@ namespace mdn {
 
 // ----------------------------------------------------------------------------------------------- geometry
 constexpr int NTHREADS = 256;                         // block size of the small standalone kernels
+constexpr int PACK_PX = 4;                            // pixels per thread of ref_pack_kernel
 // fused kernel: TW x TH tile, one thread per 2-column x 4-row patch of pixels
 constexpr int TW = 64, TH = 16;
 #ifndef MDN_PATCH_ROWS
@@ -77,6 +78,7 @@ struct KParams {
   const float* inv_K[MDN_MAX_SCALES];
   float* fmat_ws;                    // [n_scales][n_pairs][batch][9] F as the fused kernel used it (written when cam is given)
   unsigned* ticket;                  // completion ticket of finish_kernel (zeroed by the fused kernel)
+  int pack_begin[MDN_MAX_SCALES + 1], pack_blocks[MDN_MAX_SCALES];   // block ranges of ref_pack_kernel
   KScale sc[MDN_MAX_SCALES];
 };
 
@@ -238,27 +240,31 @@ __global__ void __launch_bounds__(NTHREADS) sn_max_kernel(const KParams P, unsig
 // 128-byte reads and one 512-byte write per warp.  grid.y = (scale * n_pairs + pair) * batch + b.
 __global__ void __launch_bounds__(NTHREADS) ref_pack_kernel(const __grid_constant__ KParams P) {
   pdl_wait();
-  const int job = blockIdx.y;
-  const int b = job % P.batch, sp = job / P.batch;
-  const int pair = sp % P.n_pairs, s = sp / P.n_pairs;
+  // flat grid: scale s owns blocks [pack_begin[s], pack_begin[s + 1]), pack_blocks[s] per (pair, sample) image
+  int s = 0;
+#pragma unroll
+  for (int k = 1; k < MDN_MAX_SCALES; ++k)
+    if (k < P.n_scales && (int)blockIdx.x >= P.pack_begin[k]) s = k;
   const KScale& S = P.sc[s];
+  const int rem = blockIdx.x - P.pack_begin[s];
+  const int job = rem / P.pack_blocks[s], blk = rem - job * P.pack_blocks[s];
+  const int pair = job / P.batch, b = job - pair * P.batch;
   const int hw = S.h * S.w;
   const float* src = S.ref[pair] + (size_t)b * 3 * hw;
   float4* dst = S.refp[pair] + (size_t)b * hw;
-  if ((hw & 3) == 0) {
-    // four pixels per thread: three 16-byte loads, four 16-byte stores
-    const float4* s0 = reinterpret_cast<const float4*>(src);
-    const float4* s1 = reinterpret_cast<const float4*>(src + hw);
-    const float4* s2 = reinterpret_cast<const float4*>(src + 2 * hw);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw / 4; i += gridDim.x * blockDim.x) {
-      const float4 r = __ldg(s0 + i), g = __ldg(s1 + i), bl = __ldg(s2 + i);
-      float4* d4 = dst + 4 * i;
-      d4[0] = make_float4(r.x, g.x, bl.x, 0.f); d4[1] = make_float4(r.y, g.y, bl.y, 0.f);
-      d4[2] = make_float4(r.z, g.z, bl.z, 0.f); d4[3] = make_float4(r.w, g.w, bl.w, 0.f);
-    }
-  } else {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x)
-      dst[i] = make_float4(__ldg(src + i), __ldg(src + hw + i), __ldg(src + 2 * hw + i), 0.f);
+  // PACK_PX pixels per thread, one pixel per thread and instruction: every warp load is one 128-byte line of a plane,
+  // every warp store 512 contiguous bytes
+  const int i0 = blk * (NTHREADS * PACK_PX) + threadIdx.x;
+  float r[PACK_PX], g[PACK_PX], bl[PACK_PX];
+#pragma unroll
+  for (int q = 0; q < PACK_PX; ++q) {
+    const int i = i0 + q * NTHREADS;
+    if (i < hw) { r[q] = __ldg(src + i); g[q] = __ldg(src + hw + i); bl[q] = __ldg(src + 2 * hw + i); }
+  }
+#pragma unroll
+  for (int q = 0; q < PACK_PX; ++q) {
+    const int i = i0 + q * NTHREADS;
+    if (i < hw) dst[i] = make_float4(r[q], g[q], bl[q], 0.f);
   }
 }
 
@@ -282,13 +288,17 @@ struct FParams {
 constexpr int FIN_ROWS = 24;  // FIN_ROWS * NSLOT = 960 threads: at most ~5 tiles per thread at the headline shape
 
 __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_constant__ FParams Q) {
+  // One block per SAMPLE: it folds the sample's tiles of every scale, so it also holds every d/dF of the sample and runs
+  // the pose adjoint itself; only the final fold into the loss scalars waits for the last block.
   const KParams& P = Q.K;
   __shared__ float part[FIN_ROWS][NSLOT];
   __shared__ bool is_last;
   pdl_wait();
-  const int s = blockIdx.x / P.batch, b = blockIdx.x % P.batch;
-  const KScale& S = P.sc[s];
+  const int b = blockIdx.x;
   const int slot = threadIdx.x % NSLOT, row = threadIdx.x / NSLOT;
+  const bool grads = (P.flags & MDN_OPT_GRADS) != 0;
+  for (int s = 0; s < P.n_scales; ++s) {
+  const KScale& S = P.sc[s];
   const int tiles = S.tiles_x * S.tiles_y;
   const float* src = P.partials + ((long long)S.tile_begin + (long long)b * tiles) * NSLOT;
   float t = 0.f;
@@ -303,7 +313,6 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
     Q.sample_sums[((long long)s * P.batch + b) * NSLOT + slot] = tot;
   }
   __syncthreads();
-  const bool grads = (P.flags & MDN_OPT_GRADS) != 0;
   if (grads && (P.flags & MDN_TERM_EPIPOLAR) && threadIdx.x < (unsigned)P.n_pairs) {
     const int pair = threadIdx.x;
     float gF[9];
@@ -342,6 +351,16 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
     if (Q.gf_ws)
       for (int k = 0; k < 9; ++k) Q.gf_ws[((size_t)(s * P.n_pairs + pair) * P.batch + b) * 9 + k] = gF[k];
   }
+  __syncthreads();   // part[] is rewritten by the next scale
+  }
+  // pose adjoint of this sample (what mdn_fundamental_bwd computes) from the d/dF written above by this block
+  if (Q.gf_ws && threadIdx.x < (unsigned)P.n_pairs && Q.g_cam[threadIdx.x]) {
+    FundArgs A;
+    for (int k = 0; k < MDN_MAX_SCALES; ++k) A.inv_K[k] = P.inv_K[k];
+    for (int k = 0; k < MDN_MAX_PAIRS; ++k) { A.cam[k] = P.cam[k]; A.g_cam[k] = Q.g_cam[k]; }
+    A.n_scales = P.n_scales; A.n_pairs = P.n_pairs; A.batch = P.batch;
+    fundamental_bwd_one(A, Q.gf_ws, threadIdx.x, b);
+  }
   // last block to arrive folds the per-sample sums into the loss scalars, in a fixed order
   __threadfence();
   __syncthreads();
@@ -352,17 +371,6 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // pose adjoint (what mdn_fundamental_bwd computes) from the d/dF every block has published
-  if (Q.gf_ws && threadIdx.x < (unsigned)(P.n_pairs * P.batch)) {
-    const int p = threadIdx.x / P.batch, bb = threadIdx.x - p * P.batch;
-    if (Q.g_cam[p]) {
-      FundArgs A;
-      for (int k = 0; k < MDN_MAX_SCALES; ++k) A.inv_K[k] = P.inv_K[k];
-      for (int k = 0; k < MDN_MAX_PAIRS; ++k) { A.cam[k] = P.cam[k]; A.g_cam[k] = Q.g_cam[k]; }
-      A.n_scales = P.n_scales; A.n_pairs = P.n_pairs; A.batch = P.batch;
-      fundamental_bwd_one(A, Q.gf_ws, p, bb);
-    }
-  }
   __shared__ double tots[MDN_MAX_SCALES][NSLOT];
   if (threadIdx.x < (unsigned)(P.n_scales * NSLOT)) {
     const int ss = threadIdx.x / NSLOT, k = threadIdx.x % NSLOT;
@@ -1005,9 +1013,14 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
   const bool photo = (d->flags & MDN_TERM_PHOTO) != 0;
   if (ev) cudaEventRecord(ev[0], stream);
   if (photo) {
-    const int hw0 = K.sc[0].h * K.sc[0].w;
-    const dim3 pgrid((unsigned)std::min((hw0 / 4 + NTHREADS - 1) / NTHREADS, 1024), (unsigned)(d->n_scales * d->n_pairs * d->batch));
-    MDN_LAUNCH_PDL(1, ref_pack_kernel, pgrid, dim3(NTHREADS), 0, stream, K);
+    int nblk = 0;
+    for (int s = 0; s < d->n_scales; ++s) {
+      K.pack_begin[s] = nblk;
+      K.pack_blocks[s] = (K.sc[s].h * K.sc[s].w + NTHREADS * PACK_PX - 1) / (NTHREADS * PACK_PX);
+      nblk += K.pack_blocks[s] * d->n_pairs * d->batch;
+    }
+    K.pack_begin[d->n_scales] = nblk;
+    MDN_LAUNCH_PDL(1, ref_pack_kernel, dim3(nblk), dim3(NTHREADS), 0, stream, K);
   }
   const size_t smem = fused_smem_floats(photo) * sizeof(float);
   static_assert(fused_smem_floats(true) * sizeof(float) <= 113 * 1024, "two CTAs per SM");
@@ -1034,7 +1047,7 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
   else if (maps) { auto kfn = fused_tile_kernel<false, true>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
   else { auto kfn = fused_tile_kernel<false, false>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
   if (ev) cudaEventRecord(ev[2], stream);
-  MDN_LAUNCH_PDL(4, finish_kernel, dim3(d->n_scales * d->batch), dim3(FIN_ROWS * NSLOT), 0, stream, Q);
+  MDN_LAUNCH_PDL(4, finish_kernel, dim3(d->batch), dim3(FIN_ROWS * NSLOT), 0, stream, Q);
   if (ev) cudaEventRecord(ev[3], stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
