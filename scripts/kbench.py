@@ -36,9 +36,18 @@ def main():
         _cabi._lib = _cabi.Library(os.path.abspath(path))
         loss = Loss(opt, no_ssim=False, mode=mode, photometric=True)
 
+        bwd = "--bwd" in sys.argv
+        reps = int(arg("--reps", "1"))    # rotations of the 4 input sets per graph
+
         def step(i):
             inputs, flows, mobiles, cams, inst = sets[i % 4]
+            if bwd:
+                for d in (flows, mobiles):
+                    for v in d.values():
+                        v.grad = None
             _, losses = loss(inputs, [-1, 1], flows, mobiles, inst, list(scales), cams)
+            if bwd:
+                losses["loss"].backward()
             return losses["loss"]
 
         for i in range(20):
@@ -48,17 +57,17 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for i in range(4):
+            for i in range(4 * reps):
                 step(i)
         for _ in range(3):
             g.replay()
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(iters // 4):
+        for _ in range(iters // (4 * reps)):
             g.replay()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / (iters // 4 * 4)
+        ms = e0.elapsed_time(e1) / (iters // (4 * reps) * 4 * reps)
         print(f"{path} [{flow_kind}]: {ms * 1e3:8.1f} us / forward+grads step   loss {float(step(0)):.6f}", flush=True)
 
 
