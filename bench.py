@@ -427,10 +427,15 @@ def run_ours(args):
 
     # All four dicts of a batch live in ONE pinned slab (the loader writes there); per step one cudaMemcpyAsync on a
     # copy stream brings them to the device, double-buffered so the copy of step i+1 overlaps the kernels of step i.
+    # Only the FULL-RESOLUTION frames are uploaded: the lower pyramid levels are produced on the device
+    # (mdn_sfm_b200.pyramid) instead of crossing PCIe like the reference's dataset-side resizes do.
+    from mdn_sfm_b200 import pyramid
     from mdn_sfm_b200.staging import BatchStager
-    stager = BatchStager(list(host_sets[0][:4]), dev, n_buffers=len(host_sets))
+    up_inputs = lambda d: {kk: v for kk, v in d.items() if not (kk[0] == "color" and kk[2] != 0)}
+    stager = BatchStager([up_inputs(host_sets[0][0])] + list(host_sets[0][1:4]), dev, n_buffers=len(host_sets))
     for k, hs in enumerate(host_sets):
-        stager.fill(k, hs[:4])          # untimed: producing the batch in pinned memory is the loader's part
+        stager.fill(k, [up_inputs(hs[0])] + list(hs[1:4]))   # untimed: producing the batch in pinned memory is the loader's part
+    h2d_bytes = stager.nbytes
     leaf = lambda d: {kk: v.detach().requires_grad_(True) for kk, v in d.items()}
 
     def e2e_run(n, start_event=None):
@@ -442,7 +447,8 @@ def run_ours(args):
                 stager.upload(i + 1)
             stager.wait(i)
             v = stager._dev_views[i % stager.n_buffers]
-            loss = step_on((v[0], leaf(v[1]), leaf(v[2]), leaf(v[3]), dev_sets[i % len(dev_sets)][4]))
+            inputs_i = pyramid.add_pyramid_levels(dict(v[0]), [0] + ids, list(scales))
+            loss = step_on((inputs_i, leaf(v[1]), leaf(v[2]), leaf(v[3]), dev_sets[i % len(dev_sets)][4]))
             stager.release(i)
             host_loss.copy_(loss.detach(), non_blocking=True)
 
@@ -506,8 +512,10 @@ def run_ours(args):
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
-                        "path": "mdn_sfm_b200.staging.BatchStager (one pinned slab -> one H2D copy per step on a copy stream, %d buffers) + "
-                                "mdn_sfm_b200.loss_functions.Loss.forward + backward (eager public API) + loss read back to pinned host memory" % len(host_sets)},
+                        "path": "mdn_sfm_b200.staging.BatchStager (one pinned slab -> one H2D copy per step on a copy stream, %d buffers; "
+                                "full-resolution frames, flows, mobile maps, poses, intrinsics) + mdn_sfm_b200.pyramid (lower pyramid "
+                                "levels made on the device) + mdn_sfm_b200.loss_functions.Loss.forward + backward (eager public API) + "
+                                "loss read back to pinned host memory" % len(host_sets)},
                 "gpu_launches": 4 * args.steps,
                 "launches_per_step": "mdn::ref_pack_kernel, mdn::fused_tile_kernel (builds the fundamental matrices from the poses), "
                                      "mdn::finish_kernel (loss scalars, d/dF, pose adjoint), mdn::scale_grads_kernel; "

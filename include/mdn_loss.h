@@ -242,6 +242,18 @@ MDN_API int mdn_instance_mask_resize(const uint8_t* src, int32_t batch, int32_t 
 MDN_API size_t mdn_instance_mask_resize_workspace_bytes(int32_t batch, int32_t in_h, int32_t in_w, const int32_t* out_h,
                                                         const int32_t* out_w, int32_t n_out);
 
+/*
+ * Image pyramid producer: the lower pyramid levels ("color", i, s), s >= 1, from the full-resolution
+ * frame on the device -- torchvision `Resize((H / 2**s, W / 2**s))` of an fp32 tensor (bilinear + antialias, the
+ * dataset-side resize of mono_dataset.py:106-125 applied to tensors), the same separable ATen filter as above without the
+ * rounding.  src (planes, in_h, in_w) fp32 with planes = B * 3; dst is a HOST array of n_out device pointers,
+ * dst[k] -> (planes, out_h[k], out_w[k]).  Workspace: mdn_instance_mask_resize_workspace_bytes(planes, ...).
+ * Only the full-resolution frames then have to cross PCIe.
+ */
+MDN_API int mdn_image_pyramid(const float* src, int32_t planes, int32_t in_h, int32_t in_w, float* const* dst,
+                              const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* binary_image (utils.py:100-103): out = x >= threshold ? 1 : 0 */
 MDN_API int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream);
 

@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(NTHREADS) instance_union_kernel(const __grid_c
 // (_upsample_bilinear2d_aa: _compute_weights_span / _compute_weights / interpolate_aa_single_dim) in fp32 with the same
 // operation order -- weights w_j = f((j + xmin - center + 0.5) / scale) / sum, horizontal pass, then vertical.
 struct ResizeArgs {
-  uint8_t* dst[MDN_MAX_SCALES];
+  void* dst[MDN_MAX_SCALES];           // uint8 masks or fp32 planes
   float* tmp[MDN_MAX_SCALES];          // (B, in_h, out_w[k]) horizontally resized rows (workspace)
   float* wxt[MDN_MAX_SCALES];          // [taps_x][out_w[k]] normalised x weights (workspace)
   float* wyt[MDN_MAX_SCALES];          // [out_h[k]][ty[k]] normalised y weights (workspace)
@@ -764,7 +764,8 @@ __global__ void __launch_bounds__(NTHREADS) instance_resize_weights_kernel(const
 }
 
 // grid.x = 128-column chunk, grid.y = (k, b, group of AA_HROWS source rows)
-__global__ void __launch_bounds__(128) instance_resize_h_kernel(const __grid_constant__ ResizeArgs A, const uint8_t* __restrict__ src) {
+template <typename TIn>
+__global__ void __launch_bounds__(128) instance_resize_h_kernel(const __grid_constant__ ResizeArgs A, const TIn* __restrict__ src) {
   int k = 0;
 #pragma unroll
   for (int q = 1; q < MDN_MAX_SCALES; ++q)
@@ -777,7 +778,7 @@ __global__ void __launch_bounds__(128) instance_resize_h_kernel(const __grid_con
   const int b = rem / groups, y0 = (rem - b * groups) * AA_HROWS;
   const int2 sp = __ldg(A.xspan[k] + ox);
   const float* wcol = A.wxt[k] + ox;
-  const uint8_t* row = src + ((long long)b * A.ih + y0) * A.iw + sp.x;
+  const TIn* row = src + ((long long)b * A.ih + y0) * A.iw + sp.x;
   float* tmp = A.tmp[k] + ((long long)b * A.ih + y0) * ow + ox;
   const int ny = min(AA_HROWS, A.ih - y0);
   float t[AA_HROWS];
@@ -797,7 +798,9 @@ __global__ void __launch_bounds__(128) instance_resize_h_kernel(const __grid_con
     if (y < ny) tmp[(long long)y * ow] = t[y];
 }
 
-// grid.x = 128-column chunk, grid.y = (k, b, group of AA_VROWS output rows)
+// grid.x = 128-column chunk, grid.y = (k, b, group of AA_VROWS output rows).  TOut = uint8_t: round to nearest even and
+// store the integer mask; TOut = float: store the resized value (image pyramids, mdn_image_pyramid)
+template <typename TOut>
 __global__ void __launch_bounds__(128) instance_resize_v_kernel(const __grid_constant__ ResizeArgs A) {
   int k = 0;
 #pragma unroll
@@ -815,7 +818,9 @@ __global__ void __launch_bounds__(128) instance_resize_v_kernel(const __grid_con
     const float* col = A.tmp[k] + ((long long)b * A.ih + sp.x) * ow + ox;
     float out = __fmul_rn(col[0], __ldg(wrow));
     for (int y = 1; y < sp.y; ++y) out = __fmaf_rn(col[(long long)y * ow], __ldg(wrow + y), out);
-    A.dst[k][((long long)b * oh + oy) * ow + ox] = (uint8_t)rintf(out);     // torch.round, then the cast back to integers
+    TOut* dst = reinterpret_cast<TOut*>(A.dst[k]) + ((long long)b * oh + oy) * ow + ox;
+    if (sizeof(TOut) == 1) *dst = (TOut)rintf(out);      // torch.round, then the cast back to integers
+    else *dst = (TOut)out;
   }
 }
 
@@ -1264,9 +1269,9 @@ extern "C" MDN_API size_t mdn_instance_mask_resize_workspace_bytes(int32_t batch
   return resize_ws_layout(batch, in_h, in_w, out_h, out_w, n_out).total;
 }
 
-extern "C" MDN_API int mdn_instance_mask_resize(const uint8_t* src, int32_t batch, int32_t in_h, int32_t in_w, uint8_t* const* dst,
-                                                const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* workspace,
-                                                size_t workspace_bytes, void* stream) {
+template <typename TIn, typename TOut>
+static int launch_resize(const TIn* src, int32_t batch, int32_t in_h, int32_t in_w, TOut* const* dst, const int32_t* out_h,
+                         const int32_t* out_w, int32_t n_out, void* workspace, size_t workspace_bytes, void* stream) {
   if (!src || !dst) return fail(MDN_ERR_NULL_POINTER, "src / dst is NULL");
   int rc = check_resize_sizes(batch, in_h, in_w, out_h, out_w, n_out);
   if (rc != MDN_OK) return rc;
@@ -1294,10 +1299,22 @@ extern "C" MDN_API int mdn_instance_mask_resize(const uint8_t* src, int32_t batc
   A.row_begin[n_out] = hrows; A.vrow_begin[n_out] = vrows;
   cudaStream_t st = (cudaStream_t)stream;
   MDN_LAUNCH(instance_resize_weights_kernel, dim3((n_idx + NTHREADS - 1) / NTHREADS), dim3(NTHREADS), 0, st, A);
-  MDN_LAUNCH(instance_resize_h_kernel, dim3((max_w + 127) / 128, hrows), dim3(128), 0, st, A, src);
-  MDN_LAUNCH(instance_resize_v_kernel, dim3((max_w + 127) / 128, vrows), dim3(128), 0, st, A);
+  { auto kfn = instance_resize_h_kernel<TIn>; MDN_LAUNCH(kfn, dim3((max_w + 127) / 128, hrows), dim3(128), 0, st, A, src); }
+  { auto kfn = instance_resize_v_kernel<TOut>; MDN_LAUNCH(kfn, dim3((max_w + 127) / 128, vrows), dim3(128), 0, st, A); }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" MDN_API int mdn_instance_mask_resize(const uint8_t* src, int32_t batch, int32_t in_h, int32_t in_w, uint8_t* const* dst,
+                                                const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* workspace,
+                                                size_t workspace_bytes, void* stream) {
+  return launch_resize<uint8_t, uint8_t>(src, batch, in_h, in_w, dst, out_h, out_w, n_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" MDN_API int mdn_image_pyramid(const float* src, int32_t planes, int32_t in_h, int32_t in_w, float* const* dst,
+                                         const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  return launch_resize<float, float>(src, planes, in_h, in_w, dst, out_h, out_w, n_out, workspace, workspace_bytes, stream);
 }
 
 extern "C" MDN_API int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream) {

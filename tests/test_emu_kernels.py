@@ -265,3 +265,20 @@ def test_instance_mask_union_and_resize_match_torchvision(src_hw, sizes):
         bare = loss_utils.instance_masks_u8(inst[0]["instances"], sizes[:1], "cpu", lib)
     assert assert_masks_equal_up_to_exact_ties(got, inst, sizes) == 0      # (this seed has no tie)
     assert_masks_equal_up_to_exact_ties(bare, inst[0]["instances"], sizes[:1])
+
+
+def test_image_pyramid_matches_torchvision_resize():
+    """mdn_image_pyramid == torchvision Resize((H/2**s, W/2**s)) of an fp32 image (bilinear + antialias),
+    the three lower pyramid levels in one call; fp32 round-off only (the separable sums run in the library's order)."""
+    from torchvision.transforms import Resize
+    from mdn_sfm_b200 import pyramid
+    g = torch.Generator().manual_seed(3)
+    img = (torch.rand(2, 3, 48, 80, generator=g) - 0.45) / 0.225
+    sizes = [(48, 80), (24, 40), (12, 20), (6, 10), (17, 33)]
+    with emulated() as lib:
+        got = pyramid.image_pyramid(img, sizes, lib)
+    assert got[0] is img
+    for t, s in zip(got, sizes):
+        ref = Resize(s)(img)
+        assert tuple(t.shape) == tuple(ref.shape)
+        assert float((t - ref).abs().max()) <= 2e-6 * float(ref.abs().max()), (s, float((t - ref).abs().max()))

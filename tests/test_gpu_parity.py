@@ -219,3 +219,26 @@ def test_train_step_harness_runs_on_the_cuda_loss():
         last = float(ts.step(inputs)["loss"].detach())
     assert last == last and last < first
     assert all(torch.equal(a, b) for a, b in zip(frozen, ts.nets.flownet.parameters()))
+
+
+@pytest.mark.gpu
+def test_image_pyramid_on_gpu_matches_torchvision():
+    """the lower pyramid levels made on the GPU equal torchvision's Resize of the fp32 frame (CPU), and the
+    loss on a device-made pyramid equals the loss on the dataset-made one to 1e-5."""
+    from torchvision.transforms import Resize
+    from mdn_sfm_b200 import pyramid
+    from mdn_sfm_b200.loss_functions import Loss
+    opt, batch = common.make(2, 192, 640, seed=8)
+    inputs, flows, mobiles, cams, _ = batch
+    img = inputs[("color", -1, 0)]
+    got = pyramid.image_pyramid(img.to(DEV), [(96, 320), (48, 160), (24, 80)])
+    for t, s in zip(got, [(96, 320), (48, 160), (24, 80)]):
+        ref = Resize(s)(img)
+        assert float((t.cpu() - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+    mv = lambda d: {k: v.to(DEV) for k, v in d.items()}
+    loss = Loss(opt, no_ssim=False, mode="T", photometric=True)
+    a = loss(mv(inputs), [-1, 1], mv(flows), mv(mobiles), None, [0, 1, 2, 3], mv(cams))[1]["loss"]
+    dev_in = {k: v.to(DEV) for k, v in inputs.items() if not (k[0] == "color" and k[2] != 0)}
+    pyramid.add_pyramid_levels(dev_in, [0, -1, 1], [0, 1, 2, 3])
+    b = loss(dev_in, [-1, 1], mv(flows), mv(mobiles), None, [0, 1, 2, 3], mv(cams))[1]["loss"]
+    assert float(b) == pytest.approx(float(a), rel=1e-5)
