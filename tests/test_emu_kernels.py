@@ -282,3 +282,27 @@ def test_image_pyramid_matches_torchvision_resize():
         ref = Resize(s)(img)
         assert tuple(t.shape) == tuple(ref.shape)
         assert float((t - ref).abs().max()) <= 2e-6 * float(ref.abs().max()), (s, float((t - ref).abs().max()))
+
+
+FUZZ = [  # B, H, W, scales, mode, photometric, ssim, opt overrides, flow std  (drawn once at random; odd / tiny / ragged shapes)
+    (2, 30, 3, (0,), "DS", True, False, dict(disable_smoothloss=True), 0.01),
+    (1, 37, 5, (0,), "T", False, False, {}, 0.3),
+    (1, 25, 62, (0, 1), "T", False, False, {}, 0.3),
+    (2, 14, 96, (0, 1), "TG", True, True, dict(disable_min=True, disable_smoothloss=True), 0.05),
+    (1, 3, 54, (0,), "DC", True, True, {}, 0.05),
+    (3, 38, 4, (0,), "DC", False, True, dict(disable_consisloss=True), 0.05),
+    (3, 17, 135, (0,), "T", True, True, {}, 0.05),
+    (3, 34, 139, (0,), "SN", False, True, dict(disable_min=True), 0.05),
+]
+
+
+@pytest.mark.parametrize("case", FUZZ, ids=lambda c: "%dx%dx%d-%s" % (c[0], c[1], c[2], c[4]))
+def test_odd_tiny_and_ragged_shapes_all_modes(case):
+    """Edge shapes the tile geometry does not divide (3-pixel-wide images, 3 rows, widths just past a tile, odd sizes),
+    every mode and term switch, pose gradients: product (kernel source under the SIMT emulator) vs the oracle."""
+    B, H, W, scales, mode, photo, ssim, over, fstd = case
+    opt, batch = common.make(B, H, W, scales=scales, seed=100 + H + W, flow_std=fstd, **over)
+    ref = common.oracle_run(opt, batch, mode, photo, ssim, pose_grad=True)
+    with emulated():
+        got = common.product_run(opt, batch, mode, photo, ssim, "cpu", pose_grad=True)
+        common.compare(ref, got, photo, tie_px=common.TIE_PX if mode in ("DS", "DC") else 0)
