@@ -161,6 +161,13 @@ static inline int __shfl_xor_sync(unsigned, int v, int lanemask) {
   return (int)mdn_emu::exchange((uint32_t)v, mdn_emu::st().cur ^ lanemask);
 }
 
+// vote over the 32 lanes of the caller's warp (all lanes of the warp must call it), built on the shuffle rendezvous
+static inline int __all_sync(unsigned, int pred) {
+  unsigned v = pred ? 1u : 0u;
+  for (int m = 16; m >= 1; m >>= 1) v &= mdn_emu::exchange(v, mdn_emu::st().cur ^ m);
+  return (int)v;
+}
+
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
