@@ -291,30 +291,50 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
   // One block per SAMPLE: it folds the sample's tiles of every scale, so it also holds every d/dF of the sample and runs
   // the pose adjoint itself; only the final fold into the loss scalars waits for the last block.
   const KParams& P = Q.K;
-  __shared__ float part[FIN_ROWS][NSLOT];
+  __shared__ float part4[MDN_MAX_SCALES][FIN_ROWS][NSLOT];
+  __shared__ float tots4[MDN_MAX_SCALES][NSLOT];
   __shared__ bool is_last;
   pdl_wait();
   const int b = blockIdx.x;
   const int slot = threadIdx.x % NSLOT, row = threadIdx.x / NSLOT;
   const bool grads = (P.flags & MDN_OPT_GRADS) != 0;
-  for (int s = 0; s < P.n_scales; ++s) {
-  const KScale& S = P.sc[s];
-  const int tiles = S.tiles_x * S.tiles_y;
-  const float* src = P.partials + ((long long)S.tile_begin + (long long)b * tiles) * NSLOT;
-  float t = 0.f;
-#pragma unroll 4
-  for (int k = row; k < tiles; k += FIN_ROWS) t += __ldcg(src + (long long)k * NSLOT + slot);
-  part[row][slot] = t;
-  __syncthreads();
-  if (row == 0) {
-    float tot = 0.f;
-    for (int k = 0; k < FIN_ROWS; ++k) tot += part[k][slot];
-    part[0][slot] = tot;
-    Q.sample_sums[((long long)s * P.batch + b) * NSLOT + slot] = tot;
+  // every scale in ONE round: the sample's tiles of all scales form one list walked with stride FIN_ROWS; a thread keeps
+  // one accumulator per scale (fixed order per scale: deterministic)
+  {
+    int cum[MDN_MAX_SCALES + 1];
+    cum[0] = 0;
+#pragma unroll
+    for (int s = 0; s < MDN_MAX_SCALES; ++s) cum[s + 1] = cum[s] + (s < P.n_scales ? P.sc[s].tiles_x * P.sc[s].tiles_y : 0);
+    float t[MDN_MAX_SCALES];
+#pragma unroll
+    for (int s = 0; s < MDN_MAX_SCALES; ++s) t[s] = 0.f;
+    for (int item = row; item < cum[MDN_MAX_SCALES]; item += FIN_ROWS) {
+      int s = 0;
+#pragma unroll
+      for (int q = 1; q < MDN_MAX_SCALES; ++q) s += (item >= cum[q]) ? 1 : 0;
+      const KScale& Z = P.sc[s];
+      const float v = __ldcg(P.partials + ((long long)Z.tile_begin + (long long)b * (Z.tiles_x * Z.tiles_y) + (item - cum[s])) * NSLOT + slot);
+#pragma unroll
+      for (int q = 0; q < MDN_MAX_SCALES; ++q) t[q] += (q == s) ? v : 0.f;
+    }
+#pragma unroll
+    for (int s = 0; s < MDN_MAX_SCALES; ++s) part4[s][row][slot] = t[s];
   }
   __syncthreads();
-  if (grads && (P.flags & MDN_TERM_EPIPOLAR) && threadIdx.x < (unsigned)P.n_pairs) {
-    const int pair = threadIdx.x;
+  if (threadIdx.x < (unsigned)(P.n_scales * NSLOT)) {
+    const int s = threadIdx.x / NSLOT, k = threadIdx.x % NSLOT;
+    float tot = 0.f;
+    for (int r = 0; r < FIN_ROWS; ++r) tot += part4[s][r][k];
+    tots4[s][k] = tot;
+    Q.sample_sums[((long long)s * P.batch + b) * NSLOT + k] = tot;
+  }
+  __syncthreads();
+  // d/dF of every (scale, pair) of the sample in parallel: thread = scale * n_pairs + pair
+  if (grads && (P.flags & MDN_TERM_EPIPOLAR) && threadIdx.x < (unsigned)(P.n_scales * P.n_pairs)) {
+    const int s = threadIdx.x / P.n_pairs, pair = threadIdx.x - s * P.n_pairs;
+    const KScale& S = P.sc[s];
+    const float (*part)[NSLOT] = &tots4[s];     // part[0][k] = this scale's sums
+
     float gF[9];
     for (int k = 0; k < 9; ++k) gF[k] = part[0][pair * PAIR_SLOTS + SL_GF + k];
     if (P.post == MDN_POST_SN) {
@@ -351,8 +371,7 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
     if (Q.gf_ws)
       for (int k = 0; k < 9; ++k) Q.gf_ws[((size_t)(s * P.n_pairs + pair) * P.batch + b) * 9 + k] = gF[k];
   }
-  __syncthreads();   // part[] is rewritten by the next scale
-  }
+  __syncthreads();
   // pose adjoint of this sample (what mdn_fundamental_bwd computes) from the d/dF written above by this block
   if (Q.gf_ws && threadIdx.x < (unsigned)P.n_pairs && Q.g_cam[threadIdx.x]) {
     FundArgs A;
