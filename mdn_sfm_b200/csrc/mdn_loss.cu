@@ -738,7 +738,7 @@ struct AaSpan {
   MDN_DEV float weight(int j) const { return total != 0.f ? __fdiv_rn(raw(j), total) : raw(j); }
 };
 
-MDN_DEV AaSpan aa_span(int i, int in_size, float scale) {
+MDN_DEV AaSpan aa_span_no_total(int i, int in_size, float scale) {
   AaSpan sp;
   const float support = (scale >= 1.f) ? scale : 1.f;                     // (interp_size * 0.5) * scale, interp_size = 2
   sp.center = (float)((double)scale * ((double)i + 0.5));
@@ -747,6 +747,11 @@ MDN_DEV AaSpan aa_span(int i, int in_size, float scale) {
   sp.xsize = min(max(sp.xsize, 0), (int)ceilf(support) * 2 + 1);
   sp.invscale = (scale >= 1.f) ? (float)(1.0 / (double)scale) : 1.f;
   sp.total = 0.f;
+  return sp;
+}
+
+MDN_DEV AaSpan aa_span(int i, int in_size, float scale) {
+  AaSpan sp = aa_span_no_total(i, in_size, scale);
   for (int j = 0; j < sp.xsize; ++j) sp.total = __fadd_rn(sp.total, sp.raw(j));
   return sp;
 }
@@ -761,39 +766,56 @@ MDN_DEV AaSpan aa_span(int i, int in_size, float scale) {
 constexpr int AA_HROWS = 8;      // source rows per block of the horizontal pass
 constexpr int AA_VROWS = 4;      // output rows per block of the vertical pass
 
-// one thread per (output size k, axis, output index): span -> A.xspan / A.yspan, weights -> A.wxt[k][tap][ox] / A.wyt[k][oy][tap]
-__global__ void __launch_bounds__(NTHREADS) instance_resize_weights_kernel(const __grid_constant__ ResizeArgs A) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int k = 0; k < A.n_out; ++k) {
-    if (i < A.ow[k]) {
-      const AaSpan sp = aa_span(i, A.iw, __fdiv_rn((float)A.iw, (float)A.ow[k]));   // area_pixel_compute_scale
-      A.xspan[k][i] = make_int2(sp.xmin, sp.xsize);
-      for (int j = 0; j < sp.xsize; ++j) A.wxt[k][(long long)j * A.ow[k] + i] = sp.weight(j);
-      return;
+// one WARP per (output size k, axis, output index): the lanes evaluate the taps in parallel, lane 0 adds them up in tap
+// order (the library's sequential `total_w += w`), the lanes divide.  span -> A.xspan / A.yspan, weights ->
+// A.wxt[k][tap][ox] / A.wyt[k][oy][tap]
+constexpr int AA_MAXTAPS = 1024;   // per-warp staging of the raw taps (down-scaling factors up to ~500)
+__global__ void __launch_bounds__(NTHREADS) instance_resize_weights_kernel(const __grid_constant__ ResizeArgs A, const int n_idx) {
+  __shared__ float raw_s[NTHREADS / 32][AA_MAXTAPS];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  int i = blockIdx.x * (NTHREADS / 32) + wrp;
+  const bool live = i < n_idx;        // (whole warps; idle ones still walk the warp-level synchronisation below)
+  int k = 0, axis = 0;
+  if (live)
+    for (; k < A.n_out; ++k) {
+      if (i < A.ow[k]) { axis = 0; break; }
+      i -= A.ow[k];
+      if (i < A.oh[k]) { axis = 1; break; }
+      i -= A.oh[k];
     }
-    i -= A.ow[k];
-    if (i < A.oh[k]) {
-      const AaSpan sp = aa_span(i, A.ih, __fdiv_rn((float)A.ih, (float)A.oh[k]));
-      A.yspan[k][i] = make_int2(sp.xmin, sp.xsize);
-      for (int j = 0; j < sp.xsize; ++j) A.wyt[k][(long long)i * A.ty[k] + j] = sp.weight(j);
-      return;
-    }
-    i -= A.oh[k];
+  const int in_size = axis ? A.ih : A.iw, out_size = axis ? A.oh[k] : A.ow[k];
+  AaSpan sp = aa_span_no_total(live ? i : 0, in_size, __fdiv_rn((float)in_size, (float)out_size));   // area_pixel_compute_scale
+  if (!live) sp.xsize = 0;
+  float* raw = raw_s[wrp];
+  for (int j = lane; j < sp.xsize; j += 32) raw[j] = sp.raw(j);
+  __syncwarp();
+  float total = 0.f;
+  if (lane == 0)
+    for (int j = 0; j < sp.xsize; ++j) total = __fadd_rn(total, raw[j]);
+  total = __shfl_sync(0xffffffffu, total, 0);
+  if (lane == 0 && live) (axis ? A.yspan[k] : A.xspan[k])[i] = make_int2(sp.xmin, sp.xsize);
+  for (int j = lane; j < sp.xsize; j += 32) {
+    const float wj = total != 0.f ? __fdiv_rn(raw[j], total) : raw[j];
+    if (axis) A.wyt[k][(long long)i * A.ty[k] + j] = wj;
+    else A.wxt[k][(long long)j * A.ow[k] + i] = wj;
   }
 }
 
-// grid.x = 128-column chunk, grid.y = (k, b, group of AA_HROWS source rows)
+// flat grid: output size k owns blocks [row_begin[k], row_begin[k + 1]) = (b, group of AA_HROWS source rows, 128-column chunk)
 template <typename TIn>
 __global__ void __launch_bounds__(128) instance_resize_h_kernel(const __grid_constant__ ResizeArgs A, const TIn* __restrict__ src) {
   int k = 0;
 #pragma unroll
   for (int q = 1; q < MDN_MAX_SCALES; ++q)
-    if (q < A.n_out && (int)blockIdx.y >= A.row_begin[q]) k = q;
+    if (q < A.n_out && (int)blockIdx.x >= A.row_begin[q]) k = q;
   const int ow = A.ow[k];
-  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunks = (ow + 127) / 128;
+  int rem = blockIdx.x - A.row_begin[k];
+  const int cx = rem % chunks;
+  rem /= chunks;
+  const int ox = cx * 128 + threadIdx.x;
   if (ox >= ow) return;
   const int groups = (A.ih + AA_HROWS - 1) / AA_HROWS;
-  const int rem = blockIdx.y - A.row_begin[k];
   const int b = rem / groups, y0 = (rem - b * groups) * AA_HROWS;
   const int2 sp = __ldg(A.xspan[k] + ox);
   const float* wcol = A.wxt[k] + ox;
@@ -817,19 +839,22 @@ __global__ void __launch_bounds__(128) instance_resize_h_kernel(const __grid_con
     if (y < ny) tmp[(long long)y * ow] = t[y];
 }
 
-// grid.x = 128-column chunk, grid.y = (k, b, group of AA_VROWS output rows).  TOut = uint8_t: round to nearest even and
+// flat grid: (k, b, group of AA_VROWS output rows, 128-column chunk).  TOut = uint8_t: round to nearest even and
 // store the integer mask; TOut = float: store the resized value (image pyramids, mdn_image_pyramid)
 template <typename TOut>
 __global__ void __launch_bounds__(128) instance_resize_v_kernel(const __grid_constant__ ResizeArgs A) {
   int k = 0;
 #pragma unroll
   for (int q = 1; q < MDN_MAX_SCALES; ++q)
-    if (q < A.n_out && (int)blockIdx.y >= A.vrow_begin[q]) k = q;
+    if (q < A.n_out && (int)blockIdx.x >= A.vrow_begin[q]) k = q;
   const int oh = A.oh[k], ow = A.ow[k];
-  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunks = (ow + 127) / 128;
+  int rem = blockIdx.x - A.vrow_begin[k];
+  const int cx = rem % chunks;
+  rem /= chunks;
+  const int ox = cx * 128 + threadIdx.x;
   if (ox >= ow) return;
   const int groups = (oh + AA_VROWS - 1) / AA_VROWS;
-  const int rem = blockIdx.y - A.vrow_begin[k];
   const int b = rem / groups, oy0 = (rem - b * groups) * AA_VROWS;
   for (int oy = oy0; oy < min(oy0 + AA_VROWS, oh); ++oy) {
     const int2 sp = __ldg(A.yspan[k] + oy);
@@ -1310,16 +1335,19 @@ static int launch_resize(const TIn* src, int32_t batch, int32_t in_h, int32_t in
     A.xspan[k] = (int2*)(ws + L.xspan[k]); A.yspan[k] = (int2*)(ws + L.yspan[k]);
     A.ty[k] = aa_taps(in_h, out_h[k]);
     A.row_begin[k] = hrows; A.vrow_begin[k] = vrows;
-    hrows += batch * hgroups;
-    vrows += batch * ((out_h[k] + AA_VROWS - 1) / AA_VROWS);
+    if (aa_taps(in_h, out_h[k]) > AA_MAXTAPS || aa_taps(in_w, out_w[k]) > AA_MAXTAPS)
+      return fail(MDN_ERR_UNSUPPORTED, "down-scaling factor above 500 is not supported");
+    const int chunks = (out_w[k] + 127) / 128;
+    hrows += batch * hgroups * chunks;
+    vrows += batch * ((out_h[k] + AA_VROWS - 1) / AA_VROWS) * chunks;
     max_w = std::max(max_w, (int)out_w[k]);
     n_idx += out_w[k] + out_h[k];
   }
   A.row_begin[n_out] = hrows; A.vrow_begin[n_out] = vrows;
   cudaStream_t st = (cudaStream_t)stream;
-  MDN_LAUNCH(instance_resize_weights_kernel, dim3((n_idx + NTHREADS - 1) / NTHREADS), dim3(NTHREADS), 0, st, A);
-  { auto kfn = instance_resize_h_kernel<TIn>; MDN_LAUNCH(kfn, dim3((max_w + 127) / 128, hrows), dim3(128), 0, st, A, src); }
-  { auto kfn = instance_resize_v_kernel<TOut>; MDN_LAUNCH(kfn, dim3((max_w + 127) / 128, vrows), dim3(128), 0, st, A); }
+  MDN_LAUNCH(instance_resize_weights_kernel, dim3((n_idx + NTHREADS / 32 - 1) / (NTHREADS / 32)), dim3(NTHREADS), 0, st, A, n_idx);
+  { auto kfn = instance_resize_h_kernel<TIn>; MDN_LAUNCH(kfn, dim3(hrows), dim3(128), 0, st, A, src); }
+  { auto kfn = instance_resize_v_kernel<TOut>; MDN_LAUNCH(kfn, dim3(vrows), dim3(128), 0, st, A); }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }

@@ -161,6 +161,12 @@ static inline int __shfl_xor_sync(unsigned, int v, int lanemask) {
   return (int)mdn_emu::exchange((uint32_t)v, mdn_emu::st().cur ^ lanemask);
 }
 
+static inline void __syncwarp(unsigned = 0xffffffffu) { mdn_emu::yield_to_scheduler(); }
+static inline float __shfl_sync(unsigned, float v, int src_lane) {
+  uint32_t u; memcpy(&u, &v, 4);
+  u = mdn_emu::exchange(u, (mdn_emu::st().cur & ~31) | src_lane);
+  float r; memcpy(&r, &u, 4); return r;
+}
 // vote over the 32 lanes of the caller's warp (all lanes of the warp must call it), built on the shuffle rendezvous
 static inline int __all_sync(unsigned, int pred) {
   unsigned v = pred ? 1u : 0u;
