@@ -819,24 +819,32 @@ __global__ void __launch_bounds__(128) instance_resize_h_kernel(const __grid_con
   const int b = rem / groups, y0 = (rem - b * groups) * AA_HROWS;
   const int2 sp = __ldg(A.xspan[k] + ox);
   const float* wcol = A.wxt[k] + ox;
-  const TIn* row = src + ((long long)b * A.ih + y0) * A.iw + sp.x;
-  float* tmp = A.tmp[k] + ((long long)b * A.ih + y0) * ow + ox;
   const int ny = min(AA_HROWS, A.ih - y0);
+  // row pointers once (rows past the image re-read the last valid row; their sums are not stored): the tap loop is
+  // load + accumulate only.  A {0,1} byte times w is w or 0 and fma(1, w, t) == t + w exactly, so the mask path needs no
+  // integer->float conversion: t += byte ? w : 0.
+  const TIn* rp[AA_HROWS];
+#pragma unroll
+  for (int y = 0; y < AA_HROWS; ++y) rp[y] = src + ((long long)b * A.ih + y0 + min(y, ny - 1)) * A.iw + sp.x;
+  auto term = [](TIn v, float wj) -> float { return sizeof(TIn) == 1 ? (v ? wj : 0.f) : __fmul_rn((float)v, wj); };
   float t[AA_HROWS];
+  {
+    const float w0 = __ldg(wcol);
 #pragma unroll
-  for (int y = 0; y < AA_HROWS; ++y) t[y] = 0.f;
-  for (int j = 0; j < sp.y; ++j) {            // the AA_HROWS rows are independent FMA chains sharing the weight
-    const float wj = __ldg(wcol + (long long)j * ow);
-#pragma unroll
-    for (int y = 0; y < AA_HROWS; ++y)
-      if (y < ny) {
-        const float v = (float)__ldg(row + (long long)y * A.iw + j);
-        t[y] = (j == 0) ? __fmul_rn(v, wj) : __fmaf_rn(v, wj, t[y]);
-      }
+    for (int y = 0; y < AA_HROWS; ++y) t[y] = term(__ldg(rp[y]), w0);
   }
+  for (int j = 1; j < sp.y; ++j) {            // the AA_HROWS rows are independent chains sharing the weight
+    const float wj = __ldg(wcol + (size_t)j * ow);
+#pragma unroll
+    for (int y = 0; y < AA_HROWS; ++y) {
+      const TIn v = __ldg(rp[y] + j);
+      t[y] = sizeof(TIn) == 1 ? __fadd_rn(t[y], v ? wj : 0.f) : __fmaf_rn((float)v, wj, t[y]);
+    }
+  }
+  float* tmp = A.tmp[k] + ((long long)b * A.ih + y0) * ow + ox;
 #pragma unroll
   for (int y = 0; y < AA_HROWS; ++y)
-    if (y < ny) tmp[(long long)y * ow] = t[y];
+    if (y < ny) tmp[(size_t)y * ow] = t[y];
 }
 
 // flat grid: (k, b, group of AA_VROWS output rows, 128-column chunk).  TOut = uint8_t: round to nearest even and
@@ -861,7 +869,7 @@ __global__ void __launch_bounds__(128) instance_resize_v_kernel(const __grid_con
     const float* wrow = A.wyt[k] + (long long)oy * A.ty[k];
     const float* col = A.tmp[k] + ((long long)b * A.ih + sp.x) * ow + ox;
     float out = __fmul_rn(col[0], __ldg(wrow));
-    for (int y = 1; y < sp.y; ++y) out = __fmaf_rn(col[(long long)y * ow], __ldg(wrow + y), out);
+    for (int y = 1; y < sp.y; ++y) { col += ow; out = __fmaf_rn(*col, __ldg(wrow + y), out); }
     TOut* dst = reinterpret_cast<TOut*>(A.dst[k]) + ((long long)b * oh + oy) * ow + ox;
     if (sizeof(TOut) == 1) *dst = (TOut)rintf(out);      // torch.round, then the cast back to integers
     else *dst = (TOut)out;
