@@ -833,13 +833,15 @@ __global__ void __launch_bounds__(128) instance_resize_h_kernel(const __grid_con
 #pragma unroll
     for (int y = 0; y < AA_HROWS; ++y) t[y] = term(__ldg(rp[y]), w0);
   }
+#pragma unroll 2
   for (int j = 1; j < sp.y; ++j) {            // the AA_HROWS rows are independent chains sharing the weight
     const float wj = __ldg(wcol + (size_t)j * ow);
+    TIn v[AA_HROWS];
 #pragma unroll
-    for (int y = 0; y < AA_HROWS; ++y) {
-      const TIn v = __ldg(rp[y] + j);
-      t[y] = sizeof(TIn) == 1 ? __fadd_rn(t[y], v ? wj : 0.f) : __fmaf_rn((float)v, wj, t[y]);
-    }
+    for (int y = 0; y < AA_HROWS; ++y) v[y] = __ldg(rp[y] + j);
+#pragma unroll
+    for (int y = 0; y < AA_HROWS; ++y)
+      t[y] = sizeof(TIn) == 1 ? __fadd_rn(t[y], v[y] ? wj : 0.f) : __fmaf_rn((float)v[y], wj, t[y]);
   }
   float* tmp = A.tmp[k] + ((long long)b * A.ih + y0) * ow + ox;
 #pragma unroll
@@ -868,8 +870,17 @@ __global__ void __launch_bounds__(128) instance_resize_v_kernel(const __grid_con
     const int2 sp = __ldg(A.yspan[k] + oy);
     const float* wrow = A.wyt[k] + (long long)oy * A.ty[k];
     const float* col = A.tmp[k] + ((long long)b * A.ih + sp.x) * ow + ox;
+    // loads batched eight deep (one load in flight per thread made this pass latency-bound); the sum stays sequential
     float out = __fmul_rn(col[0], __ldg(wrow));
-    for (int y = 1; y < sp.y; ++y) { col += ow; out = __fmaf_rn(*col, __ldg(wrow + y), out); }
+    int y = 1;
+    for (; y + 8 <= sp.y; y += 8) {
+      float v[8], wv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { v[q] = col[(size_t)(y + q) * ow]; wv[q] = __ldg(wrow + y + q); }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) out = __fmaf_rn(v[q], wv[q], out);
+    }
+    for (; y < sp.y; ++y) out = __fmaf_rn(col[(size_t)y * ow], __ldg(wrow + y), out);
     TOut* dst = reinterpret_cast<TOut*>(A.dst[k]) + ((long long)b * oh + oy) * ow + ox;
     if (sizeof(TOut) == 1) *dst = (TOut)rintf(out);      // torch.round, then the cast back to integers
     else *dst = (TOut)out;
