@@ -833,15 +833,26 @@ __global__ void __launch_bounds__(128) instance_resize_h_kernel(const __grid_con
 #pragma unroll
     for (int y = 0; y < AA_HROWS; ++y) t[y] = term(__ldg(rp[y]), w0);
   }
-#pragma unroll 2
-  for (int j = 1; j < sp.y; ++j) {            // the AA_HROWS rows are independent chains sharing the weight
-    const float wj = __ldg(wcol + (size_t)j * ow);
-    TIn v[AA_HROWS];
+  // four taps per trip: the byte loads use immediate offsets from row pointers bumped once per trip (address arithmetic
+  // was 2/3 of this kernel); the AA_HROWS rows are independent chains sharing the weights
+  auto acc = [](float tt, TIn v, float wj) -> float { return sizeof(TIn) == 1 ? __fadd_rn(tt, v ? wj : 0.f) : __fmaf_rn((float)v, wj, tt); };
+  int j = 1;
 #pragma unroll
-    for (int y = 0; y < AA_HROWS; ++y) v[y] = __ldg(rp[y] + j);
+  for (int y = 0; y < AA_HROWS; ++y) rp[y] += 1;
+  const float* wp = wcol + ow;
+  for (; j + 4 <= sp.y; j += 4, wp += 4 * (size_t)ow) {
+    const float w0 = __ldg(wp), w1 = __ldg(wp + ow), w2 = __ldg(wp + 2 * (size_t)ow), w3 = __ldg(wp + 3 * (size_t)ow);
 #pragma unroll
-    for (int y = 0; y < AA_HROWS; ++y)
-      t[y] = sizeof(TIn) == 1 ? __fadd_rn(t[y], v[y] ? wj : 0.f) : __fmaf_rn((float)v[y], wj, t[y]);
+    for (int y = 0; y < AA_HROWS; ++y) {
+      const TIn v0 = __ldg(rp[y]), v1 = __ldg(rp[y] + 1), v2 = __ldg(rp[y] + 2), v3 = __ldg(rp[y] + 3);
+      t[y] = acc(acc(acc(acc(t[y], v0, w0), v1, w1), v2, w2), v3, w3);
+      rp[y] += 4;
+    }
+  }
+  for (; j < sp.y; ++j, wp += ow) {
+    const float wj = __ldg(wp);
+#pragma unroll
+    for (int y = 0; y < AA_HROWS; ++y) { t[y] = acc(t[y], __ldg(rp[y]), wj); rp[y] += 1; }
   }
   float* tmp = A.tmp[k] + ((long long)b * A.ih + y0) * ow + ox;
 #pragma unroll
@@ -866,24 +877,39 @@ __global__ void __launch_bounds__(128) instance_resize_v_kernel(const __grid_con
   if (ox >= ow) return;
   const int groups = (oh + AA_VROWS - 1) / AA_VROWS;
   const int b = rem / groups, oy0 = (rem - b * groups) * AA_VROWS;
-  for (int oy = oy0; oy < min(oy0 + AA_VROWS, oh); ++oy) {
-    const int2 sp = __ldg(A.yspan[k] + oy);
-    const float* wrow = A.wyt[k] + (long long)oy * A.ty[k];
-    const float* col = A.tmp[k] + ((long long)b * A.ih + sp.x) * ow + ox;
-    // loads batched eight deep (one load in flight per thread made this pass latency-bound); the sum stays sequential
-    float out = __fmul_rn(col[0], __ldg(wrow));
-    int y = 1;
-    for (; y + 8 <= sp.y; y += 8) {
-      float v[8], wv[8];
+  // the AA_VROWS output rows advance together, tap by tap: their loads are independent, so AA_VROWS (x2 by unrolling)
+  // are in flight per thread instead of one (this pass waits on L2 / HBM latency, not on arithmetic)
+  int2 sp[AA_VROWS];
+  const float* col[AA_VROWS];
+  const float* wrow[AA_VROWS];
+  float out[AA_VROWS];
+  int maxn = 0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { v[q] = col[(size_t)(y + q) * ow]; wv[q] = __ldg(wrow + y + q); }
+  for (int r = 0; r < AA_VROWS; ++r) {
+    const int oy = min(oy0 + r, oh - 1);
+    sp[r] = __ldg(A.yspan[k] + oy);
+    if (oy0 + r >= oh) sp[r].y = 0;
+    wrow[r] = A.wyt[k] + (long long)oy * A.ty[k];
+    col[r] = A.tmp[k] + ((long long)b * A.ih + sp[r].x) * ow + ox;
+    maxn = max(maxn, sp[r].y);
+    out[r] = 0.f;
+  }
+#pragma unroll 2
+  for (int y = 0; y < maxn; ++y) {
+    float v[AA_VROWS], wv[AA_VROWS];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) out = __fmaf_rn(v[q], wv[q], out);
-    }
-    for (; y < sp.y; ++y) out = __fmaf_rn(col[(size_t)y * ow], __ldg(wrow + y), out);
-    TOut* dst = reinterpret_cast<TOut*>(A.dst[k]) + ((long long)b * oh + oy) * ow + ox;
-    if (sizeof(TOut) == 1) *dst = (TOut)rintf(out);      // torch.round, then the cast back to integers
-    else *dst = (TOut)out;
+    for (int r = 0; r < AA_VROWS; ++r)
+      if (y < sp[r].y) { v[r] = *col[r]; wv[r] = __ldg(wrow[r] + y); col[r] += ow; }
+#pragma unroll
+    for (int r = 0; r < AA_VROWS; ++r)
+      if (y < sp[r].y) out[r] = (y == 0) ? __fmul_rn(v[r], wv[r]) : __fmaf_rn(v[r], wv[r], out[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < AA_VROWS; ++r) {
+    if (oy0 + r >= oh) continue;
+    TOut* dst = reinterpret_cast<TOut*>(A.dst[k]) + ((long long)b * oh + oy0 + r) * ow + ox;
+    if (sizeof(TOut) == 1) *dst = (TOut)rintf(out[r]);      // torch.round, then the cast back to integers
+    else *dst = (TOut)out[r];
   }
 }
 
