@@ -9,8 +9,10 @@
 #ifdef MDN_EMU
 #include "cuda_emu.h"
 #else
+#include <cuda.h>
 #include <cuda_runtime.h>
-#define MDN_DYN_SMEM(name) extern __shared__ __align__(16) float name[]
+#include <cuda/ptx>
+#define MDN_DYN_SMEM(name) extern __shared__ __align__(128) float name[]
 #define MDN_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 // Programmatic dependent launch: the grid may be scheduled while the previous kernel of the stream drains; the kernel
 // calls pdl_wait() before it touches global memory, so only its launch latency overlaps.  MDN_PDL (environment) is a

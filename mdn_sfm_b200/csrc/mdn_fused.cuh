@@ -33,11 +33,11 @@ struct FusedSmem {
   float* M;      // [2][R2P] the two mobile maps, tile + halo, ZERO outside the image (halo-2 layout, 1 pixel used)
   float* FL;     // [PR][2][FT] float2: flow (x, y planes) of the own pixels, stashed by P1 for P4
   float* red;    // [FWARPS][NSLOT]
-  float* fm;     // [2][16] fundamental matrix + SN maximum of the (pair, sample)
+  float* fm;     // [2][16] fundamental matrix + SN maximum of the (pair, sample); then the TMA mbarrier (8 bytes)
 };
 
 __host__ __device__ constexpr size_t fused_smem_floats(bool photo) {
-  return 3 * R2P + (size_t)FWARPS * NSLOT + 32 + 2 * R2P + (photo ? 3 * R2P + 3 * R1P + 6 * PR * FT * 2 + PR * 2 * FT * 2 : 0);
+  return 3 * R2P + (size_t)FWARPS * NSLOT + 32 + 32 + 2 * R2P + (photo ? 3 * R2P + 3 * R1P + 6 * PR * FT * 2 + PR * 2 * FT * 2 : 0);
 }
 
 template <int NV>
@@ -56,9 +56,9 @@ MDN_DEV int stage_index(int t, int n) {
 
 // (r, j) of the first pixel of the i-th PAIR of the halo ring of the halo-2 region: two top rows, two bottom rows
 // (S2 / 2 pairs each), then the two side pairs of every interior row
-constexpr int RINGP = 2 * S2 + 2 * TH;
+constexpr int RINGP = 2 * W2 + 2 * TH;
 MDN_DEV void ring_pair(int i, int& r, int& j) {
-  constexpr int HP = S2 / 2;
+  constexpr int HP = W2 / 2;
   if (i < 2 * HP) { r = i / HP; j = 2 * (i - r * HP); }
   else if (i < 4 * HP) { i -= 2 * HP; r = i / HP; j = 2 * (i - r * HP); r += TH + 2; }
   else { i -= 4 * HP; r = 2 + (i >> 1); j = (i & 1) ? TW + 2 : 0; }
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
   sm.T = smem_raw;
   sm.red = sm.T + 3 * R2P;
   sm.fm = sm.red + FWARPS * NSLOT;
-  sm.M = sm.fm + 32;
+  sm.M = sm.fm + 64;     // (fm + 32 .. fm + 63: the mbarrier and padding that keeps the planes 128-byte aligned)
   sm.W = sm.M + 2 * R2P;
   sm.Q = sm.W + 3 * R2P;
   sm.D = sm.Q + 3 * R1P;
@@ -157,6 +157,48 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
     }
   }
 
+  // ---- TMA staging needs an mbarrier in shared memory, initialised before anybody polls it
+  uint64_t* tma_bar = reinterpret_cast<uint64_t*>(sm.fm + 32);
+  const bool use_tma = P.tma_ok[s] != 0;
+#ifndef MDN_EMU
+  if (use_tma) {
+    if (tid == 0) {
+      cuda::ptx::mbarrier_init(tma_bar, 1);
+      cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+    }
+    __syncthreads();
+  }
+#endif
+  // waits for the staged planes (both mechanisms), then patches the reflection ring a TMA copy cannot produce
+  auto staging_done = [&]() {
+    cp_async_wait_all();
+#ifndef MDN_EMU
+    if (use_tma) {
+      while (!cuda::ptx::mbarrier_try_wait_parity(tma_bar, 0u)) {}
+      // ReflectionPad2d(1) of the image planes: slots at x = -1 / w and y = -1 / h take the mirrored pixel, which the box
+      // delivered (it lies inside the image and inside this tile).  Block-uniform: interior tiles skip it.
+      const int jw = w - x0 + 2, rh = h - y0 + 2;        // slot column of x = w, slot row of y = h
+      const bool bx = (x0 == 0) | (jw < W2), by = (y0 == 0) | (rh < R2H);
+      if (need_tgt && (bx | by)) {
+        __syncthreads();
+        for (int i = tid; i < 3 * (2 * R2H + 2 * W2); i += FT) {
+          const int c = i / (2 * R2H + 2 * W2);
+          int q = i - c * (2 * R2H + 2 * W2), r, j;
+          if (q < 2 * R2H) { r = q >> 1; j = (q & 1) ? jw : 1; }          // the two ring columns
+          else { q -= 2 * R2H; j = q >> 1; r = (q & 1) ? rh : 1; }        // the two ring rows
+          if ((unsigned)j >= (unsigned)W2 || (unsigned)r >= (unsigned)R2H) continue;
+          const int x = x0 - 2 + j, y = y0 - 2 + r;
+          if ((unsigned)x < (unsigned)w && (unsigned)y < (unsigned)h) continue;      // a real pixel
+          const int xx = stage_index(x, w), yy = stage_index(y, h);
+          if ((xx | yy) < 0) continue;                                               // beyond the reflected ring: stays 0
+          float* pl = sm.T + c * R2P + OFF2;
+          pl[r * S2 + j] = pl[(yy - (y0 - 2)) * S2 + (xx - (x0 - 2))];
+        }
+      }
+    }
+#endif
+  };
+
   // ---- P0: stage the target image (planes 0-2: halo 2, reflection padded) and the two mobile maps (planes 3-4: zero
   // outside the image) with cp.async; the copies land while P1 runs.  Nothing after this reads them from global memory.
   const float* mob0 = opaque_ptr(need_mask ? S.mob[0] + (size_t)b * hw : nullptr);
@@ -168,6 +210,20 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
     auto plane_dst = [&](int pl) -> float* { return pl < 3 ? sm.T + pl * R2P : sm.M + (pl - 3) * R2P; };
     // source coordinate of slot coordinate t: reflected for the image planes, none (-1 -> zero fill) for the maps
     auto src_index = [&](int pl, int tt, int n) { return pl < 3 ? stage_index(tt, n) : ((unsigned)tt < (unsigned)n ? tt : -1); };
+#ifndef MDN_EMU
+    if (use_tma) {
+      // one TMA box per plane: 72 x 20 floats at (x0 - 4, y0 - 2, plane), zeros outside the tensor, arriving on the mbarrier
+      // initialised above; the reflected ring of the image planes is patched after the wait (border tiles only)
+      if (tid == 0) {
+        namespace ptx = cuda::ptx;
+        ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, tma_bar, (unsigned)((pl1 - pl0) * R2P * 4));
+        for (int pl = pl0; pl < pl1; ++pl) {
+          const int32_t coord[3] = {x0 - 4, y0 - 2, pl < 3 ? b * 3 + pl : b};
+          ptx::cp_async_bulk_tensor(ptx::space_cluster, ptx::space_global, plane_dst(pl), &P.tmap[s][pl < 3 ? 0 : pl - 2], coord, tma_bar);
+        }
+      }
+    } else
+#endif
     if (((w & 3) == 0) & (x0 + TW <= w)) {
       // interior columns as 16-byte copies (global x0 + 4q and slot OFF2 + 2 + 4q are both 16-byte aligned)
       for (int i = tid + pl0 * R2H * (TW / 4); i < pl1 * R2H * (TW / 4); i += FT) {
@@ -186,12 +242,12 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
         cp_async_f32(plane_dst(c) + OFF2 + r * S2 + j, plane_src(c) + (ok ? yy * w + xx : 0), ok);
       }
     } else {
-      for (int i = tid + pl0 * R2H * S2; i < pl1 * R2H * S2; i += FT) {
-        const int c = i / (R2H * S2), rr = i - c * (R2H * S2);
-        const int r = rr / S2, j = rr - r * S2;
+      for (int i = tid + pl0 * R2H * W2; i < pl1 * R2H * W2; i += FT) {
+        const int c = i / (R2H * W2), rr = i - c * (R2H * W2);
+        const int r = rr / W2, j = rr - r * W2;
         const int yy = src_index(c, y0 - 2 + r, h), xx = src_index(c, x0 - 2 + j, w);
         const bool ok = (yy | xx) >= 0;
-        cp_async_f32(plane_dst(c) + OFF2 + rr, plane_src(c) + (ok ? yy * w + xx : 0), ok);
+        cp_async_f32(plane_dst(c) + OFF2 + r * S2 + j, plane_src(c) + (ok ? yy * w + xx : 0), ok);
       }
     }
   }
@@ -495,7 +551,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
         put(G2, va, vb, cur.r, cur.j, oka, okb, it < PR ? it : -1, cur.fx, cur.fy);
         cur = nxt;
       }
-      if (!staged) { cp_async_wait_all(); staged = true; }
+      if (!staged) { staging_done(); staged = true; }
       __syncthreads();
 
       float2 vmask[PR];   // validity of the own pixels as 0 / 1
@@ -634,7 +690,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
       }
     }
 
-    if (!PHOTO && !staged) { cp_async_wait_all(); staged = true; __syncthreads(); }
+    if (!PHOTO && !staged) { staging_done(); staged = true; __syncthreads(); }
 
     // -- P4: epipolar forward + adjoint, d(loss)/d(flow)
     {

@@ -31,16 +31,19 @@ constexpr int PR = MDN_PATCH_ROWS;                           // rows of the per-
 static_assert((PR == 2 || PR == 4) && TH % PR == 0, "patch rows");
 constexpr int FT = (TW / 2) * (TH / PR), FWARPS = FT / 32;   // lane = column pair, warp = row group
 static_assert(TW == 64, "one warp spans the tile width: 32 lanes x 2 columns");
-// halo-2 planes (target / warped image): rows y0-2 .. y0+TH+1, columns x0-2 .. x0+TW+1.  Slot (r, j) lives at
-// OFF2 + r * S2 + j; OFF2 = 2 makes column x0 (j = 2) 16-byte aligned for the cp.async staging and every even j
-// 8-byte aligned for LDS.64.
-constexpr int S2 = TW + 4, R2H = TH + 4, OFF2 = 2, R2P = ((OFF2 + S2 * R2H + 3) / 4) * 4;
+// halo-2 planes (target / warped image / mobile maps): rows y0-2 .. y0+TH+1, columns x0-2 .. x0+TW+1 (W2 = TW + 4 of
+// them).  Slot (r, j) lives at OFF2 + r * S2 + j.  The row pitch S2 = 72 and OFF2 = 2 are what lets ONE TMA box copy
+// (72 x 20 x 1 floats at signed coordinates (x0 - 4, y0 - 2, plane), zero fill outside the tensor, dense rows) land a
+// whole plane at its 128-byte aligned base; they also keep column x0 (j = 2) 16-byte aligned for the cp.async fallback
+// and every even j 8-byte aligned for LDS.64.  R2P * 4 is a multiple of 128.
+constexpr int W2 = TW + 4, S2 = TW + 8, R2H = TH + 4, OFF2 = 2, R2P = S2 * R2H;
+static_assert((R2P * 4) % 128 == 0 && S2 >= OFF2 + W2, "TMA box geometry");
 // halo-1 planes (SSIM adjoint coefficients): window rows y0-1 .. y0+TH, columns x0-1 .. x0+TW
 constexpr int S1 = TW + 4, R1H = TH + 2, R1P = S1 * R1H;
 constexpr int WPR = 3;                                // window rows per SSIM patch (2 columns x WPR rows)
 static_assert((TH + 2) % WPR == 0, "SSIM patches tile the halo-1 region exactly");
 constexpr int NCP = (TW + 2) / 2, NPATCH = NCP * ((TH + 2) / WPR);
-constexpr int RING = S2 * R2H - TW * TH;              // halo slots of the halo-2 region
+constexpr int RING = W2 * R2H - TW * TH;              // halo slots of the halo-2 region
 #ifndef MDN_FUSED_MIN_CTAS
 #define MDN_FUSED_MIN_CTAS 2  // 128 registers / thread, no spills; the larger L1 carve-out of 2 CTAs / SM helps the gather
 #endif
@@ -80,7 +83,14 @@ struct KParams {
   unsigned* ticket;                  // completion ticket of finish_kernel (zeroed by the fused kernel)
   int pack_begin[MDN_MAX_SCALES + 1], pack_blocks[MDN_MAX_SCALES];   // block ranges of ref_pack_kernel
   KScale sc[MDN_MAX_SCALES];
+#ifndef MDN_EMU
+  // TMA descriptors of the staged input planes, per scale: 0 target (w, h, 3 B), 1 / 2 the mobile maps (w, h, B); valid
+  // where tma_ok[s] (row pitch a multiple of 16 bytes); otherwise the tile is staged with cp.async
+  alignas(64) CUtensorMap tmap[MDN_MAX_SCALES][3];
+#endif
+  int tma_ok[MDN_MAX_SCALES];
 };
+static_assert(sizeof(KParams) <= 3800, "kernel parameter space");
 
 // ----------------------------------------------------------------------------------------------- fundamental matrix
 struct FundArgs {
@@ -1125,6 +1135,44 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
       maps |= S.post_map[p] || S.ori_map[p] || S.warped[p] || S.diff[p] || S.valid[p] || S.ssim_map[p];
     }
   K.prefetch_distance = MDN_FUSED_MIN_CTAS * 148;   // one wave of resident CTAs (148 SMs on B200)
+#ifndef MDN_EMU
+  {
+    // TMA descriptors for the input tiles (target image, mobile maps): one box copy per plane instead of ~400 cp.async
+    // with their index arithmetic.  MDN_NO_TMA=1 (environment) keeps the cp.async staging.
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      const char* off = getenv("MDN_NO_TMA");
+      if (off && off[0] == '1') return (EncodeFn) nullptr;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) fn = nullptr;
+      return (EncodeFn)fn;
+    }();
+    const bool need_tgt = (d->flags & (MDN_TERM_PHOTO | MDN_TERM_SMOOTH)) != 0;
+    const bool need_mask = (d->flags & (MDN_TERM_EPIPOLAR | MDN_TERM_SMOOTH | MDN_TERM_CONSIS)) != 0;
+    for (int s = 0; s < d->n_scales; ++s) {
+      KScale& Z = K.sc[s];
+      bool ok = encode != nullptr && (Z.w % 4) == 0;
+      auto make = [&](CUtensorMap* m, const float* base, int planes) {
+        if (!ok || !base) return;
+        const cuuint64_t dims[3] = {(cuuint64_t)Z.w, (cuuint64_t)Z.h, (cuuint64_t)planes};
+        const cuuint64_t strides[2] = {(cuuint64_t)Z.w * 4, (cuuint64_t)Z.w * Z.h * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)S2, (cuuint32_t)R2H, 1}, es[3] = {1, 1, 1};
+        ok = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      };
+      if (need_tgt) make(&K.tmap[s][0], Z.tgt, 3 * d->batch);
+      if (need_mask) {
+        make(&K.tmap[s][1], Z.mob[0], d->batch);
+        if (d->mask_mode != MDN_MASK_SHARED) make(&K.tmap[s][2], Z.mob[1], d->batch);
+      }
+      K.tma_ok[s] = ok ? 1 : 0;
+    }
+  }
+#endif
   if (ev) cudaEventRecord(ev[1], stream);
   const dim3 grid(K.n_tiles), block(FT);
   static bool smem_opt_in = false;   // > 48 KB of dynamic shared memory needs the opt-in attribute (idempotent; set once)
