@@ -516,6 +516,16 @@ MDN_DEV void cp_async_f32x4(float* smem_dst, const float* gsrc, bool pred) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 #endif
 }
+// 8-byte variant (both addresses 8-byte aligned): even image widths that are not a multiple of four (1242)
+MDN_DEV void cp_async_f32x2(float* smem_dst, const float* gsrc, bool pred) {
+#ifdef MDN_EMU
+  for (int i = 0; i < 2; ++i) smem_dst[i] = pred ? gsrc[i] : 0.f;
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+#endif
+}
 // Pulls a 128-byte line into L2 (no register, no stall): used to fetch the NEXT wave's inputs from HBM ahead of time
 MDN_DEV void prefetch_l2(const void* p) {
 #ifndef MDN_EMU

@@ -224,14 +224,25 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
       }
     } else
 #endif
-    if (((w & 3) == 0) & (x0 + TW <= w)) {
-      // interior columns as 16-byte copies (global x0 + 4q and slot OFF2 + 2 + 4q are both 16-byte aligned)
-      for (int i = tid + pl0 * R2H * (TW / 4); i < pl1 * R2H * (TW / 4); i += FT) {
-        const int c = i / (R2H * (TW / 4)), rr = i - c * (R2H * (TW / 4));
-        const int r = rr / (TW / 4), q = rr - r * (TW / 4);
-        const int yy = src_index(c, y0 - 2 + r, h);
-        const bool ok = yy >= 0;
-        cp_async_f32x4(plane_dst(c) + OFF2 + r * S2 + 2 + 4 * q, plane_src(c) + (ok ? yy * w : 0) + x0 + 4 * q, ok);
+    if (((w & 1) == 0) & (x0 + TW <= w)) {
+      if ((w & 3) == 0) {
+        // interior columns as 16-byte copies (global x0 + 4q and slot OFF2 + 2 + 4q are both 16-byte aligned)
+        for (int i = tid + pl0 * R2H * (TW / 4); i < pl1 * R2H * (TW / 4); i += FT) {
+          const int c = i / (R2H * (TW / 4)), rr = i - c * (R2H * (TW / 4));
+          const int r = rr / (TW / 4), q = rr - r * (TW / 4);
+          const int yy = src_index(c, y0 - 2 + r, h);
+          const bool ok = yy >= 0;
+          cp_async_f32x4(plane_dst(c) + OFF2 + r * S2 + 2 + 4 * q, plane_src(c) + (ok ? yy * w : 0) + x0 + 4 * q, ok);
+        }
+      } else {
+        // even width, rows 8-byte aligned only (375 x 1242): 8-byte copies
+        for (int i = tid + pl0 * R2H * (TW / 2); i < pl1 * R2H * (TW / 2); i += FT) {
+          const int c = i / (R2H * (TW / 2)), rr = i - c * (R2H * (TW / 2));
+          const int r = rr / (TW / 2), q = rr - r * (TW / 2);
+          const int yy = src_index(c, y0 - 2 + r, h);
+          const bool ok = yy >= 0;
+          cp_async_f32x2(plane_dst(c) + OFF2 + r * S2 + 2 + 2 * q, plane_src(c) + (ok ? yy * w : 0) + x0 + 2 * q, ok);
+        }
       }
       for (int i = tid + pl0 * R2H * 4; i < pl1 * R2H * 4; i += FT) {
         const int c = i / (R2H * 4), rr = i - c * (R2H * 4);

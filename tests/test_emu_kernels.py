@@ -293,6 +293,7 @@ FUZZ = [  # B, H, W, scales, mode, photometric, ssim, opt overrides, flow std  (
     (3, 38, 4, (0,), "DC", False, True, dict(disable_consisloss=True), 0.05),
     (3, 17, 135, (0,), "T", True, True, {}, 0.05),
     (3, 34, 139, (0,), "SN", False, True, dict(disable_min=True), 0.05),
+    (1, 20, 134, (0,), "T", True, True, {}, 0.05),      # even width, not a multiple of 4: the 8-byte staging path (1242)
 ]
 
 
