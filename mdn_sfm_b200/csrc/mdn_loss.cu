@@ -221,17 +221,37 @@ __global__ void __launch_bounds__(NTHREADS) sn_max_kernel(const KParams P, unsig
   const float* fx = S.flow[pair] + (long long)b * 2 * hw;
   const float* fy = fx + hw;
   unsigned long long best = 0ull;
-  int per = (hw + chunks_per_img - 1) / chunks_per_img;
-  int beg = blockIdx.x * per, end = min(hw, beg + per);
-  for (int i = beg + (int)threadIdx.x; i < end; i += blockDim.x) {
-    int y = i / S.w, x = i - y * S.w;
-    float u = __fadd_rn((float)x, __fmul_rn(S.sx, __ldg(fx + i)));
-    float v = __fadd_rn((float)y, __fmul_rn(S.sy, __ldg(fy + i)));
+  auto consider = [&](int i, int x, int y, float fxv, float fyv) {
+    float u = __fadd_rn((float)x, __fmul_rn(S.sx, fxv));
+    float v = __fadd_rn((float)y, __fmul_rn(S.sy, fyv));
     Epi e = epipolar_distance(Fm, (float)x, (float)y, u, v);
     float ae = fabsf(e.d);
     if (ae == ae) {   // NaNs never win (torch.max would propagate; degenerate input)
       unsigned long long key = ((unsigned long long)__float_as_uint(ae) << 32) | (unsigned)(0xffffffffu - (unsigned)i);
       best = key > best ? key : best;
+    }
+  };
+  if ((S.w & 3) == 0) {
+    // four pixels of one row per trip (16-byte loads, one index division): the pass is bound by the bytes a thread keeps
+    // in flight, not by its arithmetic
+    const int quads = hw >> 2;
+    const int per = (quads + chunks_per_img - 1) / chunks_per_img;
+    const int beg = blockIdx.x * per, end = min(quads, beg + per);
+    const float4* fx4 = reinterpret_cast<const float4*>(fx);
+    const float4* fy4 = reinterpret_cast<const float4*>(fy);
+#pragma unroll 2
+    for (int q = beg + (int)threadIdx.x; q < end; q += blockDim.x) {
+      const float4 a = __ldg(fx4 + q), c = __ldg(fy4 + q);
+      const int i = q << 2, y = i / S.w, x = i - y * S.w;
+      consider(i, x, y, a.x, c.x); consider(i + 1, x + 1, y, a.y, c.y);
+      consider(i + 2, x + 2, y, a.z, c.z); consider(i + 3, x + 3, y, a.w, c.w);
+    }
+  } else {
+    const int per = (hw + chunks_per_img - 1) / chunks_per_img;
+    const int beg = blockIdx.x * per, end = min(hw, beg + per);
+    for (int i = beg + (int)threadIdx.x; i < end; i += blockDim.x) {
+      const int y = i / S.w, x = i - y * S.w;
+      consider(i, x, y, __ldg(fx + i), __ldg(fy + i));
     }
   }
 #pragma unroll
