@@ -151,6 +151,8 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
           if (pl < 3) base = need_tgt ? Z.tgt + ((size_t)b2 * 3 + pl) * hw2 : nullptr;
           else if (pl < 7) { const int q = pl - 3; base = Z.flow[q >> 1] ? Z.flow[q >> 1] + ((size_t)b2 * 2 + (q & 1)) * hw2 : nullptr; }
           else base = (need_mask && Z.mob[pl - 7]) ? Z.mob[pl - 7] + (size_t)b2 * hw2 : nullptr;
+          // planes that arrive by TMA are asynchronous anyway: only the flows (loaded by the gather phase) are worth it
+          if (P.tma_ok[s2] && (pl < 3 || pl >= 7)) base = nullptr;
           if (base) prefetch_l2(base + (size_t)y * Z.w + x);
         }
       }
