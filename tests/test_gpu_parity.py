@@ -242,3 +242,17 @@ def test_image_pyramid_on_gpu_matches_torchvision():
     pyramid.add_pyramid_levels(dev_in, [0, -1, 1], [0, 1, 2, 3])
     b = loss(dev_in, [-1, 1], mv(flows), mv(mobiles), None, [0, 1, 2, 3], mv(cams))[1]["loss"]
     assert float(b) == pytest.approx(float(a), rel=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 6, 8), (1, 17, 20), (2, 16, 64), (1, 40, 132), (3, 21, 76), (1, 2, 4)])
+def test_tma_staging_on_images_smaller_than_the_box(shape):
+    """The TMA box (72 x 20) is larger than these images / their edge tiles: out-of-tensor elements must arrive as zeros and
+    the reflected ring must be patched from inside the tile -- every mode family against the oracle on the same GPU."""
+    B, H, W = shape
+    for mode, photo in (("T", True), ("SN", True), ("TG", False)):
+        if mode == "TG" and (H < 8 or W < 8):
+            continue        # (the reference's Gaussian weight table needs at least 8 pixels over its 4 scales)
+        opt, batch = common.make(B, H, W, scales=(0,), seed=31, flow_std=0.1)
+        got = common.product_run(opt, batch, mode, photo, True, DEV, pose_grad=True)
+        common.compare(common.oracle_run(opt, batch, mode, photo, True, DEV, pose_grad=True), got, photo)
