@@ -307,3 +307,26 @@ def test_odd_tiny_and_ragged_shapes_all_modes(case):
     with emulated():
         got = common.product_run(opt, batch, mode, photo, ssim, "cpu", pose_grad=True)
         common.compare(ref, got, photo, tie_px=common.TIE_PX if mode in ("DS", "DC") else 0)
+
+
+def test_epipolar_statistics_match_the_reference_quantiles():
+    """per-sample quantiles of |e| over batches == loss_utils.compute_quantiles (:197-202) of the oracle."""
+    from mdn_sfm_b200 import layers, statistics
+    opt, batch = common.make(2, 24, 72, scales=(0,), seed=19, flow_std=0.05)
+    inputs, flows, _, cams, _ = batch
+    B, h, w = 2, 24, 72
+    pix = restate.create_coords(B, h, w)
+    ones = torch.ones(B, 1, h, w)
+    p1 = torch.cat([pix, ones], 1).view(B, 3, -1)
+    q = torch.linspace(0, 1, 50)
+    with emulated() as lib:
+        st = statistics.EpipolarStatistics(num_quantile=50, library=lib, arith="cpu")
+        st.update(flows, inputs[("inv_K", 0)], cams)
+        st.update(flows, inputs[("inv_K", 0)], cams)
+        per, thr = st.result()
+    assert per.shape == (2, 50, 4) and thr.shape == (8,)
+    sf = layers.get_scale_factor(B, h, w)
+    for k, i in enumerate((-1, 1)):
+        ref = restate.compute_quantiles(flows, cams[i], inputs[("inv_K", 0)], p1, pix, ones, sf, q, i, B)
+        got = torch.from_numpy(per[k, :, :B])
+        assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), i

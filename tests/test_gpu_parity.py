@@ -256,3 +256,28 @@ def test_tma_staging_on_images_smaller_than_the_box(shape):
         opt, batch = common.make(B, H, W, scales=(0,), seed=31, flow_std=0.1)
         got = common.product_run(opt, batch, mode, photo, True, DEV, pose_grad=True)
         common.compare(common.oracle_run(opt, batch, mode, photo, True, DEV, pose_grad=True), got, photo)
+
+
+@pytest.mark.gpu
+def test_epipolar_statistics_on_gpu():
+    """SURVEY 8f-N4 on the GPU (poses into the maps-only launch): quantiles of |e| == the oracle's compute_quantiles run on the
+    same GPU, and the thresholds come out ordered."""
+    from oracle import restate
+    from mdn_sfm_b200 import layers, statistics
+    opt, batch = common.make(4, 192, 640, scales=(0,), seed=19, flow_std=0.02)
+    inputs, flows, _, cams, _ = batch
+    mv = lambda d: {k: v.to(DEV) for k, v in d.items()}
+    inputs, flows, cams = mv(inputs), mv(flows), mv(cams)
+    B, h, w = 4, 192, 640
+    st = statistics.EpipolarStatistics(num_quantile=100)
+    st.update(flows, inputs[("inv_K", 0)], cams)
+    per, thr = st.result()
+    pix = restate.create_coords(B, h, w, DEV)
+    ones = torch.ones(B, 1, h, w, device=DEV)
+    p1 = torch.cat([pix, ones], 1).view(B, 3, -1)
+    q = torch.linspace(0, 1, 100, device=DEV)
+    sf = layers.get_scale_factor(B, h, w).to(DEV)
+    for k, i in enumerate((-1, 1)):
+        ref = restate.compute_quantiles(flows, cams[i], inputs[("inv_K", 0)], p1, pix, ones, sf, q, i, B).cpu()
+        assert float((torch.from_numpy(per[k]) - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), i
+    assert (thr[1:] >= thr[:-1]).all()
