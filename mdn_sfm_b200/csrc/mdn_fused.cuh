@@ -4,16 +4,19 @@
 // processed by the same CTA so that d(loss)/d(mobile) is written exactly once.  A thread owns a 2-column x PR-row
 // patch of pixels (lane = column pair, warp = row group): every global access is an 8-byte vector, every shared
 // memory access an LDS.64 / STS.64, and the arithmetic of the two columns is packed fp32x2 (FFMA2 / FADD2 / FMUL2).
-// Per-row loops are ROLLED: the kernel is issue- and instruction-fetch-bound, so code size is kept near 2.5 k
-// instructions; state that must survive a rolled loop lives in thread-private shared memory (sm.D) or rotates
-// through a register ring.
+// The channel / patch loops are ROLLED: the kernel is issue- and instruction-fetch-bound, so code size is kept near 5 k
+// instructions; state that must survive a rolled loop lives in thread-private shared memory (sm.D, sm.FL).
 //
-// Shared memory (73 KB -> 3 CTAs per SM):
+// Shared memory (95 KB; two CTAs per SM inside the 196 KB carve-out):
 //   sT [3][R2P]      target image, tile + 2-pixel halo, reflection padded (slot -1 holds pixel 1, slot n holds n-2)
+//   sM [2][R2P]      the two mobile maps, same layout, zero outside the image
+//                    (sT and sM arrive by TMA: one 72 x 20 box per plane on an mbarrier; cp.async where the row pitch
+//                    is not a multiple of 16 bytes)
 //   sW [3][R2P]      warped source image of the current pair, same layout
 //   sQ [3][R1P]      SSIM adjoint coefficient planes (A, B, C) of the current pair AND channel, tile + 1-pixel halo
 //   sD [6][PR][FT]   thread-private float2 slots: d(warped_c)/d(ix), d(warped_c)/d(iy) of the own pixels
-// Per pair:
+//   sFL [PR][2][FT]  thread-private float2 slots: the flow of the own pixels (P1 -> P4)
+// Per pair (with the poses given, nine threads first rebuild F = K^-T [t]x R K^-1 of the (pair, sample)):
 //   P1  one rolled loop over pixel PAIRS: the thread's PR own pairs, then its share of the halo ring.  flow ->
 //       sampling coordinates -> bilinear gather of the 3 source channels (gather_pair) -> sW; derivatives -> sD
 //   per channel c (rolled):
@@ -22,8 +25,9 @@
 //         (ssim_window2); writes the adjoint planes of channel c
 //     P3  the thread's own pixels: separable 3x3 adjoint gather of the three planes (packed), L1 term, chain rule
 //         to d(loss)/d(ix, iy)
-//   P4  rolled over rows: epipolar distance, post-processing, masked sums and their adjoints; d(loss)/d(flow)
-// then the tail (rolled over rows): smoothness + consistency + routing of d/dmask through the min; block reduction.
+//   P4  both rows of the patch: epipolar distance, post-processing, masked sums and their adjoints; d(loss)/d(flow)
+// then the tail: smoothness + consistency + routing of d/dmask through the min; block reduction.  P4 and the tail read
+// nothing from global memory.
 
 struct FusedSmem {
   float* T;      // [3][R2P]

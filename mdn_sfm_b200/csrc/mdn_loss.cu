@@ -2,11 +2,16 @@
 //
 // Kernel inventory
 //   sn_max_kernel        per-sample max / first arg-max of |e| (SN post-processing pre-pass, loss_utils.py:96)
-//   fused_tile_kernel    ONE launch over every (scale, sample, 32x16 tile): epipolar map + post-processing +
-//                        masked reductions, bilinear flow warp, SSIM + L1, smoothness, consistency, min mask,
-//                        forward values AND gradients (upstream gradient 1), per-tile partial sums
-//   finish_kernel        deterministic second stage: per-sample sums -> d/dF, SN arg-max fix-up, loss scalars
+//   ref_pack_kernel      source images NCHW -> float4 per pixel for the warp gather (photometric term)
+//   fused_tile_kernel    ONE launch over every (scale, sample, 64x16 tile): fundamental matrix from the pose, TMA-staged
+//                        input tiles, epipolar map + post-processing + masked reductions, bilinear flow warp, SSIM + L1,
+//                        smoothness, consistency, min mask, forward values AND gradients (upstream gradient 1),
+//                        per-tile partial sums
+//   finish_kernel        deterministic second stage, one block per sample: tile sums -> d/dF, SN arg-max fix-up, pose
+//                        adjoint; last block -> loss scalars
 //   scale_grads_kernel   backward for an upstream gradient != 1 (exits immediately when it is 1)
+//   instance_union / instance_resize_{weights,h,v}_kernel   DS / DC instance masks and fp32 image pyramids (torchvision
+//                        antialiased Resize replayed)
 //   small standalone kernels for the individually exported reference functions
 //
 // All of it is bandwidth/latency-bound stencil + gather work: no tensor cores by design.
