@@ -481,6 +481,29 @@ def run_ours(args):
         ms2, _ = timed_steps(dev2, n2, max(3, args.warmup // 4), 0.3)
         second = {"flow": FLOW_DESC[other], "value": B * n2 / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2 / n2, "steps": n2}
 
+    # ---- the same step when the data side hands the source frames over already packed (the pyramid
+    # producer writes (r, g, b, -) per pixel, ('color_packed', i, s)): no repack kernel inside the step.  Reported beside
+    # the headline, never instead of it -- the headline takes the reference's NCHW inputs.
+    packed_run = None
+    if not args.no_second_flow and world == 1:
+        try:
+            from mdn_sfm_b200 import pyramid as pyr
+            pk_sets = []
+            for s in dev_sets[:2]:
+                inp = dict(s[0])
+                for i in ids:
+                    for sc in scales:
+                        lvl = inp.pop(("color", i, sc))
+                        inp[("color_packed", i, sc)] = pyr.image_pyramid(lvl, [tuple(lvl.shape[-2:])], packed=True)[0]
+                pk_sets.append((inp,) + tuple(s[1:]))
+            n3 = max(50, args.steps // 4)
+            ms3, _ = timed_steps(pk_sets, n3, max(3, args.warmup // 4), 0.3)
+            packed_run = {"inputs": "source frames as ('color_packed', i, s) from mdn_sfm_b200.pyramid (no ref_pack_kernel in the step)",
+                          "value": B * n3 / (ms3 * 1e-3), "unit": "frames/s", "ms_per_step": ms3 / n3, "steps": n3}
+            del pk_sets
+        except Exception as e:
+            packed_run = {"error": repr(e)}
+
     # ---- BASELINE configs[2]: the whole train step (stand-in nets on cuDNN -> TG loss -> backward -> DDP -> clip -> Adam)
     train = None
     if not args.no_train_step:
@@ -520,7 +543,7 @@ def run_ours(args):
                 "launches_per_step": "mdn::ref_pack_kernel, mdn::fused_tile_kernel (builds the fundamental matrices from the poses), "
                                      "mdn::finish_kernel (loss scalars, d/dF, pose adjoint), mdn::scale_grads_kernel; "
                                      "(+ torch's ones_like fill for the upstream gradient)",
-                "other_flow": second, "train_step": train,
+                "other_flow": second, "packed_sources": packed_run, "train_step": train,
                 "roofline": roofline, "cpu_baseline": cpu_base}
         print(json.dumps(line), flush=True)
     if world > 1:

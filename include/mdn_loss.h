@@ -98,6 +98,10 @@ typedef struct MdnScale {
   float* diff[MDN_MAX_PAIRS];          /* (B,3,h,w) |tgt - warped| * valid ("diffs")                          */
   uint8_t* valid[MDN_MAX_PAIRS];       /* (B,1,h,w) validity mask, one channel ("valids" is its 3x repeat)    */
   float* ssim_map[MDN_MAX_PAIRS];      /* (B,3,h,w) SSIM distance map                                         */
+  /* optional: the source image already in the layout the warp gather reads -- (B,h,w,4) fp32, (r, g, b, unused) per
+   * pixel, as mdn_pack_rgb / mdn_image_pyramid_packed write it.  When given, ref[p] is not read (may be NULL) and the
+   * call launches no repack kernel for that image. */
+  const float* ref_packed[MDN_MAX_PAIRS];
 } MdnScale;
 
 typedef struct MdnLossDesc {
@@ -253,6 +257,13 @@ MDN_API size_t mdn_instance_mask_resize_workspace_bytes(int32_t batch, int32_t i
 MDN_API int mdn_image_pyramid(const float* src, int32_t planes, int32_t in_h, int32_t in_w, float* const* dst,
                               const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* workspace,
                               size_t workspace_bytes, void* stream);
+
+/* The same with every level written as (planes / 3, out_h, out_w, 4): one (r, g, b, unused) float4 per pixel -- the
+ * `ref_packed` input of MdnScale.  planes must be a multiple of 3 (B x RGB).  Output sizes equal to the input size are
+ * allowed (a pure repack of the full-resolution frame). */
+MDN_API int mdn_image_pyramid_packed(const float* src, int32_t planes, int32_t in_h, int32_t in_w, float* const* dst,
+                                     const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* workspace,
+                                     size_t workspace_bytes, void* stream);
 
 /* binary_image (utils.py:100-103): out = x >= threshold ? 1 : 0 */
 MDN_API int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream);

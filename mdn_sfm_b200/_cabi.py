@@ -30,7 +30,7 @@ class MdnScale(C.Structure):
                 ("weight", _P), ("inst", _P),
                 ("g_flow", _PAIR), ("g_mob", _PAIR), ("g_fmat", _PAIR),
                 ("post_map", _PAIR), ("ori_map", _PAIR), ("warped", _PAIR), ("diff", _PAIR), ("valid", _PAIR),
-                ("ssim_map", _PAIR)]
+                ("ssim_map", _PAIR), ("ref_packed", _PAIR)]
 
 
 class MdnLossDesc(C.Structure):
@@ -48,7 +48,7 @@ EXPORTS = ("mdn_version", "mdn_last_error_string", "mdn_loss_workspace_bytes", "
            "mdn_fundamental_fwd", "mdn_fundamental_bwd",
            "mdn_epipolar_points_fwd", "mdn_epipolar_points_bwd", "mdn_epipolar_points_workspace_bytes",
            "mdn_flow_warp_fwd", "mdn_flow_warp_bwd", "mdn_ssim_fwd", "mdn_ssim_bwd", "mdn_binary_image",
-           "mdn_instance_mask_union", "mdn_instance_mask_resize", "mdn_instance_mask_resize_workspace_bytes", "mdn_image_pyramid")
+           "mdn_instance_mask_union", "mdn_instance_mask_resize", "mdn_instance_mask_resize_workspace_bytes", "mdn_image_pyramid", "mdn_image_pyramid_packed")
 
 
 class Library:
@@ -82,6 +82,7 @@ class Library:
             "mdn_instance_mask_union": (C.c_int, [C.POINTER(_P), C.POINTER(i32), _P, i32, i64, _P]),
             "mdn_instance_mask_resize": (C.c_int, [_P, i32, i32, i32, C.POINTER(_P), C.POINTER(i32), C.POINTER(i32), i32, _P, sz, _P]),
             "mdn_image_pyramid": (C.c_int, [_P, i32, i32, i32, C.POINTER(_P), C.POINTER(i32), C.POINTER(i32), i32, _P, sz, _P]),
+            "mdn_image_pyramid_packed": (C.c_int, [_P, i32, i32, i32, C.POINTER(_P), C.POINTER(i32), C.POINTER(i32), i32, _P, sz, _P]),
             "mdn_instance_mask_resize_workspace_bytes": (sz, [i32, i32, i32, C.POINTER(i32), C.POINTER(i32), i32]),
         }
         for name, (res, args) in sig.items():
@@ -133,7 +134,7 @@ class FusedCall:
     """Fills an MdnLossDesc from tensors and keeps them alive for the duration of the (asynchronous) call."""
 
     PAIR_FIELDS = ("ref", "flow", "mob", "fmat", "g_flow", "g_mob", "g_fmat", "post_map", "ori_map", "warped", "diff",
-                   "valid", "ssim_map")
+                   "valid", "ssim_map", "ref_packed")
     ONE_FIELDS = ("tgt", "weight", "inst")
 
     def __init__(self, *, batch, n_pairs, post, mask_mode, flags, threshold=0.0, alpha=0.0, w_d2_sim=0.0, w_e=1.0,

@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(NTHREADS) ref_pack_kernel(const __grid_constan
   const int job = rem / P.pack_blocks[s], blk = rem - job * P.pack_blocks[s];
   const int pair = job / P.batch, b = job - pair * P.batch;
   const int hw = S.h * S.w;
+  if (!S.ref[pair]) return;                       // this image came already packed (MdnScale.ref_packed)
   const float* src = S.ref[pair] + (size_t)b * 3 * hw;
   float4* dst = S.refp[pair] + (size_t)b * hw;
   // PACK_PX pixels per thread, one pixel per thread and instruction: every warp load is one 128-byte line of a plane,
@@ -755,6 +756,7 @@ struct ResizeArgs {
   int row_begin[MDN_MAX_SCALES + 1];   // first blockIdx.y of each output size, horizontal pass (row groups)
   int vrow_begin[MDN_MAX_SCALES + 1];  // ... vertical pass (output rows)
   int n_out, batch, ih, iw;
+  int packed;                          // fp32 outputs as one (r, g, b, 0) float4 per pixel (planes = images x 3)
 };
 
 MDN_DEV float aa_tri(float x) { x = x < 0.f ? -x : x; return x < 1.f ? __fsub_rn(1.f, x) : 0.f; }
@@ -942,6 +944,12 @@ __global__ void __launch_bounds__(128) instance_resize_v_kernel(const __grid_con
 #pragma unroll
   for (int r = 0; r < AA_VROWS; ++r) {
     if (oy0 + r >= oh) continue;
+    if (A.packed) {      // plane b = image * 3 + channel -> component `channel` of the pixel's float4
+      float* dst = reinterpret_cast<float*>(A.dst[k]) + (((long long)(b / 3) * oh + oy0 + r) * ow + ox) * 4 + (b % 3);
+      *dst = out[r];
+      if (b % 3 == 2) dst[1] = 0.f;
+      continue;
+    }
     TOut* dst = reinterpret_cast<TOut*>(A.dst[k]) + ((long long)b * oh + oy0 + r) * ow + ox;
     if (sizeof(TOut) == 1) *dst = (TOut)rintf(out[r]);      // torch.round, then the cast back to integers
     else *dst = (TOut)out[r];
@@ -1012,7 +1020,7 @@ static int check_desc(const MdnLossDesc* d) {
       if (d->mask_mode != MDN_MASK_SHARED) NEED(S.mob[1], "mob[1]");   // MIN / OWN / consistency read both maps
     }
     for (int p = 0; p < d->n_pairs; ++p) {
-      if (f & MDN_TERM_PHOTO) NEED(S.ref[p], "ref");
+      if (f & MDN_TERM_PHOTO) { if (S.ref_packed[p]) OPT(S.ref_packed[p], "ref_packed"); else NEED(S.ref[p], "ref"); }
       if (f & (MDN_TERM_PHOTO | MDN_TERM_EPIPOLAR)) NEED(S.flow[p], "flow");
       if ((f & MDN_TERM_EPIPOLAR) && !poses) { if (!S.fmat[p]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "fmat"); }
       OPT(S.g_flow[p], "g_flow"); OPT(S.g_mob[p], "g_mob"); OPT(S.post_map[p], "post_map"); OPT(S.ori_map[p], "ori_map");
@@ -1123,12 +1131,17 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
       Z.valid[p] = S.valid[p]; Z.ssim_map[p] = S.ssim_map[p];
     }
   }
+  bool any_repack = false;
   {   // carve the repacked source images out of the workspace
     float4* rp = (float4*)(ws + L.refpack);
     for (int s = 0; s < d->n_scales; ++s)
       for (int p = 0; p < d->n_pairs; ++p) {
         K.sc[s].refp[p] = (d->flags & MDN_TERM_PHOTO) ? rp : nullptr;
         if (d->flags & MDN_TERM_PHOTO) rp += (size_t)d->batch * K.sc[s].h * K.sc[s].w;
+        if ((d->flags & MDN_TERM_PHOTO) && d->scale[s].ref_packed[p]) {     // the caller's packed image: no repack
+          K.sc[s].refp[p] = reinterpret_cast<float4*>(const_cast<float*>(d->scale[s].ref_packed[p]));
+          K.sc[s].ref[p] = nullptr;
+        } else any_repack = true;
       }
   }
   // the completion ticket is zeroed by the fused kernel itself; only the SN pre-pass needs a cleared buffer
@@ -1141,7 +1154,7 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
   }
   const bool photo = (d->flags & MDN_TERM_PHOTO) != 0;
   if (ev) cudaEventRecord(ev[0], stream);
-  if (photo) {
+  if (photo && any_repack) {
     int nblk = 0;
     for (int s = 0; s < d->n_scales; ++s) {
       K.pack_begin[s] = nblk;
@@ -1433,13 +1446,14 @@ extern "C" MDN_API size_t mdn_instance_mask_resize_workspace_bytes(int32_t batch
 
 template <typename TIn, typename TOut>
 static int launch_resize(const TIn* src, int32_t batch, int32_t in_h, int32_t in_w, TOut* const* dst, const int32_t* out_h,
-                         const int32_t* out_w, int32_t n_out, void* workspace, size_t workspace_bytes, void* stream) {
+                         const int32_t* out_w, int32_t n_out, void* workspace, size_t workspace_bytes, void* stream,
+                         bool packed = false) {
   if (!src || !dst) return fail(MDN_ERR_NULL_POINTER, "src / dst is NULL");
   int rc = check_resize_sizes(batch, in_h, in_w, out_h, out_w, n_out);
   if (rc != MDN_OK) return rc;
   ResizeArgs A;
   memset(&A, 0, sizeof(A));
-  A.n_out = n_out; A.batch = batch; A.ih = in_h; A.iw = in_w;
+  A.n_out = n_out; A.batch = batch; A.ih = in_h; A.iw = in_w; A.packed = packed ? 1 : 0;
   const ResizeWs L = resize_ws_layout(batch, in_h, in_w, out_h, out_w, n_out);
   if (!workspace || workspace_bytes < L.total) return fail(MDN_ERR_WORKSPACE, "workspace too small");
   if (!aligned16(workspace)) return fail(MDN_ERR_MISALIGNED, "%s is not 16-byte aligned", "workspace");
@@ -1480,6 +1494,13 @@ extern "C" MDN_API int mdn_image_pyramid(const float* src, int32_t planes, int32
                                          const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* workspace,
                                          size_t workspace_bytes, void* stream) {
   return launch_resize<float, float>(src, planes, in_h, in_w, dst, out_h, out_w, n_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" MDN_API int mdn_image_pyramid_packed(const float* src, int32_t planes, int32_t in_h, int32_t in_w, float* const* dst,
+                                                const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* workspace,
+                                                size_t workspace_bytes, void* stream) {
+  if (planes % 3) return fail(MDN_ERR_BAD_SHAPE, "planes must be a multiple of 3 (B x RGB)");
+  return launch_resize<float, float>(src, planes, in_h, in_w, dst, out_h, out_w, n_out, workspace, workspace_bytes, stream, true);
 }
 
 extern "C" MDN_API int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream) {

@@ -41,6 +41,7 @@ class ScaleData:
     scale_div: float
     tgt: Optional[torch.Tensor] = None
     ref: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
+    ref_packed: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])   # (B,h,w,4): no repack kernel
     flow: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
     mob: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
     fmat: List[Optional[torch.Tensor]] = field(default_factory=lambda: [None, None])
@@ -128,7 +129,7 @@ def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None
                     bufs = [torch.empty((B, 3, h, w), dtype=torch.float32, device=dev) for _ in range(cfg.n_pairs)]
                 maps[name] = bufs
                 extra[name] = bufs
-        call.add_scale(h, w, S.flow_sx, S.flow_sy, S.scale_div, tgt=S.tgt, ref=S.ref, flow=S.flow, mob=S.mob,
+        call.add_scale(h, w, S.flow_sx, S.flow_sy, S.scale_div, tgt=S.tgt, ref=S.ref, ref_packed=S.ref_packed, flow=S.flow, mob=S.mob,
                        fmat=S.fmat, weight=S.weight, inst=S.inst, g_flow=g["flow"], g_mob=g["mob"], g_fmat=g["fmat"],
                        **extra)
         grads.append(g)

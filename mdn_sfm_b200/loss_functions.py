@@ -283,7 +283,13 @@ class Loss(nn.Module):
                 if F_all is not None:
                     S.fmat[p] = F_all[k, p]
                 if self.photometric:
-                    S.ref[p] = _c(inputs[("color", i, s)], "source image")
+                    pk = inputs.get(("color_packed", i, s)) if hasattr(inputs, "get") else None
+                    if pk is not None:      # the pyramid producer already wrote (r, g, b, -) per pixel: no repack launch
+                        if tuple(pk.shape) != (b, h, w, 4):
+                            raise ValueError("('color_packed', %d, %d) must be (B,h,w,4)" % (i, s))
+                        S.ref_packed[p] = _c(pk, "packed source image")
+                    else:
+                        S.ref[p] = _c(inputs[("color", i, s)], "source image")
             if self.opt.disable_min and len(ids) == 2:   # pair p is masked with its own frame's map
                 S.mob[0] = _c(mobile[("mobile", ids[0], s)], "mobile mask")
                 S.mob[1] = _c(mobile[("mobile", ids[1], s)], "mobile mask")
@@ -332,7 +338,7 @@ class Loss(nn.Module):
                 return cache
             with torch.no_grad():
                 S0 = data[0]
-                S = fused.ScaleData(S0.height, S0.width, S0.flow_sx, S0.flow_sy, 1.0, tgt=S0.tgt, ref=S0.ref,
+                S = fused.ScaleData(S0.height, S0.width, S0.flow_sx, S0.flow_sy, 1.0, tgt=S0.tgt, ref=S0.ref, ref_packed=S0.ref_packed,
                                     flow=[None if f is None else f.detach() for f in S0.flow],
                                     mob=[m.detach() for m in S0.mob],
                                     fmat=[None if f is None else f.detach() for f in S0.fmat],

@@ -14,13 +14,28 @@ import torch
 from . import _cabi
 
 
-def image_pyramid(img, sizes, library=None):
+def image_pyramid(img, sizes, library=None, packed=False):
     """img (B,C,H,W) fp32 CUDA tensor -> [Resize(size)(img) for size in sizes] in one call (three launches).
 
-    Sizes equal to (H, W) return `img` itself, like torchvision does."""
+    Sizes equal to (H, W) return `img` itself, like torchvision does.  packed=True (C == 3): every level comes as
+    (B,h,w,4), one (r, g, b, 0) float4 per pixel -- the layout the warp gather of the loss reads, handed to `Loss.forward`
+    as inputs[("color_packed", i, s)] so that it launches no repack kernel; (H, W) itself is then a pure repack."""
     library = library or _cabi.lib()
     img = _cabi.check_tensor(img, what="img").contiguous()
     B, Cn, H, W = img.shape
+    if packed:
+        if Cn != 3:
+            raise ValueError("packed pyramids need 3 channels")
+        outs = [torch.empty((B, int(h), int(w), 4), dtype=torch.float32, device=img.device) for h, w in sizes]
+        for k0 in range(0, len(outs), _cabi.MAX_SCALES):
+            chunk = outs[k0:k0 + _cabi.MAX_SCALES]
+            oh = (C.c_int32 * len(chunk))(*[o.shape[1] for o in chunk])
+            ow = (C.c_int32 * len(chunk))(*[o.shape[2] for o in chunk])
+            nbytes = library.cdll.mdn_instance_mask_resize_workspace_bytes(B * 3, H, W, oh, ow, len(chunk))
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=img.device)
+            library.call("mdn_image_pyramid_packed", img.data_ptr(), B * 3, H, W, _cabi.ptr_array(chunk), oh, ow, len(chunk),
+                         ws.data_ptr(), nbytes, _cabi.stream_ptr(img))
+        return outs
     outs = [img if (int(h), int(w)) == (H, W) else torch.empty((B, Cn, int(h), int(w)), dtype=torch.float32, device=img.device)
             for h, w in sizes]
     todo = [o for o in outs if o is not img]
@@ -35,11 +50,18 @@ def image_pyramid(img, sizes, library=None):
     return outs
 
 
-def add_pyramid_levels(inputs, frame_ids, scales, library=None):
-    """Fills inputs[("color", i, s)] for s >= 1 from inputs[("color", i, 0)] (what the dataset's per-scale Resize produced)."""
+def add_pyramid_levels(inputs, frame_ids, scales, library=None, packed_sources=False):
+    """Fills inputs[("color", i, s)] for s >= 1 from inputs[("color", i, 0)] (what the dataset's per-scale Resize produced).
+
+    packed_sources=True: the source frames (i != 0) get inputs[("color_packed", i, s)] for EVERY scale instead -- the loss
+    then runs without its repack kernel (the NCHW levels of the source frames are not needed by it)."""
     for i in frame_ids:
         full = inputs[("color", i, 0)]
         H, W = full.shape[-2:]
+        if packed_sources and i != 0:
+            for s, t in zip(scales, image_pyramid(full, [(H // 2 ** s, W // 2 ** s) for s in scales], library, packed=True)):
+                inputs[("color_packed", i, s)] = t
+            continue
         lower = [s for s in scales if s != 0]
         for s, t in zip(lower, image_pyramid(full, [(H // 2 ** s, W // 2 ** s) for s in lower], library)):
             inputs[("color", i, s)] = t

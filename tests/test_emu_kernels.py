@@ -330,3 +330,29 @@ def test_epipolar_statistics_match_the_reference_quantiles():
         ref = restate.compute_quantiles(flows, cams[i], inputs[("inv_K", 0)], p1, pix, ones, sf, q, i, B)
         got = torch.from_numpy(per[k, :, :B])
         assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), i
+
+
+def test_packed_source_pyramid_feeds_the_loss_without_a_repack():
+    """SURVEY 8f-N3, second half: source frames handed over as ('color_packed', i, s) -- (B,h,w,4), what
+    mdn_image_pyramid_packed writes -- give bit-identical losses, gradients and maps to the NCHW form (which the call
+    repacks itself), and the packed pyramid made from the full-resolution frame equals torchvision's Resize."""
+    from torchvision.transforms import Resize
+    from mdn_sfm_b200 import pyramid
+    from mdn_sfm_b200.loss_functions import Loss
+    opt, batch = common.make(2, 32, 80, scales=(0, 1), seed=29, flow_std=0.08)
+    inputs, flows, mobiles, cams, _ = batch
+    with emulated() as lib:
+        a = common.product_run(opt, batch, "T", True, True, "cpu", pose_grad=True, arith="cuda")
+        packed = dict(inputs)
+        for i in (-1, 1):
+            for s in (0, 1):
+                lvl = inputs[("color", i, s)]
+                packed[("color_packed", i, s)] = pyramid.image_pyramid(lvl, [tuple(lvl.shape[-2:])], lib, packed=True)[0]
+                del packed[("color", i, s)]          # the NCHW source levels are not read any more
+        b = common.product_run(opt, (packed, flows, mobiles, cams, None), "T", True, True, "cpu", pose_grad=True, arith="cuda")
+        common.assert_identical_runs(a, b, maps=("epipolars", "epipolar_ori", "warps", "diffs"))
+        pk = pyramid.image_pyramid(inputs[("color", 1, 0)], [(32, 80), (16, 40), (9, 21)], lib, packed=True)
+    for t, sz in zip(pk, [(32, 80), (16, 40), (9, 21)]):
+        ref = Resize(sz)(inputs[("color", 1, 0)]).permute(0, 2, 3, 1)
+        assert tuple(t.shape) == (2,) + sz + (4,)
+        assert float((t[..., :3] - ref).abs().max()) <= 2e-6 * float(ref.abs().max()) and float(t[..., 3].abs().max()) == 0.0

@@ -281,3 +281,26 @@ def test_epipolar_statistics_on_gpu():
         ref = restate.compute_quantiles(flows, cams[i], inputs[("inv_K", 0)], p1, pix, ones, sf, q, i, B).cpu()
         assert float((torch.from_numpy(per[k]) - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), i
     assert (thr[1:] >= thr[:-1]).all()
+
+
+@pytest.mark.gpu
+def test_packed_source_pyramid_on_gpu():
+    """SURVEY 8f-N3, second half, on the GPU at configs[0]'s shape: ('color_packed', i, s) sources == NCHW sources bit for
+    bit (the call's own repack is skipped), and the packed pyramid equals torchvision's Resize of the fp32 frame."""
+    from torchvision.transforms import Resize
+    from mdn_sfm_b200 import pyramid
+    opt, batch = common.make(4, 192, 640, seed=29)
+    inputs, flows, mobiles, cams, _ = batch
+    a = common.product_run(opt, batch, "T", True, True, DEV, pose_grad=True)
+    packed = {k: v for k, v in inputs.items()}
+    for i in (-1, 1):
+        for s in range(4):
+            lvl = packed.pop(("color", i, s)).to(DEV)
+            packed[("color_packed", i, s)] = pyramid.image_pyramid(lvl, [tuple(lvl.shape[-2:])], packed=True)[0]
+    b = common.product_run(opt, (packed, flows, mobiles, cams, None), "T", True, True, DEV, pose_grad=True)
+    common.assert_identical_runs(a, b, maps=("epipolars", "epipolar_ori", "warps", "diffs"))
+    sizes = [(192, 640), (96, 320), (48, 160), (24, 80)]
+    pk = pyramid.image_pyramid(inputs[("color", 1, 0)].to(DEV), sizes, packed=True)
+    for t, sz in zip(pk, sizes):
+        ref = Resize(sz)(inputs[("color", 1, 0)]).permute(0, 2, 3, 1)
+        assert float((t[..., :3].cpu() - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
