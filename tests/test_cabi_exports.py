@@ -65,3 +65,32 @@ def test_error_codes():
         lib.call("mdn_ssim_fwd", None, None, None, 1, 4, 4, None)
     with pytest.raises(RuntimeError, match="shape"):
         lib.call("mdn_flow_warp_bwd", 16, 16, 16, 16, 1, 3, 1, 8, 0, None)
+
+
+def test_error_codes_of_the_data_side_entry_points():
+    """Argument checks of the instance-mask / pyramid entry points and of the pose inputs of mdn_loss_fused return status
+    codes before any launch (no GPU needed)."""
+    import ctypes as C
+    from mdn_sfm_b200 import _cabi, build
+    lib = _cabi.Library(build.build())
+    one = (C.c_int32 * 1)(8)
+    with pytest.raises(RuntimeError, match="NULL"):
+        lib.call("mdn_instance_mask_union", None, None, None, 1, 16, None)
+    with pytest.raises(RuntimeError, match="out of range"):
+        lib.call("mdn_instance_mask_resize", 16, 0, 8, 8, (C.c_void_p * 1)(16), one, one, 1, 16, 1 << 20, None)
+    with pytest.raises(RuntimeError, match="workspace too small"):
+        lib.call("mdn_image_pyramid", 16, 3, 8, 8, (C.c_void_p * 1)(16), one, one, 1, 16, 0, None)
+    with pytest.raises(RuntimeError, match="multiple of 3"):
+        lib.call("mdn_image_pyramid_packed", 16, 4, 8, 8, (C.c_void_p * 1)(16), one, one, 1, 16, 1 << 20, None)
+    assert lib.cdll.mdn_instance_mask_resize_workspace_bytes(2, 8, 8, one, one, 1) > 0
+    assert lib.cdll.mdn_instance_mask_resize_workspace_bytes(0, 8, 8, one, one, 1) == 0
+    # poses: every pair's pose or none, and the inverse intrinsics of every scale
+    call = _cabi.FusedCall(batch=1, n_pairs=2, post=1, mask_mode=2, flags=1)
+    call.desc.n_scales = 1
+    call.desc.scale[0].height, call.desc.scale[0].width = 8, 8
+    call.desc.cam[0] = 16
+    assert lib.cdll.mdn_loss_workspace_bytes(C.byref(call.desc)) == 0
+    assert b"every pair" in lib.cdll.mdn_last_error_string()
+    call.desc.cam[1] = 16
+    assert lib.cdll.mdn_loss_workspace_bytes(C.byref(call.desc)) == 0
+    assert b"inv_K" in lib.cdll.mdn_last_error_string()
