@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(ROOT, "mdn_sfm_b200", "csrc", "mdn_loss.cu")
-DEPS = [SRC, os.path.join(ROOT, "mdn_sfm_b200", "csrc", "mdn_common.cuh"), os.path.join(os.path.join(ROOT, "mdn_sfm_b200"), "csrc", "mdn_fused.cuh"), os.path.join(ROOT, "include", "mdn_loss.h"),
+DEPS = [SRC, os.path.join(ROOT, "mdn_sfm_b200", "csrc", "mdn_common.cuh"), os.path.join(os.path.join(ROOT, "mdn_sfm_b200"), "csrc", "mdn_fused.cuh"), os.path.join(ROOT, "mdn_sfm_b200", "csrc", "mdn_resize.cuh"), os.path.join(ROOT, "include", "mdn_loss.h"),
         os.path.join(HERE, "cuda_emu.h")]
 OUT = os.path.join(HERE, "_build", "libmdn_loss_emu.so")
 
