@@ -304,3 +304,27 @@ def test_packed_source_pyramid_on_gpu():
     for t, sz in zip(pk, sizes):
         ref = Resize(sz)(inputs[("color", 1, 0)]).permute(0, 2, 3, 1)
         assert float((t[..., :3].cpu() - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+
+
+@pytest.mark.gpu
+def test_graphed_loss_step_replays_on_refreshed_inputs():
+    """mdn_sfm_b200.graphs.GraphedLossStep: the captured forward + backward, replayed after the static tensors were
+    refreshed in place, equals the eager step on the same values bit for bit (losses and every gradient)."""
+    from mdn_sfm_b200.graphs import GraphedLossStep
+    from mdn_sfm_b200.loss_functions import Loss
+    opt, b1 = common.make(2, 64, 128, seed=3)
+    _, b2 = common.make(2, 64, 128, seed=4)
+    dev = lambda d, g=False: {k: v.to(DEV).requires_grad_(g) for k, v in d.items()}
+    inputs, flows, mobiles, cams = dev(b1[0]), dev(b1[1], True), dev(b1[2], True), dev(b1[3], True)
+    loss = Loss(opt, no_ssim=False, mode="TG", photometric=True)
+    step = GraphedLossStep(loss, inputs, [-1, 1], flows, mobiles, None, [0, 1, 2, 3], cams)
+    with torch.no_grad():        # refresh every static tensor with the second batch
+        for dst, src in ((inputs, b2[0]), (flows, b2[1]), (mobiles, b2[2]), (cams, b2[3])):
+            for k in dst:
+                dst[k].copy_(src[k])
+    got = step.replay()
+    ref = common.product_run(opt, b2, "TG", True, True, DEV, pose_grad=True)
+    assert torch.equal(got["loss"], ref[1]["loss"].detach())
+    for mine, theirs in ((flows, ref[2]), (mobiles, ref[3]), (cams, ref[4])):
+        for k in mine:
+            assert torch.equal(mine[k].grad, theirs[k].grad), k
