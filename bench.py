@@ -432,9 +432,12 @@ def run_ours(args):
     from mdn_sfm_b200 import pyramid
     from mdn_sfm_b200.staging import BatchStager
     up_inputs = lambda d: {kk: v for kk, v in d.items() if not (kk[0] == "color" and kk[2] != 0)}
-    stager = BatchStager([up_inputs(host_sets[0][0])] + list(host_sets[0][1:4]), dev, n_buffers=len(host_sets))
-    for k, hs in enumerate(host_sets):
-        stager.fill(k, [up_inputs(hs[0])] + list(hs[1:4]))   # untimed: producing the batch in pinned memory is the loader's part
+    # DS / DC: the Detectron2-style boolean instance masks of the batch cross PCIe every step too
+    up_inst = lambda inst: {("inst", j): d["instances"].pred_masks for j, d in enumerate(inst)} if inst is not None else {}
+    stager = BatchStager([up_inputs(host_sets[0][0])] + list(host_sets[0][1:4]) + [up_inst(host_sets[0][4])], dev,
+                         n_buffers=len(host_sets))
+    for k, hs in enumerate(host_sets):   # untimed: producing the batch in pinned memory is the loader's part
+        stager.fill(k, [up_inputs(hs[0])] + list(hs[1:4]) + [up_inst(hs[4])])
     h2d_bytes = stager.nbytes
     leaf = lambda d: {kk: v.detach().requires_grad_(True) for kk, v in d.items()}
 
@@ -448,7 +451,8 @@ def run_ours(args):
             stager.wait(i)
             v = stager._dev_views[i % stager.n_buffers]
             inputs_i = pyramid.add_pyramid_levels(dict(v[0]), [0] + ids, list(scales))
-            loss = step_on((inputs_i, leaf(v[1]), leaf(v[2]), leaf(v[3]), dev_sets[i % len(dev_sets)][4]))
+            inst_i = [{"instances": synthetic.SyntheticInstances(v[4][("inst", j)])} for j in range(len(v[4]))] if with_inst else None
+            loss = step_on((inputs_i, leaf(v[1]), leaf(v[2]), leaf(v[3]), inst_i))
             stager.release(i)
             host_loss.copy_(loss.detach(), non_blocking=True)
 
