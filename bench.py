@@ -481,6 +481,64 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
+    # ---- the same end-to-end step with the frames crossing PCIe as the loader holds them: uint8 HWC, normalised on the device
+    # (mdn_normalize_u8 = the dataset's ArrayToTensor + Normalize, bit-identical).  Reported beside `e2e`, which uploads the
+    # fp32 tensors the reference's loader produces.
+    e2e_u8 = None
+    if not args.no_second_flow:
+        try:
+            to_u8 = lambda x: ((x * 0.225 + 0.45) * 255).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+            u8_part = lambda d: {kk: to_u8(v) for kk, v in d.items() if kk[0] == "color" and kk[2] == 0}
+            rest_part = lambda d: {kk: v for kk, v in d.items() if kk[0] != "color"}
+            st8 = BatchStager([u8_part(host_sets[0][0]), rest_part(host_sets[0][0])] + list(host_sets[0][1:4]) + [up_inst(host_sets[0][4])],
+                              dev, n_buffers=len(host_sets))
+            for k, hs in enumerate(host_sets):
+                st8.fill(k, [u8_part(hs[0]), rest_part(hs[0])] + list(hs[1:4]) + [up_inst(hs[4])])
+
+            def e2e8_run(n, start_event=None):
+                if start_event is not None:
+                    st8.copy_stream.wait_event(start_event)
+                st8.upload(0)
+                for i in range(n):
+                    if i + 1 < n:
+                        st8.upload(i + 1)
+                    st8.wait(i)
+                    v = st8._dev_views[i % st8.n_buffers]
+                    inputs_i = dict(v[1])
+                    for kk, fr in v[0].items():
+                        inputs_i[kk] = pyramid.frames_from_u8(fr)
+                    pyramid.add_pyramid_levels(inputs_i, [0] + ids, list(scales))
+                    inst_i = [{"instances": synthetic.SyntheticInstances(v[5][("inst", j)])} for j in range(len(v[5]))] if with_inst else None
+                    loss = step_on((inputs_i, leaf(v[2]), leaf(v[3]), leaf(v[4]), inst_i))
+                    st8.release(i)
+                    host_loss.copy_(loss.detach(), non_blocking=True)
+
+            e2e8_run(6)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            runs8 = []
+            for _ in range(2):
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                e2e8_run(n_e2e, f0)
+                f1.record()
+                torch.cuda.synchronize()
+                ms_run = f0.elapsed_time(f1)
+                if world > 1:
+                    t = torch.tensor([ms_run], device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms_run = float(t.item())
+                runs8.append(ms_run)
+            e2e_u8 = {"value": world * B * n_e2e / (min(runs8) * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": st8.nbytes,
+                      "d2h_bytes_per_step": 4, "steps": n_e2e, "ms_per_step": min(runs8) / n_e2e,
+                      "runs_ms_per_step": [r / n_e2e for r in runs8],
+                      "path": "as e2e, but the three full-resolution frames are uploaded as (B,H,W,3) uint8 and normalised on the "
+                              "device (mdn_sfm_b200.pyramid.frames_from_u8)"}
+            del st8
+        except Exception as e:
+            e2e_u8 = {"error": repr(e)}
+
     # ---- the same workload on the other flow kind (short run, reported beside the headline, never instead of it)
     second = None
     if not args.no_second_flow and world == 1:
@@ -553,7 +611,7 @@ def run_ours(args):
                 "launches_per_step": "mdn::ref_pack_kernel, mdn::fused_tile_kernel (builds the fundamental matrices from the poses), "
                                      "mdn::finish_kernel (loss scalars, d/dF, pose adjoint), mdn::scale_grads_kernel; "
                                      "(+ torch's ones_like fill for the upstream gradient)",
-                "other_flow": second, "packed_sources": packed_run, "train_step": train,
+                "e2e_u8_frames": e2e_u8, "other_flow": second, "packed_sources": packed_run, "train_step": train,
                 "roofline": roofline, "cpu_baseline": cpu_base}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -265,6 +265,15 @@ MDN_API int mdn_image_pyramid_packed(const float* src, int32_t planes, int32_t i
                                      const int32_t* out_h, const int32_t* out_w, int32_t n_out, void* workspace,
                                      size_t workspace_bytes, void* stream);
 
+/*
+ * The dataset's ArrayToTensor + Normalize on the device (datasets/custom_transforms.py:72-80,103-112, mono_dataset.py:51-52,
+ * 112): src (B,H,W,3) uint8 frames as the loader holds them, dst (B,3,H,W) fp32 = ((x / 255) - mean[c]) / std[c], every
+ * operation rounded on its own like the CPU tensor ops of the reference.  `mean`, `std` are HOST arrays of 3 floats.
+ * With it, frames cross PCIe as bytes (a quarter of the fp32 size).
+ */
+MDN_API int mdn_normalize_u8(const uint8_t* src, float* dst, int32_t batch, int32_t height, int32_t width,
+                             const float* mean, const float* stdv, void* stream);
+
 /* binary_image (utils.py:100-103): out = x >= threshold ? 1 : 0 */
 MDN_API int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream);
 

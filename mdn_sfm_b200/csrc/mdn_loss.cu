@@ -1249,6 +1249,18 @@ extern "C" MDN_API int mdn_image_pyramid_packed(const float* src, int32_t planes
   return launch_resize<float, float>(src, planes, in_h, in_w, dst, out_h, out_w, n_out, workspace, workspace_bytes, stream, true);
 }
 
+extern "C" MDN_API int mdn_normalize_u8(const uint8_t* src, float* dst, int32_t batch, int32_t height, int32_t width,
+                                        const float* mean, const float* stdv, void* stream) {
+  if (!src || !dst || !mean || !stdv) return fail(MDN_ERR_NULL_POINTER, "src / dst / mean / std is NULL");
+  if (batch < 1 || height < 1 || width < 1) return fail(MDN_ERR_BAD_SHAPE, "batch / height / width out of range");
+  NormArgs A;
+  for (int c = 0; c < 3; ++c) { A.mean[c] = mean[c]; A.stdv[c] = stdv[c]; }
+  const long long hw = (long long)height * width;
+  MDN_LAUNCH(normalize_u8_kernel, dim3(blocks_for(hw, 148 * 4), batch), dim3(NTHREADS), 0, (cudaStream_t)stream, src, dst, hw, A);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
 extern "C" MDN_API int mdn_binary_image(const float* x, float* out, int64_t n, float threshold, void* stream) {
   if (!x || !out) return fail(MDN_ERR_NULL_POINTER, "x / out is NULL");
   if (n < 1) return MDN_OK;

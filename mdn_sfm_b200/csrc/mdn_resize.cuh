@@ -258,3 +258,22 @@ __global__ void __launch_bounds__(128) instance_resize_v_kernel(const __grid_con
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------- uint8 frames -> fp32 NCHW
+// ArrayToTensor + Normalize of the dataset (datasets/custom_transforms.py:72-80, 103-112): HWC uint8 -> CHW,
+// x.float() / 255, then (t - mean) / std per channel, each op rounded on its own like the CPU tensor ops the dataset runs.
+struct NormArgs { float mean[3], stdv[3]; };
+
+__global__ void __launch_bounds__(NTHREADS) normalize_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long hw,
+                                                                const NormArgs A) {
+  const int b = blockIdx.y;
+  const uint8_t* s = src + (long long)b * hw * 3;
+  float* d = dst + (long long)b * hw * 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float t = __fdiv_rn((float)__ldg(s + i * 3 + c), 255.f);
+      d[(long long)c * hw + i] = __fdiv_rn(__fsub_rn(t, A.mean[c]), A.stdv[c]);
+    }
+  }
+}

@@ -14,6 +14,21 @@ import torch
 from . import _cabi
 
 
+def frames_from_u8(frames_u8, mean=(0.45, 0.45, 0.45), std=(0.225, 0.225, 0.225), library=None):
+    """(B,H,W,3) uint8 CUDA frames, as the loader holds them -> (B,3,H,W) fp32 normalised frames: the dataset's
+    ArrayToTensor + Normalize (custom_transforms.py:72-80,103-112; mean / std of mono_dataset.py:51-52) on the device,
+    bit-identical to the CPU ops.  Frames then cross PCIe as bytes."""
+    library = library or _cabi.lib()
+    src = _cabi.check_tensor(frames_u8, dtype=torch.uint8, what="frames_u8").contiguous()
+    if src.dim() != 4 or src.shape[-1] != 3:
+        raise ValueError("frames_u8 must be (B,H,W,3)")
+    B, H, W, _ = src.shape
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=src.device)
+    m, s = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    library.call("mdn_normalize_u8", src.data_ptr(), out.data_ptr(), B, H, W, m, s, _cabi.stream_ptr(src))
+    return out
+
+
 def image_pyramid(img, sizes, library=None, packed=False):
     """img (B,C,H,W) fp32 CUDA tensor -> [Resize(size)(img) for size in sizes] in one call (three launches).
 

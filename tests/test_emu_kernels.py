@@ -356,3 +356,16 @@ def test_packed_source_pyramid_feeds_the_loss_without_a_repack():
         ref = Resize(sz)(inputs[("color", 1, 0)]).permute(0, 2, 3, 1)
         assert tuple(t.shape) == (2,) + sz + (4,)
         assert float((t[..., :3] - ref).abs().max()) <= 2e-6 * float(ref.abs().max()) and float(t[..., 3].abs().max()) == 0.0
+
+
+def test_uint8_frames_normalised_on_the_device_equal_the_dataset_transforms():
+    """mdn_normalize_u8 == ArrayToTensor + Normalize of the reference's dataset (custom_transforms.py:72-80,103-112), bit for bit."""
+    from mdn_sfm_b200 import pyramid
+    g = torch.Generator().manual_seed(2)
+    u8 = torch.randint(0, 256, (2, 13, 37, 3), dtype=torch.uint8, generator=g)
+    ref = u8.permute(0, 3, 1, 2).float() / 255
+    for t, m, s in zip(ref.unbind(1), (0.45, 0.45, 0.45), (0.225, 0.225, 0.225)):
+        t.sub_(m).div_(s)
+    with emulated() as lib:
+        got = pyramid.frames_from_u8(u8, library=lib)
+    assert torch.equal(got, ref.contiguous())

@@ -328,3 +328,15 @@ def test_graphed_loss_step_replays_on_refreshed_inputs():
     for mine, theirs in ((flows, ref[2]), (mobiles, ref[3]), (cams, ref[4])):
         for k in mine:
             assert torch.equal(mine[k].grad, theirs[k].grad), k
+
+
+@pytest.mark.gpu
+def test_uint8_frames_on_gpu_equal_the_dataset_transforms():
+    """mdn_normalize_u8 on the GPU == ArrayToTensor + Normalize of the reference's dataset run on the CPU, bit for bit."""
+    from mdn_sfm_b200 import pyramid
+    g = torch.Generator().manual_seed(2)
+    u8 = torch.randint(0, 256, (3, 192, 640, 3), dtype=torch.uint8, generator=g)
+    ref = u8.permute(0, 3, 1, 2).float() / 255
+    for t, m, s in zip(ref.unbind(1), (0.45, 0.45, 0.45), (0.225, 0.225, 0.225)):
+        t.sub_(m).div_(s)
+    assert torch.equal(pyramid.frames_from_u8(u8.to(DEV)).cpu(), ref.contiguous())
