@@ -118,6 +118,12 @@ def check_tensor(t, dtype=torch.float32, what="tensor"):
     return t
 
 
+def on_device(t):
+    """Context manager that makes `t`'s CUDA device current (a no-op for host tensors: the emulated test build)."""
+    import contextlib
+    return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
+
+
 def stream_ptr(ref_tensor):
     return torch.cuda.current_stream(ref_tensor.device).cuda_stream if ref_tensor.is_cuda else 0
 
@@ -193,8 +199,9 @@ class FusedCall:
 
     def run(self, library, loss_out, workspace, stream):
         self.keep += [loss_out, workspace]
-        library.call("mdn_loss_fused", C.byref(self.desc), loss_out.data_ptr(), workspace.data_ptr(),
-                     workspace.numel() * workspace.element_size(), stream)
+        with on_device(loss_out):      # launches go to the tensors' device even when it is not the current one
+            library.call("mdn_loss_fused", C.byref(self.desc), loss_out.data_ptr(), workspace.data_ptr(),
+                         workspace.numel() * workspace.element_size(), stream)
 
     def profile(self, library, loss_out, workspace, stream):
         """Blocking measurement aid: returns (repack_ms, fused_kernel_ms, finish_ms) of one call (mdn_loss_fused_profile)."""
@@ -204,4 +211,5 @@ class FusedCall:
         return float(ms[0]), float(ms[1]), float(ms[2])
 
     def scale_grads(self, library, g, applied, stream):
-        library.call("mdn_loss_scale_grads", C.byref(self.desc), g.data_ptr(), applied.data_ptr(), stream)
+        with on_device(applied):
+            library.call("mdn_loss_scale_grads", C.byref(self.desc), g.data_ptr(), applied.data_ptr(), stream)

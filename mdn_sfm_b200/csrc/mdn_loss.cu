@@ -959,14 +959,20 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
 #endif
   if (ev) cudaEventRecord(ev[1], stream);
   const dim3 grid(K.n_tiles), block(FT);
-  static bool smem_opt_in = false;   // > 48 KB of dynamic shared memory needs the opt-in attribute (idempotent; set once)
-  if (!smem_opt_in) {
+  // > 48 KB of dynamic shared memory needs the opt-in attribute, per device (idempotent; set once per device)
+  static unsigned long long smem_opt_in_devices = 0ull;
+  int dev_index = 0;
+#ifndef MDN_EMU
+  cudaGetDevice(&dev_index);
+#endif
+  const unsigned long long dev_bit = 1ull << (dev_index & 63);
+  if (!(smem_opt_in_devices & dev_bit)) {
     const int bytes = (int)(fused_smem_floats(true) * sizeof(float));
     cudaFuncSetAttribute(fused_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(fused_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(fused_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(fused_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    smem_opt_in = true;
+    smem_opt_in_devices |= dev_bit;
   }
   if (photo && maps) { auto kfn = fused_tile_kernel<true, true>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
   else if (photo) { auto kfn = fused_tile_kernel<true, false>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }

@@ -340,3 +340,15 @@ def test_uint8_frames_on_gpu_equal_the_dataset_transforms():
     for t, m, s in zip(ref.unbind(1), (0.45, 0.45, 0.45), (0.225, 0.225, 0.225)):
         t.sub_(m).div_(s)
     assert torch.equal(pyramid.frames_from_u8(u8.to(DEV)).cpu(), ref.contiguous())
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process():
+    """The loss launched on cuda:1 while cuda:0 is current (and after cuda:0 was used) equals the cuda:0 result."""
+    opt, batch = common.make(2, 64, 128, seed=5)
+    a = common.product_run(opt, batch, "T", True, True, "cuda:0", pose_grad=True)
+    b = common.product_run(opt, batch, "T", True, True, "cuda:1", pose_grad=True)
+    assert torch.equal(a[1]["loss"].cpu(), b[1]["loss"].cpu())
+    for k in a[2]:
+        assert torch.equal(a[2][k].grad.cpu(), b[2][k].grad.cpu()), k
