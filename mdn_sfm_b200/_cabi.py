@@ -92,8 +92,19 @@ class Library:
         if d.mdn_version() != ABI_VERSION:
             raise RuntimeError("libmdn_loss ABI version mismatch")
 
-    def call(self, name, *args):
-        rc = getattr(self.cdll, name)(*args)
+    def call(self, name, *args, dev=None):
+        """Calls an entry point and raises on a non-zero status.  `dev` (a tensor or a device) names the CUDA device the
+        launches belong to: it is made current for the duration of the call, so a stream of that device is never used
+        from another current device (every call site passes one of the tensors it hands over)."""
+        if dev is not None:
+            dev = getattr(dev, "device", dev)
+            if getattr(dev, "type", None) == "cuda":
+                with torch.cuda.device(dev):
+                    rc = getattr(self.cdll, name)(*args)
+            else:
+                rc = getattr(self.cdll, name)(*args)
+        else:
+            rc = getattr(self.cdll, name)(*args)
         if rc != 0:
             raise RuntimeError("%s failed (%d): %s" % (name, rc, self.cdll.mdn_last_error_string().decode()))
 
@@ -199,17 +210,16 @@ class FusedCall:
 
     def run(self, library, loss_out, workspace, stream):
         self.keep += [loss_out, workspace]
-        with on_device(loss_out):      # launches go to the tensors' device even when it is not the current one
-            library.call("mdn_loss_fused", C.byref(self.desc), loss_out.data_ptr(), workspace.data_ptr(),
-                         workspace.numel() * workspace.element_size(), stream)
+        # launches go to the tensors' device even when it is not the current one
+        library.call("mdn_loss_fused", C.byref(self.desc), loss_out.data_ptr(), workspace.data_ptr(),
+                     workspace.numel() * workspace.element_size(), stream, dev=loss_out)
 
     def profile(self, library, loss_out, workspace, stream):
         """Blocking measurement aid: returns (repack_ms, fused_kernel_ms, finish_ms) of one call (mdn_loss_fused_profile)."""
         ms = (C.c_float * 3)()
         library.call("mdn_loss_fused_profile", C.byref(self.desc), loss_out.data_ptr(), workspace.data_ptr(),
-                     workspace.numel() * workspace.element_size(), stream, ms)
+                     workspace.numel() * workspace.element_size(), stream, ms, dev=loss_out)
         return float(ms[0]), float(ms[1]), float(ms[2])
 
     def scale_grads(self, library, g, applied, stream):
-        with on_device(applied):
-            library.call("mdn_loss_scale_grads", C.byref(self.desc), g.data_ptr(), applied.data_ptr(), stream)
+        library.call("mdn_loss_scale_grads", C.byref(self.desc), g.data_ptr(), applied.data_ptr(), stream, dev=applied)

@@ -19,6 +19,7 @@
 #include "../../include/mdn_loss.h"
 
 #include <algorithm>
+#include <atomic>
 #include <stdio.h>
 #include <string.h>
 
@@ -959,20 +960,28 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
 #endif
   if (ev) cudaEventRecord(ev[1], stream);
   const dim3 grid(K.n_tiles), block(FT);
-  // > 48 KB of dynamic shared memory needs the opt-in attribute, per device (idempotent; set once per device)
-  static unsigned long long smem_opt_in_devices = 0ull;
+  // > 48 KB of dynamic shared memory needs the opt-in attribute, per device (idempotent; set once per device).  The bit is
+  // published only after every attribute call succeeded, with an atomic OR: concurrent first calls from two host threads
+  // may both set the attributes (harmless) but never see a half-initialised device.
+  static std::atomic<unsigned long long> smem_opt_in_devices{0ull};
   int dev_index = 0;
 #ifndef MDN_EMU
   cudaGetDevice(&dev_index);
 #endif
   const unsigned long long dev_bit = 1ull << (dev_index & 63);
-  if (!(smem_opt_in_devices & dev_bit)) {
+  if (!(smem_opt_in_devices.load(std::memory_order_acquire) & dev_bit)) {
     const int bytes = (int)(fused_smem_floats(true) * sizeof(float));
-    cudaFuncSetAttribute(fused_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(fused_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(fused_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(fused_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    smem_opt_in_devices |= dev_bit;
+    cudaError_t a = cudaFuncSetAttribute(fused_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (a == cudaSuccess) a = cudaFuncSetAttribute(fused_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (a == cudaSuccess) a = cudaFuncSetAttribute(fused_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (a == cudaSuccess) a = cudaFuncSetAttribute(fused_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (a != cudaSuccess) {
+      cudaGetLastError();
+      snprintf(g_err, sizeof(g_err), "the fused kernel needs %d bytes of opt-in shared memory per block on device %d: %s", bytes, dev_index,
+               cudaGetErrorString(a));
+      return MDN_ERR_CUDA;
+    }
+    smem_opt_in_devices.fetch_or(dev_bit, std::memory_order_release);
   }
   if (photo && maps) { auto kfn = fused_tile_kernel<true, true>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
   else if (photo) { auto kfn = fused_tile_kernel<true, false>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }

@@ -122,7 +122,8 @@ class LossModule(nn.Module):
     def _tg_weight(self, h, w, device):
         ws = self.weights
         if ws is None:
-            ws = self.weights = gauss_distance_weight(len(getattr(self.options, "scales", [0, 1, 2, 3])),
+            # one table per pyramid level 0 .. max(scales), so that opt.scales = [0, 2] finds its level-2 table
+            ws = self.weights = gauss_distance_weight(max(getattr(self.options, "scales", [0, 1, 2, 3])) + 1,
                                                       self.options.height, self.options.width)
         for k, t in enumerate(ws):
             if tuple(t.shape[-2:]) == (h, w):
@@ -131,9 +132,9 @@ class LossModule(nn.Module):
                 return t.reshape(h, w).contiguous()
         raise ValueError("no Gaussian weight table of size %dx%d (tables are built from opt.height/width)" % (h, w))
 
-    def _epi_extras(self, post, bits, h, w, device, instances_info):
+    def _epi_extras(self, post, bits, h, w, device, instances_info, batch=None):
         weight = self._tg_weight(h, w, device) if post == fused.POST_TG else None
-        inst = instance_mask_u8(instances_info, (h, w), device, self._library) if bits & (OPT_INST_MASK | OPT_CROSS_ENT) else None
+        inst = instance_mask_u8(instances_info, (h, w), device, self._library, batch) if bits & (OPT_INST_MASK | OPT_CROSS_ENT) else None
         return weight, inst
 
     def _frames(self, inputs, frame_ids, flow, mobiles, instances_info, cam_T_cam, scale, mask_mode):
@@ -149,7 +150,7 @@ class LossModule(nn.Module):
             S.flow[p] = _c(flow[("flow", i, scale)], "flow")
             S.mob[p] = _c(mobiles[p], "mobile mask")
             S.fmat[p] = fused.fundamental_matrix(inv_K, cam_T_cam[i][:, :3, :3], cam_T_cam[i][:, :3, -1]).contiguous()
-        S.weight, S.inst = self._epi_extras(post, bits, h, w, tgt.device, instances_info)
+        S.weight, S.inst = self._epi_extras(post, bits, h, w, tgt.device, instances_info, b)
         thr = getattr(o, "threshold", None) if post != fused.POST_SN else None
         # two launches so that losses["epip"] and losses["smooth"] each own their gradient (the reference
         # keeps them as separate differentiable accumulators); Loss.forward uses a single launch instead
@@ -200,7 +201,7 @@ class LossModule(nn.Module):
         S = fused.ScaleData(h, w, 1.0, 1.0, 1.0)
         S.flow[0], S.mob[0] = flow_map, mobile_mask
         S.fmat[0] = fused.fundamental_matrix(inv_K[:, :3, :3], ro, tran).contiguous()
-        S.weight, S.inst = self._epi_extras(post, bits, h, w, flow_map.device, instances_info)
+        S.weight, S.inst = self._epi_extras(post, bits, h, w, flow_map.device, instances_info, b)
         o = self.options
         cfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=1, post=post, mask_mode=MASK_SHARED, flags=bits,
                                 threshold=getattr(o, "threshold", None) if post != fused.POST_SN else None,
@@ -290,16 +291,20 @@ class Loss(nn.Module):
                         S.ref_packed[p] = _c(pk, "packed source image")
                     else:
                         S.ref[p] = _c(inputs[("color", i, s)], "source image")
-            if self.opt.disable_min and len(ids) == 2:   # pair p is masked with its own frame's map
+            if self.opt.disable_min:   # pair p is masked with its own frame's map (loss_functions.py:183-186)
+                # one source frame: its own map masks the pair; the other frame's map is only the consistency term's
+                # second operand ((p - r)^2 is symmetric, each map receives its own gradient)
+                second = ids[1] if len(ids) == 2 else -ids[0]
                 S.mob[0] = _c(mobile[("mobile", ids[0], s)], "mobile mask")
-                S.mob[1] = _c(mobile[("mobile", ids[1], s)], "mobile mask")
+                S.mob[1] = _c(mobile[("mobile", second, s)], "mobile mask")
             else:                                         # torch.cat([m(-1), m(+1)]).min(1): this order breaks ties
                 S.mob[0] = _c(mobile[("mobile", -1, s)], "mobile mask")
                 S.mob[1] = _c(mobile[("mobile", 1, s)], "mobile mask")
             S.weight, _ = lm._epi_extras(post, 0, h, w, tgt.device, None)
             data.append(S)
         if bits & (OPT_INST_MASK | OPT_CROSS_ENT):   # DS / DC: the masks of every pyramid level from one pass (two launches)
-            insts = instance_masks_u8(instances_info, [(S.height, S.width) for S in data], data[0].tgt.device, self._library)
+            insts = instance_masks_u8(instances_info, [(S.height, S.width) for S in data], data[0].tgt.device, self._library,
+                                      data[0].tgt.shape[0])
             for S, m in zip(data, insts):
                 S.inst = m
         return data, F_all, poses

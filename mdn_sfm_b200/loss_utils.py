@@ -58,13 +58,14 @@ def _pred_masks(instances_info):
     return [instances_info.pred_masks]
 
 
-def instance_masks_u8(instances_info, sizes, device, library=None):
+def instance_masks_u8(instances_info, sizes, device, library=None, batch=None):
     """One-channel uint8 {0,1} instance masks at every size in `sizes` (a list of (h, w)), from ONE pass over the
     Detectron2 masks: `get_batch_instance_mask` (loss_utils.py:102-124: union of the instances of each sample) and the
     `Resize(size)` of loss_utils.py:73-75 / :135-137 (torchvision bilinear + antialias on the integer mask, rounded
     back to integers) run as two kernels -- `mdn_instance_mask_union`, `mdn_instance_mask_resize` -- instead of the
     reference's per-(frame, scale) int64 (B,3,375,1242) tensors.  The three channels upstream carries are identical;
-    one is kept.  -> list of (B, h, w) uint8 tensors."""
+    one is kept.  -> list of (B, h, w) uint8 tensors.  `batch`: the batch size of the maps the masks will meet; a single
+    bare `Instances` (trainer.py:494, evaluate_mix.py:63) then broadcasts over it like the reference's (1,3,H,W) mask."""
     import ctypes as C
     library = library or _cabi.lib()
     masks = []
@@ -81,7 +82,7 @@ def instance_masks_u8(instances_info, sizes, device, library=None):
     union = torch.empty((B, H, W), dtype=torch.uint8, device=masks[0].device)
     stream = _cabi.stream_ptr(union)
     counts = (C.c_int32 * B)(*[int(m.shape[0]) if m.dim() == 3 else 1 for m in masks])
-    library.call("mdn_instance_mask_union", _cabi.ptr_array(masks), counts, union.data_ptr(), B, H * W, stream)
+    library.call("mdn_instance_mask_union", _cabi.ptr_array(masks), counts, union.data_ptr(), B, H * W, stream, dev=union)
     outs = [torch.empty((B, int(h), int(w)), dtype=torch.uint8, device=union.device) for h, w in sizes]
     for k0 in range(0, len(outs), _cabi.MAX_SCALES):
         chunk = outs[k0:k0 + _cabi.MAX_SCALES]
@@ -90,13 +91,17 @@ def instance_masks_u8(instances_info, sizes, device, library=None):
         nbytes = library.cdll.mdn_instance_mask_resize_workspace_bytes(B, H, W, oh, ow, len(chunk))
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=union.device)
         library.call("mdn_instance_mask_resize", union.data_ptr(), B, H, W, _cabi.ptr_array(chunk), oh, ow, len(chunk),
-                     ws.data_ptr(), nbytes, stream)
+                     ws.data_ptr(), nbytes, stream, dev=union)
+    if batch is not None and B == 1 and batch > 1:
+        outs = [o.expand(batch, -1, -1).contiguous() for o in outs]
+    elif batch is not None and B != batch:
+        raise ValueError("instances_info holds %d samples, the maps %d" % (B, batch))
     return outs
 
 
-def instance_mask_u8(instances_info, size, device, library=None):
+def instance_mask_u8(instances_info, size, device, library=None, batch=None):
     """Single-size form of instance_masks_u8."""
-    return instance_masks_u8(instances_info, [tuple(size)], device, library)[0]
+    return instance_masks_u8(instances_info, [tuple(size)], device, library, batch)[0]
 
 
 def detectron2_similarity_loss(mobile_mask, instances_info):

@@ -22,7 +22,7 @@ class FlowWarpFn(torch.autograd.Function):
         grid = torch.empty((B, h, w, 2), dtype=torch.float32, device=flow.device)
         valid = torch.empty((B, h, w), dtype=torch.uint8, device=flow.device)
         library.call("mdn_flow_warp_fwd", _cabi.ptr(ref) if want_warp else None, flow.data_ptr(), _cabi.ptr(warped),
-                     grid.data_ptr(), valid.data_ptr(), B, C, h, w, int(warp_flags), _cabi.stream_ptr(flow))
+                     grid.data_ptr(), valid.data_ptr(), B, C, h, w, int(warp_flags), _cabi.stream_ptr(flow), dev=flow)
         ctx.library, ctx.warp_flags = library, int(warp_flags)
         ctx.save_for_backward(ref, flow)
         ctx.mark_non_differentiable(grid, valid)
@@ -40,7 +40,7 @@ class FlowWarpFn(torch.autograd.Function):
         B, C, h, w = ref.shape
         g_flow = torch.empty_like(flow)
         ctx.library.call("mdn_flow_warp_bwd", ref.data_ptr(), flow.data_ptr(), g_warped.contiguous().data_ptr(),
-                         g_flow.data_ptr(), B, C, h, w, ctx.warp_flags, _cabi.stream_ptr(flow))
+                         g_flow.data_ptr(), B, C, h, w, ctx.warp_flags, _cabi.stream_ptr(flow), dev=flow)
         return None, g_flow, None, None, None
 
 
@@ -53,7 +53,7 @@ class EpipolarPointsFn(torch.autograd.Function):
         B, _, n = p1.shape
         out = torch.empty((B, 1, n), dtype=torch.float32, device=p1.device)
         library.call("mdn_epipolar_points_fwd", p1.data_ptr(), p2.data_ptr(), fmat.data_ptr(), out.data_ptr(), B, n,
-                     _cabi.stream_ptr(p1))
+                     _cabi.stream_ptr(p1), dev=p1)
         ctx.library = library
         ctx.save_for_backward(p1, p2, fmat)
         return out
@@ -69,7 +69,7 @@ class EpipolarPointsFn(torch.autograd.Function):
         nbytes = lib.cdll.mdn_epipolar_points_workspace_bytes(B, n)
         ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=p1.device)
         lib.call("mdn_epipolar_points_bwd", p1.data_ptr(), p2.data_ptr(), fmat.data_ptr(), g_out.contiguous().data_ptr(),
-                 _cabi.ptr(g1), _cabi.ptr(g2), _cabi.ptr(gF), B, n, ws.data_ptr(), nbytes, _cabi.stream_ptr(p1))
+                 _cabi.ptr(g1), _cabi.ptr(g2), _cabi.ptr(gF), B, n, ws.data_ptr(), nbytes, _cabi.stream_ptr(p1), dev=p1)
         return g1, g2, gF, None
 
 
@@ -82,7 +82,7 @@ class SsimFn(torch.autograd.Function):
         out = torch.empty_like(x)
         h, w = x.shape[-2:]
         planes = x.numel() // (h * w)
-        library.call("mdn_ssim_fwd", x.data_ptr(), y.data_ptr(), out.data_ptr(), planes, h, w, _cabi.stream_ptr(x))
+        library.call("mdn_ssim_fwd", x.data_ptr(), y.data_ptr(), out.data_ptr(), planes, h, w, _cabi.stream_ptr(x), dev=x)
         ctx.library = library
         ctx.save_for_backward(x, y)
         return out
@@ -95,7 +95,7 @@ class SsimFn(torch.autograd.Function):
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
         ctx.library.call("mdn_ssim_bwd", x.data_ptr(), y.data_ptr(), g.contiguous().data_ptr(), _cabi.ptr(gx),
-                         _cabi.ptr(gy), planes, h, w, _cabi.stream_ptr(x))
+                         _cabi.ptr(gy), planes, h, w, _cabi.stream_ptr(x), dev=x)
         return gx, gy, None
 
 
@@ -112,7 +112,7 @@ class FundamentalFn(torch.autograd.Function):
         B = cams[0].shape[0]
         fmat = torch.empty((n_scales, len(cams), B, 3, 3), dtype=torch.float32, device=cams[0].device)
         library.call("mdn_fundamental_fwd", _cabi.ptr_array(inv_K), _cabi.ptr_array(cams), fmat.data_ptr(), n_scales,
-                     len(cams), B, _cabi.stream_ptr(fmat))
+                     len(cams), B, _cabi.stream_ptr(fmat), dev=fmat)
         ctx.library, ctx.n_scales, ctx.mats = library, n_scales, (inv_K, cams)
         return fmat
 
@@ -122,7 +122,7 @@ class FundamentalFn(torch.autograd.Function):
         g = g.contiguous()
         g_cam = [torch.empty_like(c) for c in cams]
         ctx.library.call("mdn_fundamental_bwd", _cabi.ptr_array(inv_K), _cabi.ptr_array(cams), g.data_ptr(),
-                         _cabi.ptr_array(g_cam), ctx.n_scales, len(cams), cams[0].shape[0], _cabi.stream_ptr(g))
+                         _cabi.ptr_array(g_cam), ctx.n_scales, len(cams), cams[0].shape[0], _cabi.stream_ptr(g), dev=g)
         return (None, None) + (None,) * ctx.n_scales + tuple(g_cam)
 
 

@@ -25,7 +25,7 @@ def frames_from_u8(frames_u8, mean=(0.45, 0.45, 0.45), std=(0.225, 0.225, 0.225)
     B, H, W, _ = src.shape
     out = torch.empty((B, 3, H, W), dtype=torch.float32, device=src.device)
     m, s = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
-    library.call("mdn_normalize_u8", src.data_ptr(), out.data_ptr(), B, H, W, m, s, _cabi.stream_ptr(src))
+    library.call("mdn_normalize_u8", src.data_ptr(), out.data_ptr(), B, H, W, m, s, _cabi.stream_ptr(src), dev=src)
     return out
 
 
@@ -49,7 +49,7 @@ def image_pyramid(img, sizes, library=None, packed=False):
             nbytes = library.cdll.mdn_instance_mask_resize_workspace_bytes(B * 3, H, W, oh, ow, len(chunk))
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=img.device)
             library.call("mdn_image_pyramid_packed", img.data_ptr(), B * 3, H, W, _cabi.ptr_array(chunk), oh, ow, len(chunk),
-                         ws.data_ptr(), nbytes, _cabi.stream_ptr(img))
+                         ws.data_ptr(), nbytes, _cabi.stream_ptr(img), dev=img)
         return outs
     outs = [img if (int(h), int(w)) == (H, W) else torch.empty((B, Cn, int(h), int(w)), dtype=torch.float32, device=img.device)
             for h, w in sizes]
@@ -61,7 +61,7 @@ def image_pyramid(img, sizes, library=None, packed=False):
         nbytes = library.cdll.mdn_instance_mask_resize_workspace_bytes(B * Cn, H, W, oh, ow, len(chunk))
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=img.device)
         library.call("mdn_image_pyramid", img.data_ptr(), B * Cn, H, W, _cabi.ptr_array(chunk), oh, ow, len(chunk),
-                     ws.data_ptr(), nbytes, _cabi.stream_ptr(img))
+                     ws.data_ptr(), nbytes, _cabi.stream_ptr(img), dev=img)
     return outs
 
 

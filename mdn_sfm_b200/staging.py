@@ -43,6 +43,8 @@ class BatchStager:
         self.free = [torch.cuda.Event() for _ in range(n_buffers)]      # consumers of buffer k have finished
         self._host_views = [self._views(h) for h in self.host]
         self._dev_views = [self._views(d) for d in self.dev]
+        self._copy_pending = [False] * n_buffers   # an upload of buffer k was enqueued and not yet known to have landed
+        self._in_use = [False] * n_buffers         # device buffer k was uploaded and its consumers not yet release()d
         for e in self.free:
             e.record(torch.cuda.current_stream(self.device))
 
@@ -52,8 +54,18 @@ class BatchStager:
             out[di][k] = slab[off:off + nbytes].view(dtype).view(shape)
         return out
 
+    def acquire_host(self, k):
+        """Blocks the calling host thread until the last enqueued copy OUT of pinned buffer k has landed: only then may
+        the loader overwrite it (a non_blocking copy that is still in flight would otherwise read a torn batch)."""
+        k %= self.n_buffers
+        if self._copy_pending[k]:
+            self.ready[k].synchronize()
+            self._copy_pending[k] = False
+
     def host_views(self, k):
-        """The pinned host tensors of buffer k (same keys / shapes as the template): write the next batch here."""
+        """The pinned host tensors of buffer k (same keys / shapes as the template): write the next batch here.
+        Waits (host side) for an in-flight upload of that buffer first, see acquire_host()."""
+        self.acquire_host(k)
         return self._host_views[k % self.n_buffers]
 
     def fill(self, k, dicts):
@@ -66,10 +78,15 @@ class BatchStager:
         """Enqueues the copy of buffer k on the copy stream (after the previous consumers of that device buffer are
         done) and returns the device views.  Call wait(k) on the consuming stream before using them."""
         k %= self.n_buffers
+        if self._in_use[k]:
+            raise RuntimeError("BatchStager: device buffer %d is uploaded again before release(%d) marked the end of its "
+                               "consumers (protocol: upload -> wait -> [kernels] -> release)" % (k, k))
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.free[k])
             self.dev[k].copy_(self.host[k], non_blocking=True)
             self.ready[k].record(self.copy_stream)
+        self._copy_pending[k] = True
+        self._in_use[k] = True
         return self._dev_views[k]
 
     def wait(self, k):
@@ -77,4 +94,6 @@ class BatchStager:
 
     def release(self, k):
         """Marks the end of the work that reads device buffer k (recorded on the current stream)."""
-        self.free[k % self.n_buffers].record(torch.cuda.current_stream(self.device))
+        k %= self.n_buffers
+        self.free[k].record(torch.cuda.current_stream(self.device))
+        self._in_use[k] = False

@@ -14,7 +14,7 @@ def binary_image(x, threshold=0.5, library=None):
     x = _c(x, "x")
     out = torch.empty_like(x)
     (library or _cabi.lib()).call("mdn_binary_image", x.data_ptr(), out.data_ptr(), x.numel(), float(threshold),
-                                  _cabi.stream_ptr(x))
+                                  _cabi.stream_ptr(x), dev=x)
     return out
 
 
