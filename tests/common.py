@@ -32,24 +32,64 @@ def rel_max(a, b):
     return ((a - b).abs().max() / a.abs().max().clamp_min(1e-30)).item()
 
 
-TIE_PX = 3   # per-pixel maps of the DS / DC modes: pixels exempted from a comparison (see rel_max_but)
+class tie_ruling:
+    """DS / DC only.  The reference resizes the integer instance mask with torchvision's antialiased bilinear `Resize` and
+    rounds; where the resized value is an EXACT 0.5 tie in exact arithmetic (rectangle edges of the synthetic Detectron2
+    masks land on such ties: ~17 pixels per 375x1242 -> 192x640 sample) its own CPU and CUDA kernels round to different
+    sides, and so may `mdn_instance_mask_resize`.  A flipped mask pixel changes that pixel's gradients by O(1).
+
+    Inside this context `restate.resized_instance_mask` returns the reference's own mask with the PRODUCT's value
+    substituted at exactly those pixels where the two disagree -- after proving, in float64, that each of them is such a
+    tie (anything else fails the test).  Comparisons then run with no exempted pixel at all.  `.substituted` counts them."""
+
+    def __init__(self, product_device, library=None):
+        self.dev, self.library, self.substituted = product_device, library, 0
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        from mdn_sfm_b200 import loss_utils
+        self._orig = orig = restate.resized_instance_mask
+        cache = {}
+
+        def ruled(instances_info, size):
+            size = tuple(int(v) for v in size)
+            key = (id(instances_info), size)
+            if key in cache:
+                return cache[key]
+            ref = orig(instances_info, size)                                   # (B or 1, 3, h, w) int64, the oracle's device
+            masks = instances_info if isinstance(instances_info, list) else [{"instances": instances_info}]
+            moved = [{"instances": d["instances"].to(self.dev)} for d in masks]
+            got = loss_utils.instance_masks_u8(moved, [size], self.dev, self.library)[0].to(ref.device)   # (B, h, w) uint8
+            bad = got.unsqueeze(1) != ref[:, :1]
+            if bool(bad.any()):
+                full = restate.get_batch_instance_mask([{"instances": d["instances"].to("cpu")} for d in masks])[:, :1].double()
+                v64 = F.interpolate(full, size=size, mode="bilinear", align_corners=False, antialias=True)
+                assert float((v64[bad.cpu()] - 0.5).abs().max()) < 1e-6, ("instance masks differ away from an exact 0.5 tie", size, int(bad.sum()))
+                self.substituted += int(bad.sum())
+                ref = torch.where(bad.expand_as(ref), got.unsqueeze(1).expand_as(ref).to(ref.dtype), ref)
+            cache[key] = ref
+            return ref
+
+        restate.resized_instance_mask = ruled
+        return self
+
+    def __exit__(self, *exc):
+        restate.resized_instance_mask = self._orig
+        return False
 
 
-def rel_max_but(a, b, k):
-    """rel_max over (B,C,h,w) maps ignoring the k worst PIXELS.  DS / DC only: the instance mask the reference resizes
-    with torchvision sits on an exact 0.5 tie at about one pixel per million, where its own CPU and CUDA kernels round
-    to different sides (tests/test_emu_kernels.py::test_instance_mask_union_and_resize_match_torchvision pins that every
-    disagreement IS such a tie); a flipped mask pixel changes the gradients of that one pixel by O(1)."""
-    a, b = a.detach().double().cpu(), b.detach().double().cpu()
-    err = (a - b).abs().amax(dim=1).reshape(-1)
-    if k and err.numel() > k:
-        err = err.topk(k + 1).values[-1]
-    else:
-        err = err.max()
-    return (err / a.abs().max().clamp_min(1e-30)).item()
+def oracle_run(opt, batch, mode, photo, ssim_on, device="cpu", pose_grad=False, product_device=None, library=None,
+               rule_ties=True):
+    """product_device / library: where (and with which build) the product's instance masks are made for the DS / DC tie
+    ruling (see tie_ruling); default = the oracle's own device.  rule_ties=False: the oracle exactly as it is (comparisons
+    against the reference's golden fixtures, where no product is involved)."""
+    if rule_ties and mode in ("DS", "DC") and batch[4] is not None:
+        with tie_ruling(product_device or device, library):
+            return _oracle_run(opt, batch, mode, photo, ssim_on, device, pose_grad)
+    return _oracle_run(opt, batch, mode, photo, ssim_on, device, pose_grad)
 
 
-def oracle_run(opt, batch, mode, photo, ssim_on, device="cpu", pose_grad=False):
+def _oracle_run(opt, batch, mode, photo, ssim_on, device="cpu", pose_grad=False):
     inputs, flows, mobiles, cams, inst = batch
     mv = lambda d: {k: v.to(device) for k, v in d.items()}
     inputs, cams = mv(inputs), mv(cams)
@@ -86,17 +126,17 @@ def product_run(opt, batch, mode, photo, ssim_on, device, pose_grad=False, libra
     return out, losses, f, m, cams
 
 
-def compare(ref, got, photo, check_maps=True, fwd_tol=FWD_TOL, grad_tol=GRAD_TOL, tie_px=0):
-    """tie_px: pixels per gradient map exempted from the comparison -- TIE_PX for the DS / DC modes (rel_max_but), else 0."""
+def compare(ref, got, photo, check_maps=True, fwd_tol=FWD_TOL, grad_tol=GRAD_TOL):
+    """No pixel is exempted: DS / DC oracle runs go through tie_ruling."""
     o_r, l_r, f_r, m_r, c_r = ref
     o_g, l_g, f_g, m_g, c_g = got
     for k in ("loss", "epip", "smooth", "consis") + (("photo",) if photo else ()):
         a, b = float(l_r[k]), float(l_g[k])
         assert abs(a - b) <= fwd_tol * max(abs(a), 1e-12), (k, a, b)
     for k in f_r:
-        assert rel_max_but(f_r[k].grad, f_g[k].grad, tie_px) <= grad_tol, ("d/dflow", k, rel_max(f_r[k].grad, f_g[k].grad))
+        assert rel_max(f_r[k].grad, f_g[k].grad) <= grad_tol, ("d/dflow", k, rel_max(f_r[k].grad, f_g[k].grad))
     for k in m_r:
-        assert rel_max_but(m_r[k].grad, m_g[k].grad, tie_px) <= grad_tol, ("d/dmobile", k, rel_max(m_r[k].grad, m_g[k].grad))
+        assert rel_max(m_r[k].grad, m_g[k].grad) <= grad_tol, ("d/dmobile", k, rel_max(m_r[k].grad, m_g[k].grad))
     for k in c_r:
         if c_r[k].grad is not None:
             assert rel_max(c_r[k].grad, c_g[k].grad) <= grad_tol, ("d/dpose", k, rel_max(c_r[k].grad, c_g[k].grad))
@@ -106,7 +146,7 @@ def compare(ref, got, photo, check_maps=True, fwd_tol=FWD_TOL, grad_tol=GRAD_TOL
             assert set(o_r[name].keys()) == set(o_g[name].keys()), name
             for key in o_r[name]:
                 assert o_r[name][key].shape == o_g[name][key].shape, (name, key)
-                assert rel_max_but(o_r[name][key], o_g[name][key], tie_px) <= fwd_tol, (name, key, rel_max(o_r[name][key], o_g[name][key]))
+                assert rel_max(o_r[name][key], o_g[name][key]) <= fwd_tol, (name, key, rel_max(o_r[name][key], o_g[name][key]))
         if photo:
             for key in o_r["valids"]:
                 assert o_g["valids"][key].dtype == torch.bool

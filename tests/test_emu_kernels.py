@@ -15,8 +15,8 @@ from oracle import restate
 @pytest.mark.parametrize("mode,photo,ssim_on,disable_min", common.CASES)
 def test_fused_loss_matches_oracle(mode, photo, ssim_on, disable_min):
     opt, batch = common.make(2, 32, 64, disable_min=disable_min)
-    ref = common.oracle_run(opt, batch, mode, photo, ssim_on)
     with emulated():
+        ref = common.oracle_run(opt, batch, mode, photo, ssim_on)      # (inside: the DS / DC tie ruling runs the emulated kernels)
         got = common.product_run(opt, batch, mode, photo, ssim_on, "cpu")
         common.compare(ref, got, photo)
 
@@ -303,10 +303,10 @@ def test_odd_tiny_and_ragged_shapes_all_modes(case):
     every mode and term switch, pose gradients: product (kernel source under the SIMT emulator) vs the oracle."""
     B, H, W, scales, mode, photo, ssim, over, fstd = case
     opt, batch = common.make(B, H, W, scales=scales, seed=100 + H + W, flow_std=fstd, **over)
-    ref = common.oracle_run(opt, batch, mode, photo, ssim, pose_grad=True)
     with emulated():
+        ref = common.oracle_run(opt, batch, mode, photo, ssim, pose_grad=True)
         got = common.product_run(opt, batch, mode, photo, ssim, "cpu", pose_grad=True)
-        common.compare(ref, got, photo, tie_px=common.TIE_PX if mode in ("DS", "DC") else 0)
+        common.compare(ref, got, photo)
 
 
 def test_epipolar_statistics_match_the_reference_quantiles():

@@ -17,11 +17,10 @@ def test_fused_vs_oracle_small(mode, photo, ssim_on, disable_min):
     opt, batch = common.make(2, 64, 96, disable_min=disable_min)
     # against the reference arithmetic run eagerly on this GPU ...
     got = common.product_run(opt, batch, mode, photo, ssim_on, DEV, arith="cuda")
-    tie = common.TIE_PX if mode in ("DS", "DC") else 0
-    common.compare(common.oracle_run(opt, batch, mode, photo, ssim_on, DEV), got, photo, tie_px=tie)
+    common.compare(common.oracle_run(opt, batch, mode, photo, ssim_on, DEV), got, photo)
     # ... and against the same code on the host CPU (whose `tensor /= scalar` rounds differently: arith="cpu")
     got = common.product_run(opt, batch, mode, photo, ssim_on, DEV, arith="cpu")
-    common.compare(common.oracle_run(opt, batch, mode, photo, ssim_on, "cpu"), got, photo, tie_px=tie)
+    common.compare(common.oracle_run(opt, batch, mode, photo, ssim_on, "cpu", product_device=DEV), got, photo)
 
 
 @pytest.mark.parametrize("mode", ["SN", "T", "TG", "DC"])
@@ -29,7 +28,7 @@ def test_fused_vs_oracle_config1_shape(mode):
     # BASELINE configs[0]: B=4, 3x192x640, 4 scales
     opt, batch = common.make(4, 192, 640, seed=42, flow_std=0.01)
     got = common.product_run(opt, batch, mode, True, True, DEV)
-    common.compare(common.oracle_run(opt, batch, mode, True, True, DEV), got, True, tie_px=common.TIE_PX if mode in ("DS", "DC") else 0)
+    common.compare(common.oracle_run(opt, batch, mode, True, True, DEV), got, True)
 
 
 def test_fused_vs_oracle_headline_shape():
@@ -44,7 +43,7 @@ def test_fused_vs_oracle_full_res_kitti():
     opt, batch = common.make(2, 375, 1242, scales=(0,), seed=42, flow_std=0.02)
     for mode in ("SN", "TG"):
         got = common.product_run(opt, batch, mode, True, True, DEV)
-        common.compare(common.oracle_run(opt, batch, mode, True, True, DEV), got, True, tie_px=common.TIE_PX if mode in ("DS", "DC") else 0)
+        common.compare(common.oracle_run(opt, batch, mode, True, True, DEV), got, True)
 
 
 def test_deterministic_and_repeatable():
