@@ -161,6 +161,19 @@ static inline int __shfl_xor_sync(unsigned, int v, int lanemask) {
   return (int)mdn_emu::exchange((uint32_t)v, mdn_emu::st().cur ^ lanemask);
 }
 
+// lane - delta / lane + delta of the caller's warp; lanes without such a neighbour keep their own value (like the hardware)
+static inline float __shfl_up_sync(unsigned, float v, unsigned delta) {
+  uint32_t u; memcpy(&u, &v, 4);
+  const int cur = mdn_emu::st().cur, lane = cur & 31;
+  u = mdn_emu::exchange(u, lane >= (int)delta ? cur - (int)delta : cur);
+  float r; memcpy(&r, &u, 4); return r;
+}
+static inline float __shfl_down_sync(unsigned, float v, unsigned delta) {
+  uint32_t u; memcpy(&u, &v, 4);
+  const int cur = mdn_emu::st().cur, lane = cur & 31;
+  u = mdn_emu::exchange(u, lane + (int)delta <= 31 ? cur + (int)delta : cur);
+  float r; memcpy(&r, &u, 4); return r;
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) { mdn_emu::yield_to_scheduler(); }
 static inline float __shfl_sync(unsigned, float v, int src_lane) {
   uint32_t u; memcpy(&u, &v, 4);
@@ -184,7 +197,7 @@ static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c);
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fdividef(float a, float b) { return a / b; }
-static inline float __saturatef(float a) { return a < 0.f ? 0.f : (a > 1.f ? 1.f : a); }
+static inline float __saturatef(float a) { return !(a > 0.f) ? 0.f : (a > 1.f ? 1.f : a); }   // NaN -> 0 like the hardware
 #define __expf(a) expf(a)
 #define __logf(a) logf(a)
 using std::max;
