@@ -31,7 +31,7 @@ extern "C" {
 #define MDN_API
 #endif
 
-#define MDN_ABI_VERSION 2
+#define MDN_ABI_VERSION 3
 #define MDN_MAX_SCALES 4
 #define MDN_MAX_PAIRS 2
 
@@ -114,7 +114,7 @@ typedef struct MdnLossDesc {
   float w_d2_sim;      /* DC cross-entropy weight (opt.w_d2_sim)                                              */
   float w_e, w_s, w_c, w_p;  /* loss_functions.py:191-194                                                    */
   MdnScale scale[MDN_MAX_SCALES];
-  /* Optional pose inputs (ABI 2).  When cam[p] is given for every pair, the fundamental matrices are built INSIDE the
+  /* Optional pose inputs (since ABI 2).  When cam[p] is given for every pair, the fundamental matrices are built INSIDE the
    * call -- F = K^-T ((t_x R) K^-1), loss_utils.py:50-62, with R = cam[:, :3, :3], t = cam[:, :3, 3]
    * (loss_functions.py:45-46) and K^-1 = inv_K[s][:, :3, :3] (:123), products accumulated like mdn_fundamental_fwd --
    * and scale[s].fmat[p] is ignored (may be NULL); inv_K[s] is then required for every scale.  With MDN_OPT_GRADS,
@@ -123,6 +123,18 @@ typedef struct MdnLossDesc {
   const float* cam[MDN_MAX_PAIRS];     /* (B,4,4) relative pose target -> source frame p                          */
   float* g_cam[MDN_MAX_PAIRS];         /* (B,4,4)                                                                 */
   const float* inv_K[MDN_MAX_SCALES];  /* (B,4,4) inverse intrinsics of pyramid level s                           */
+  /* Optional pose PARAMETERS instead of pose matrices (ABI 3): PoseNet's outputs as trainer.py:270 holds them, before
+   * transformation_from_parameters (networks/layers.py:16-98, invert=False, trainer.py:272).  axisangle[p] and
+   * translation[p] are (B,1,1,3) contiguous = 3 floats per sample; give them for every pair INSTEAD of cam[p] (inv_K as
+   * above).  The kernels then build the pose themselves -- Rodrigues' formula with the reference's operation order
+   * (angle = |v|, axis = v / (angle + 1e-7), R = cos I + (1 - cos) k k^T + sin [k]_x; M[:3,:3] = R, M[:3,3] = t) -- in the
+   * threads that build F, and with MDN_OPT_GRADS g_axisangle[p] / g_translation[p] (B,1,1,3, each may be NULL) receive
+   * d(loss)/d(axisangle[p]), d(loss)/d(translation[p]): the ~40 small ATen launches of layers.py:16-98 and their autograd
+   * backward leave the step.  g_cam[p] may still be given (it receives d(loss)/d(built pose)). */
+  const float* axisangle[MDN_MAX_PAIRS];
+  const float* translation[MDN_MAX_PAIRS];
+  float* g_axisangle[MDN_MAX_PAIRS];
+  float* g_translation[MDN_MAX_PAIRS];
 } MdnLossDesc;
 
 /* loss_out layout (MDN_OUT_COUNT = 8 device floats) written by mdn_loss_fused.  MDN_OUT_APPLIED is the upstream

@@ -17,7 +17,7 @@ OPT_SSIM, OPT_INST_MASK, OPT_CROSS_ENT, OPT_GRADS, OPT_CUDA_ARITH = 16, 32, 64, 
 WARP_FLOWWARP_NORM, WARP_CUDA_ARITH = 1, 2
 OUT_LOSS, OUT_EPIP, OUT_SMOOTH, OUT_CONSIS, OUT_PHOTO, OUT_APPLIED, OUT_COUNT = 0, 1, 2, 3, 4, 5, 8
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _P = C.c_void_p
 _PAIR = _P * MAX_PAIRS
@@ -38,7 +38,8 @@ class MdnLossDesc(C.Structure):
                 ("mask_mode", C.c_int32), ("flags", C.c_int32), ("threshold", C.c_double), ("alpha", C.c_float),
                 ("w_d2_sim", C.c_float), ("w_e", C.c_float), ("w_s", C.c_float), ("w_c", C.c_float),
                 ("w_p", C.c_float), ("scale", MdnScale * MAX_SCALES),
-                ("cam", _PAIR), ("g_cam", _PAIR), ("inv_K", _P * MAX_SCALES)]
+                ("cam", _PAIR), ("g_cam", _PAIR), ("inv_K", _P * MAX_SCALES),
+                ("axisangle", _PAIR), ("translation", _PAIR), ("g_axisangle", _PAIR), ("g_translation", _PAIR)]
 
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmdn_loss.so")
@@ -200,6 +201,25 @@ class FusedCall:
                 if t is not None:
                     d.g_cam[p] = t.data_ptr()
                     self.keep.append(t)
+        return self
+
+    def set_pose_params(self, axisangles, translations, inv_Ks, g_axisangles=None, g_translations=None):
+        """Pose PARAMETERS instead of pose matrices (MdnLossDesc.axisangle / translation, ABI 3): one (B,1,1,3) tensor per
+        pair each, as PoseNet emits them; the kernels run transformation_from_parameters themselves and return
+        d(loss)/d(axisangle), d(loss)/d(translation) into the given buffers."""
+        d = self.desc
+        for p, (a, t) in enumerate(zip(axisangles, translations)):
+            d.axisangle[p], d.translation[p] = a.data_ptr(), t.data_ptr()
+        for k, t in enumerate(inv_Ks):
+            d.inv_K[k] = t.data_ptr()
+        self.keep += list(axisangles) + list(translations) + list(inv_Ks)
+        for name, seq in (("g_axisangle", g_axisangles), ("g_translation", g_translations)):
+            if seq is not None:
+                arr = getattr(d, name)
+                for p, t in enumerate(seq):
+                    if t is not None:
+                        arr[p] = t.data_ptr()
+                        self.keep.append(t)
         return self
 
     def workspace_bytes(self, library):

@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
     if (epi_on && tid < 10) {   // fundamental matrix + SN maximum of this (pair, sample): staged now, read in P4
       float v = 1.f;
       if (tid < 9) {
-        if (P.cam[pair]) {
+        if (has_pose(P, pair)) {
           // poses given: every one of the nine threads builds F (81 FMAs) and keeps its own entry; the sample's first
           // tile publishes it for finish_kernel's SN fix-up
           float Fp[9];

@@ -84,6 +84,8 @@ struct KParams {
   const unsigned long long* snkey;   // [n_scales][n_pairs][batch] packed (bits(max)<<32 | ~argmax)
   // poses given instead of fundamental matrices (MdnLossDesc.cam / inv_K): F is built by the kernels that need it
   const float* cam[MDN_MAX_PAIRS];   // (B,4,4) or NULL
+  const float* aa[MDN_MAX_PAIRS];    // or pose PARAMETERS: axis-angle (B,3) and translation (B,3); cam is then built in-kernel
+  const float* tr[MDN_MAX_PAIRS];
   const float* inv_K[MDN_MAX_SCALES];
   float* fmat_ws;                    // [n_scales][n_pairs][batch][9] F as the fused kernel used it (written when cam is given)
   unsigned* ticket;                  // completion ticket of finish_kernel (zeroed by the fused kernel)
@@ -102,9 +104,67 @@ static_assert(sizeof(KParams) <= 3800, "kernel parameter space");
 struct FundArgs {
   const float* inv_K[MDN_MAX_SCALES];
   const float* cam[MDN_MAX_PAIRS];
+  const float* aa[MDN_MAX_PAIRS];      // pose parameters instead of cam (see pose_from_params)
+  const float* tr[MDN_MAX_PAIRS];
   float* g_cam[MDN_MAX_PAIRS];
+  float* g_aa[MDN_MAX_PAIRS];
+  float* g_tr[MDN_MAX_PAIRS];
   int n_scales, n_pairs, batch;
 };
+
+// transformation_from_parameters (networks/layers.py:16-98, invert=False as trainer.py:272 calls it): Rodrigues' formula
+// with the reference's operation order and separate roundings -- angle = |v| (:64), axis = v / (angle + 1e-7) (:65), cos /
+// sin (:67-68), C = 1 - cos (:69), the nine entries (:87-95); M = T R (:38) leaves M[:3,:3] = R and M[:3,3] = t exactly
+// (the products with T's zeros and ones add +0).  cam: 16 floats, row-major (4,4).
+MDN_DEV void pose_from_params(const float* aa, const float* tr, float* cam) {
+  const float vx = aa[0], vy = aa[1], vz = aa[2];
+  const float angle = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
+  const float den = __fadd_rn(angle, 1e-7f);
+  const float x = __fdiv_rn(vx, den), y = __fdiv_rn(vy, den), z = __fdiv_rn(vz, den);
+  const float ca = cosf(angle), sa = sinf(angle);
+  const float C = __fsub_rn(1.f, ca);
+  const float xs = __fmul_rn(x, sa), ys = __fmul_rn(y, sa), zs = __fmul_rn(z, sa);
+  const float xC = __fmul_rn(x, C), yC = __fmul_rn(y, C), zC = __fmul_rn(z, C);
+  const float xyC = __fmul_rn(x, yC), yzC = __fmul_rn(y, zC), zxC = __fmul_rn(z, xC);
+  cam[0] = __fadd_rn(__fmul_rn(x, xC), ca); cam[1] = __fsub_rn(xyC, zs); cam[2] = __fadd_rn(zxC, ys); cam[3] = tr[0];
+  cam[4] = __fadd_rn(xyC, zs); cam[5] = __fadd_rn(__fmul_rn(y, yC), ca); cam[6] = __fsub_rn(yzC, xs); cam[7] = tr[1];
+  cam[8] = __fsub_rn(zxC, ys); cam[9] = __fadd_rn(yzC, xs); cam[10] = __fadd_rn(__fmul_rn(z, zC), ca); cam[11] = tr[2];
+  cam[12] = 0.f; cam[13] = 0.f; cam[14] = 0.f; cam[15] = 1.f;
+}
+
+// adjoint of the rotation part: gR = d(loss)/dR (3x3 row-major) -> g = d(loss)/d(axis-angle) (3)
+MDN_DEV void pose_params_bwd(const float* aa, const float* gR, float* g) {
+  const float vx = aa[0], vy = aa[1], vz = aa[2];
+  const float angle = sqrtf(vx * vx + vy * vy + vz * vz);
+  const float inv = 1.f / (angle + 1e-7f);
+  const float x = vx * inv, y = vy * inv, z = vz * inv;
+  const float ca = cosf(angle), sa = sinf(angle), C = 1.f - ca;
+  const float s01 = gR[1] + gR[3], s02 = gR[2] + gR[6], s12 = gR[5] + gR[7];      // symmetric parts
+  const float a01 = gR[3] - gR[1], a02 = gR[2] - gR[6], a12 = gR[7] - gR[5];      // antisymmetric parts
+  const float dC = gR[0] * x * x + gR[4] * y * y + gR[8] * z * z + s01 * x * y + s02 * z * x + s12 * y * z;
+  const float dsa = a01 * z + a02 * y + a12 * x;
+  const float dca = gR[0] + gR[4] + gR[8] - dC;
+  const float dx = 2.f * gR[0] * x * C + s01 * y * C + s02 * z * C + a12 * sa;
+  const float dy = 2.f * gR[4] * y * C + s01 * x * C + s12 * z * C + a02 * sa;
+  const float dz = 2.f * gR[8] * z * C + s02 * x * C + s12 * y * C + a01 * sa;
+  // through cos / sin and through the normalisation of the axis; d|v|/dv = v / |v| (0 at the origin, like torch.norm)
+  const float dangle = dsa * ca - dca * sa - (dx * vx + dy * vy + dz * vz) * inv * inv;
+  const float k = angle > 0.f ? dangle / angle : 0.f;
+  g[0] = dx * inv + k * vx; g[1] = dy * inv + k * vy; g[2] = dz * inv + k * vz;
+}
+
+// the (4,4) pose of (pair p, sample b): loaded, or built from the pose parameters
+template <class A>
+MDN_DEV void load_cam(const A& a, int p, int b, float* cam) {
+  if (a.aa[p]) pose_from_params(a.aa[p] + b * 3, a.tr[p] + b * 3, cam);
+  else {
+    const float* src = a.cam[p] + b * 16;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) cam[k] = src[k];
+  }
+}
+template <class A>
+MDN_DEV bool has_pose(const A& a, int p) { return a.cam[p] != nullptr || a.aa[p] != nullptr; }
 
 MDN_DEV void mat3_mul(const float* A, const float* Bm, float* C) {   // C = A B, k-ordered FMA accumulation from 0
 #pragma unroll
@@ -146,8 +206,9 @@ MDN_DEV void fundamental_from_pose(const float* cam, const float* kp, float* F) 
 
 // d(loss)/d(cam[p][b]) from d(loss)/dF of every scale; g_fmat is [n_scales][n_pairs][batch][9]
 MDN_DEV void fundamental_bwd_one(const FundArgs& A, const float* g_fmat, int p, int b) {
-  float R[9], tx[9], G1[9];
-  load_pose(A.cam[p] + b * 16, R, tx);
+  float R[9], tx[9], G1[9], cam[16];
+  load_cam(A, p, b, cam);
+  load_pose(cam, R, tx);
 #pragma unroll
   for (int k = 0; k < 9; ++k) G1[k] = 0.f;
   for (int s = 0; s < A.n_scales; ++s) {                // dL/dM1 = sum_s K gF K^T   (K = K^-1 of scale s)
@@ -173,22 +234,36 @@ MDN_DEV void fundamental_bwd_one(const FundArgs& A, const float* g_fmat, int p, 
     for (int c = 0; c < 3; ++c) { txT[c * 3 + r] = tx[r * 3 + c]; RT[c * 3 + r] = R[r * 3 + c]; }
   mat3_mul(txT, G1, gR);                                // M1 = t_x R
   mat3_mul(G1, RT, gTx);
-  float* out = A.g_cam[p] + b * 16;
+  const float gt0 = gTx[7] - gTx[5];                    // t0: t_x[2][1] = t0, t_x[1][2] = -t0
+  const float gt1 = gTx[2] - gTx[6];                    // t1: t_x[0][2] = t1, t_x[2][0] = -t1
+  const float gt2 = gTx[3] - gTx[1];                    // t2: t_x[1][0] = t2, t_x[0][1] = -t2
+  if (A.g_cam[p]) {
+    float* out = A.g_cam[p] + b * 16;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) out[k] = 0.f;
+    for (int k = 0; k < 16; ++k) out[k] = 0.f;
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) out[r * 4 + c] = gR[r * 3 + c];
-  out[3] = gTx[7] - gTx[5];                             // t0: t_x[2][1] = t0, t_x[1][2] = -t0
-  out[7] = gTx[2] - gTx[6];                             // t1: t_x[0][2] = t1, t_x[2][0] = -t1
-  out[11] = gTx[3] - gTx[1];                            // t2: t_x[1][0] = t2, t_x[0][1] = -t2
+      for (int c = 0; c < 3; ++c) out[r * 4 + c] = gR[r * 3 + c];
+    out[3] = gt0; out[7] = gt1; out[11] = gt2;
+  }
+  // pose parameters given: the adjoint of transformation_from_parameters too (M[:3,3] = t, M[:3,:3] = Rodrigues(axisangle))
+  if (A.aa[p] && A.g_tr[p]) { float* o = A.g_tr[p] + b * 3; o[0] = gt0; o[1] = gt1; o[2] = gt2; }
+  if (A.aa[p] && A.g_aa[p]) {
+    float ga[3];
+    pose_params_bwd(A.aa[p] + b * 3, gR, ga);
+    float* o = A.g_aa[p] + b * 3;
+    o[0] = ga[0]; o[1] = ga[1]; o[2] = ga[2];
+  }
 }
 
 // the fundamental matrix of (scale s, pair, sample b): built from the pose when one was given, else loaded
 MDN_DEV void tile_fmat(const KParams& P, int s, int pair, int b, float* F) {
-  if (P.cam[pair]) fundamental_from_pose(P.cam[pair] + b * 16, P.inv_K[s] + b * 16, F);
-  else {
+  if (has_pose(P, pair)) {
+    float cam[16];
+    load_cam(P, pair, b, cam);
+    fundamental_from_pose(cam, P.inv_K[s] + b * 16, F);
+  } else {
     const float* src = P.sc[s].fmat[pair] + b * 9;
 #pragma unroll
     for (int k = 0; k < 9; ++k) F[k] = __ldg(src + k);
@@ -315,6 +390,8 @@ struct FParams {
   float* g_fmat[MDN_MAX_SCALES][2];
   float* gf_ws;            // [n_scales][n_pairs][batch][9] d(loss)/dF, for the pose adjoint of the last block
   float* g_cam[MDN_MAX_PAIRS];
+  float* g_aa[MDN_MAX_PAIRS];
+  float* g_tr[MDN_MAX_PAIRS];
   float alpha, w_d2, w_e, w_s, w_c, w_p, l1_coef, ssim_coef;
   float scale_div[MDN_MAX_SCALES];
   // reciprocals of the mean denominators, precomputed on the host in double: the single-thread epilogue multiplies
@@ -384,7 +461,7 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
         int y = idx / S.w, x = idx - y * S.w;
         const float* flx = S.flow[pair] + (long long)b * 2 * hw;
         float Fm[9];
-        const float* Fsrc = P.cam[pair] ? P.fmat_ws + ((size_t)(s * P.n_pairs + pair) * P.batch + b) * 9 : S.fmat[pair] + b * 9;
+        const float* Fsrc = has_pose(P, pair) ? P.fmat_ws + ((size_t)(s * P.n_pairs + pair) * P.batch + b) * 9 : S.fmat[pair] + b * 9;
         for (int k = 0; k < 9; ++k) Fm[k] = Fsrc[k];
         float u = __fadd_rn((float)x, __fmul_rn(S.sx, flx[idx]));
         float v = __fadd_rn((float)y, __fmul_rn(S.sy, flx[hw + idx]));
@@ -410,10 +487,13 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
   }
   __syncthreads();
   // pose adjoint of this sample (what mdn_fundamental_bwd computes) from the d/dF written above by this block
-  if (Q.gf_ws && threadIdx.x < (unsigned)P.n_pairs && Q.g_cam[threadIdx.x]) {
+  if (Q.gf_ws && threadIdx.x < (unsigned)P.n_pairs && (Q.g_cam[threadIdx.x] || Q.g_aa[threadIdx.x] || Q.g_tr[threadIdx.x])) {
     FundArgs A;
     for (int k = 0; k < MDN_MAX_SCALES; ++k) A.inv_K[k] = P.inv_K[k];
-    for (int k = 0; k < MDN_MAX_PAIRS; ++k) { A.cam[k] = P.cam[k]; A.g_cam[k] = Q.g_cam[k]; }
+    for (int k = 0; k < MDN_MAX_PAIRS; ++k) {
+      A.cam[k] = P.cam[k]; A.aa[k] = P.aa[k]; A.tr[k] = P.tr[k];
+      A.g_cam[k] = Q.g_cam[k]; A.g_aa[k] = Q.g_aa[k]; A.g_tr[k] = Q.g_tr[k];
+    }
     A.n_scales = P.n_scales; A.n_pairs = P.n_pairs; A.batch = P.batch;
     fundamental_bwd_one(A, Q.gf_ws, threadIdx.x, b);
   }
@@ -472,8 +552,8 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
 // ----------------------------------------------------------------------------------------------- scale grads
 struct GradList {
   int n;
-  float* ptr[MDN_MAX_SCALES * 6 + MDN_MAX_PAIRS];
-  long long count[MDN_MAX_SCALES * 6 + MDN_MAX_PAIRS];
+  float* ptr[MDN_MAX_SCALES * 6 + 3 * MDN_MAX_PAIRS];
+  long long count[MDN_MAX_SCALES * 6 + 3 * MDN_MAX_PAIRS];
 };
 
 __global__ void __launch_bounds__(NTHREADS) scale_grads_kernel(const __grid_constant__ GradList L, const float* g, float* applied,
@@ -575,8 +655,9 @@ __global__ void fundamental_fwd_kernel(const __grid_constant__ FundArgs A, float
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n_pairs * A.batch) return;
   const int p = i / A.batch, b = i - p * A.batch;
-  float R[9], tx[9], M1[9];
-  load_pose(A.cam[p] + b * 16, R, tx);
+  float R[9], tx[9], M1[9], cam[16];
+  load_cam(A, p, b, cam);
+  load_pose(cam, R, tx);
   mat3_mul(tx, R, M1);                                  // loss_utils.py:61
   for (int s = 0; s < A.n_scales; ++s) {
     float F[9];
@@ -748,9 +829,18 @@ static int check_desc(const MdnLossDesc* d) {
     return fail(MDN_ERR_UNSUPPORTED, "consistency term needs two mobile maps (not MDN_MASK_SHARED)");
   const int f = d->flags;
   // poses instead of fundamental matrices: all pairs or none, and the inverse intrinsics of every scale
-  bool poses = d->cam[0] != nullptr;
-  for (int p = 0; p < d->n_pairs; ++p)
-    if ((d->cam[p] != nullptr) != poses) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "cam[p] (give every pair's pose or none)");
+  const bool params = d->axisangle[0] != nullptr;      // pose parameters instead of pose matrices (ABI 3)
+  bool poses = d->cam[0] != nullptr || params;
+  for (int p = 0; p < d->n_pairs; ++p) {
+    if (params) {
+      if (!d->axisangle[p] || !d->translation[p]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "axisangle[p] / translation[p] (give every pair's or none)");
+      if (d->cam[p]) return fail(MDN_ERR_UNSUPPORTED, "give either cam[p] or axisangle[p] / translation[p], not both");
+    } else {
+      if ((d->cam[p] != nullptr) != poses) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "cam[p] (give every pair's pose or none)");
+      if (d->axisangle[p] || d->translation[p] || d->g_axisangle[p] || d->g_translation[p])
+        return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "axisangle[0] (pose parameters: all pairs or none)");
+    }
+  }
   if (poses)
     for (int s = 0; s < d->n_scales; ++s)
       if (!d->inv_K[s]) return fail(MDN_ERR_NULL_POINTER, "%s is NULL", "inv_K[s] (required with cam)");
@@ -803,8 +893,9 @@ static WsLayout ws_layout(const MdnLossDesc* d, int n_tiles) {
   L.snkeys = take((size_t)d->n_scales * d->n_pairs * d->batch * sizeof(unsigned long long));
   L.ticket = take(256);
   const size_t nf = (size_t)d->n_scales * d->n_pairs * d->batch * 9 * sizeof(float);
-  L.fmat = take(d->cam[0] ? nf : 0);
-  L.gfmat = take(d->cam[0] ? nf : 0);
+  const bool poses = d->cam[0] != nullptr || d->axisangle[0] != nullptr;
+  L.fmat = take(poses ? nf : 0);
+  L.gfmat = take(poses ? nf : 0);
   L.total = off;
   L.n_tiles = n_tiles;
   return L;
@@ -840,10 +931,15 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
   Q.sample_sums = (float*)(ws + L.sample_sums);
   K.ticket = (unsigned*)(ws + L.ticket);
   Q.loss_out = loss_out;
-  const bool poses = d->cam[0] != nullptr && (d->flags & MDN_TERM_EPIPOLAR);
+  const bool poses = (d->cam[0] != nullptr || d->axisangle[0] != nullptr) && (d->flags & MDN_TERM_EPIPOLAR);
   if (poses) {
     K.fmat_ws = (float*)(ws + L.fmat);
-    for (int p = 0; p < d->n_pairs; ++p) { K.cam[p] = d->cam[p]; Q.g_cam[p] = (d->flags & MDN_OPT_GRADS) ? d->g_cam[p] : nullptr; }
+    const bool gr = (d->flags & MDN_OPT_GRADS) != 0;
+    for (int p = 0; p < d->n_pairs; ++p) {
+      K.cam[p] = d->cam[p]; K.aa[p] = d->axisangle[p]; K.tr[p] = d->translation[p];
+      Q.g_cam[p] = gr ? d->g_cam[p] : nullptr;
+      Q.g_aa[p] = gr ? d->g_axisangle[p] : nullptr; Q.g_tr[p] = gr ? d->g_translation[p] : nullptr;
+    }
     for (int s = 0; s < d->n_scales; ++s) K.inv_K[s] = d->inv_K[s];
     if (d->flags & MDN_OPT_GRADS) Q.gf_ws = (float*)(ws + L.gfmat);
   }
@@ -1030,8 +1126,11 @@ extern "C" MDN_API int mdn_loss_scale_grads(const MdnLossDesc* d, const float* g
       if (S.g_fmat[p]) { L.ptr[L.n] = S.g_fmat[p]; L.count[L.n++] = 9ll * d->batch; }
     }
   }
-  for (int p = 0; p < MDN_MAX_PAIRS; ++p)
+  for (int p = 0; p < MDN_MAX_PAIRS; ++p) {
     if (d->g_cam[p]) { L.ptr[L.n] = d->g_cam[p]; L.count[L.n++] = 16ll * d->batch; }
+    if (d->g_axisangle[p]) { L.ptr[L.n] = d->g_axisangle[p]; L.count[L.n++] = 3ll * d->batch; }
+    if (d->g_translation[p]) { L.ptr[L.n] = d->g_translation[p]; L.count[L.n++] = 3ll * d->batch; }
+  }
   if (L.n == 0) return MDN_OK;
   // applied[1] (MDN_OUT_APPLIED + 1) is the completion ticket, zeroed by mdn_loss_fused
   MDN_LAUNCH_PDL(8, scale_grads_kernel, dim3(296), dim3(NTHREADS), 0, stream, L, g, applied, reinterpret_cast<unsigned*>(applied + 1));

@@ -79,7 +79,8 @@ def _workspace(device, nbytes):
     return ws
 
 
-def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None, g_fmat_all=None, poses=None, g_cams=None):
+def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None, g_fmat_all=None, poses=None, g_cams=None,
+              pose_params=None, g_pose_params=None):
     """Launches the fused kernel.
 
     need_grad: per scale a dict {"flow": [bool,bool], "mob": [bool,bool], "fmat": [bool,bool]}.
@@ -87,12 +88,16 @@ def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None
     poses: optional (cams, inv_Ks) -- one (B,4,4) pose per pair and one (B,4,4) inverse intrinsics per scale; the
     kernels then build the fundamental matrices themselves (MdnLossDesc.cam / inv_K) and `fmat` entries are ignored.
     g_cams: with poses, per pair a (B,4,4) buffer (or None) that receives d(loss)/d(pose).
+    pose_params: optional (axisangles, translations, inv_Ks) INSTEAD of poses -- PoseNet's (B,1,1,3) outputs per pair; the
+    kernels build the pose matrices too (transformation_from_parameters, networks/layers.py:16-98).
+    g_pose_params: with pose_params, (g_axisangles, g_translations): per pair a (B,1,1,3) buffer or None.
     Returns (loss_out (8,), grads (same structure, tensors or None), maps (dict name -> [pair tensors]), call).
     """
     library = library or _cabi.lib()
     dev = None
     any_grad = (any(any(v) for ng in need_grad for v in ng.values()) or g_fmat_all is not None
-                or (g_cams is not None and any(g is not None for g in g_cams)))
+                or (g_cams is not None and any(g is not None for g in g_cams))
+                or (g_pose_params is not None and any(g is not None for seq in g_pose_params for g in seq)))
     flags = cfg.flags | (OPT_GRADS if any_grad else 0) | (OPT_CUDA_ARITH if cfg.cuda_arith else 0)
     call = _cabi.FusedCall(batch=cfg.batch, n_pairs=cfg.n_pairs, post=cfg.post, mask_mode=cfg.mask_mode, flags=flags,
                            threshold=cfg.threshold, alpha=cfg.alpha, w_d2_sim=cfg.w_d2_sim, w_e=cfg.w_e, w_s=cfg.w_s,
@@ -135,6 +140,9 @@ def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None
         grads.append(g)
     if poses is not None:
         call.set_poses(poses[0], poses[1], g_cams)
+    if pose_params is not None:
+        gp = g_pose_params or (None, None)
+        call.set_pose_params(pose_params[0], pose_params[1], pose_params[2], gp[0], gp[1])
     loss_out = torch.empty(OUT_COUNT, dtype=torch.float32, device=dev)
     ws = _workspace(dev, call.workspace_bytes(library))
     call.run(library, loss_out, ws, _cabi.stream_ptr(loss_out))
@@ -146,20 +154,25 @@ class _FusedLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, scales, slots, library, poses, *diff_inputs):
-        # slots[i] = (scale index, kind, pair) for diff_inputs[i]
+        # slots[i] = (scale index, kind, pair) for diff_inputs[i]; poses = ("cam", cams, inv_Ks) | ("params", aas, trs, inv_Ks) | None
         need = [{"flow": [False, False], "mob": [False, False], "fmat": [False, False]} for _ in scales]
         g_fmat_all = None
-        g_cams = [None, None] if poses is not None else None
+        mats = poses[1:] if poses is not None and poses[0] == "cam" else None
+        params = poses[1:] if poses is not None and poses[0] == "params" else None
+        g_cams = [None, None] if mats is not None else None
+        g_par = ([None, None], [None, None]) if params is not None else None
         for (k, kind, p), t in zip(slots, diff_inputs):
             if kind == "fmat_all":
                 g_fmat_all = torch.empty_like(t)
             elif kind == "cam":
                 g_cams[p] = torch.empty_like(t)
+            elif kind in ("aa", "tr"):
+                g_par[0 if kind == "aa" else 1][p] = torch.empty(t.shape, dtype=torch.float32, device=t.device)
             elif t.requires_grad:
                 need[k][kind][p] = True
-        loss_out, grads, maps, call = run_fused(cfg, scales, need, library, g_fmat_all, poses, g_cams)
+        loss_out, grads, maps, call = run_fused(cfg, scales, need, library, g_fmat_all, mats, g_cams, params, g_par)
         ctx.call, ctx.library, ctx.slots, ctx.grads, ctx.loss_out = call, library, slots, grads, loss_out
-        ctx.g_fmat_all, ctx.g_cams = g_fmat_all, g_cams
+        ctx.g_fmat_all, ctx.g_cams, ctx.g_par = g_fmat_all, g_cams, g_par
         ctx.maps = maps
         total = loss_out[0]
         terms = loss_out[1:5]
@@ -178,37 +191,54 @@ class _FusedLossFn(torch.autograd.Function):
         ctx.call.scale_grads(ctx.library, g, ctx.loss_out[OUT_APPLIED:], _cabi.stream_ptr(g))
         # Give the buffers AWAY: with no other reference left, AccumulateGrad adopts them as `.grad` instead of cloning
         # them (18 device-to-device copies, 94 MB of traffic and 45 us per step at the headline shape otherwise).
-        grads, g_fmat_all, g_cams = ctx.grads, ctx.g_fmat_all, ctx.g_cams
-        ctx.grads = ctx.g_fmat_all = ctx.g_cams = None
+        grads, g_fmat_all, g_cams, g_par = ctx.grads, ctx.g_fmat_all, ctx.g_cams, ctx.g_par
+        ctx.grads = ctx.g_fmat_all = ctx.g_cams = ctx.g_par = None
         ctx.call.keep = []     # (stream-ordered allocator: the launches above keep using the memory safely)
         out = [None, None, None, None, None]
         for (k, kind, p) in ctx.slots:
-            out.append(g_fmat_all if kind == "fmat_all" else (g_cams[p] if kind == "cam" else grads[k][kind][p]))
+            if kind == "fmat_all":
+                out.append(g_fmat_all)
+            elif kind == "cam":
+                out.append(g_cams[p])
+            elif kind in ("aa", "tr"):
+                out.append(g_par[0 if kind == "aa" else 1][p])
+            else:
+                out.append(grads[k][kind][p])
         return tuple(out)
 
 
-def fused_loss(cfg: FusedConfig, scales: List[ScaleData], library=None, fmat_all=None, cams=None, inv_Ks=None):
+def fused_loss(cfg: FusedConfig, scales: List[ScaleData], library=None, fmat_all=None, cams=None, inv_Ks=None, axisangles=None,
+               translations=None):
     """-> (total 0-d tensor with grad_fn, terms (4,) = [epip, smooth, consis, photo] detached, maps dict).
 
     fmat_all: the (S,P,B,3,3) tensor the per-scale `fmat` entries are slices of; when it requires grad its gradient
     is returned as ONE tensor instead of S*P slice gradients.
     cams / inv_Ks: poses (one (B,4,4) per pair) and inverse intrinsics (one (B,4,4) per scale) INSTEAD of fundamental
-    matrices: F is built inside the call and the pose gradients come back from the same launches."""
+    matrices: F is built inside the call and the pose gradients come back from the same launches.
+    axisangles / translations (+ inv_Ks): PoseNet's (B,1,1,3) outputs per pair INSTEAD of cams -- the call also runs
+    transformation_from_parameters and returns the gradients w.r.t. the parameters."""
     library = library or _cabi.lib()
     slots, diff = [], []
     grad_on = torch.is_grad_enabled()
     poses = None
     if cams is not None:
-        poses = ([c.detach() for c in cams], [k.detach() for k in inv_Ks])
+        poses = ("cam", [c.detach() for c in cams], [k.detach() for k in inv_Ks])
         for p, c in enumerate(cams):
             if c.requires_grad and grad_on:
                 slots.append((0, "cam", p))
                 diff.append(c)
+    elif axisangles is not None:
+        poses = ("params", [a.detach() for a in axisangles], [t.detach() for t in translations], [k.detach() for k in inv_Ks])
+        for kind, seq in (("aa", axisangles), ("tr", translations)):
+            for p, t in enumerate(seq):
+                if t.requires_grad and grad_on:
+                    slots.append((0, kind, p))
+                    diff.append(t)
     if fmat_all is not None and fmat_all.requires_grad and grad_on:
         slots.append((0, "fmat_all", 0))
         diff.append(fmat_all)
     for k, S in enumerate(scales):
-        for kind in ("flow", "mob") + (() if (fmat_all is not None or cams is not None) else ("fmat",)):
+        for kind in ("flow", "mob") + (() if (fmat_all is not None or cams is not None or axisangles is not None) else ("fmat",)):
             for p, t in enumerate(getattr(S, kind)):
                 if t is not None and t.requires_grad and torch.is_grad_enabled():
                     if kind == "mob" and cfg.mask_mode == MASK_SHARED and p == 1:
@@ -221,6 +251,7 @@ def fused_loss(cfg: FusedConfig, scales: List[ScaleData], library=None, fmat_all
         maps = total.grad_fn.maps if total.grad_fn is not None and hasattr(total.grad_fn, "maps") else holder
     else:
         need = [{"flow": [False, False], "mob": [False, False], "fmat": [False, False]} for _ in scales]
-        loss_out, _, maps, _ = run_fused(cfg, scales, need, library, poses=poses)
+        loss_out, _, maps, _ = run_fused(cfg, scales, need, library, poses=poses[1:] if poses and poses[0] == "cam" else None,
+                                         pose_params=poses[1:] if poses and poses[0] == "params" else None)
         total, terms = loss_out[0], loss_out[1:5]
     return total, terms, maps

@@ -38,6 +38,22 @@ def get_translation_matrix(translation_vector):
     return torch.cat([T[:, :, :3], torch.cat([translation_vector.contiguous().view(B, 3, 1), T[:, 3:, 3:]], 1)], 2)
 
 
+class PoseParameters:
+    """PoseNet's outputs for one source frame -- axisangle, translation, each (B,1,1,3) -- handed to ``Loss.forward`` AS
+    PARAMETERS in place of the (B,4,4) matrix (``cam_T_cam[i] = PoseParameters(axisangle, translation)``).  The fused call
+    then runs transformation_from_parameters itself (MdnLossDesc.axisangle / translation) and returns the gradients
+    w.r.t. both: the ~40 small launches of networks/layers.py:16-98 and their autograd backward leave the training step.
+    ``matrix()`` materialises the reference's (B,4,4) tensor for any other consumer."""
+
+    def __init__(self, axisangle, translation):
+        if tuple(axisangle.shape[1:]) != (1, 1, 3) or tuple(translation.shape) != tuple(axisangle.shape):
+            raise ValueError("axisangle / translation must be (B,1,1,3) (pose_net_v3.py:62-64)")
+        self.axisangle, self.translation = axisangle, translation
+
+    def matrix(self, invert=False):
+        return transformation_from_parameters(self.axisangle, self.translation, invert)
+
+
 def transformation_from_parameters(axis_angle, translation, invert=False):
     """networks/layers.py:16-40."""
     R = rot_from_axisangle(axis_angle.squeeze(1))

@@ -29,7 +29,7 @@ from torch import nn
 from . import _cabi, fused
 from ._cabi import (MASK_MIN, MASK_OWN, MASK_SHARED, OPT_CROSS_ENT, OPT_INST_MASK, OPT_SSIM, OUT_CONSIS, OUT_EPIP,
                     OUT_PHOTO, OUT_SMOOTH, TERM_CONSIS, TERM_EPIPOLAR, TERM_PHOTO, TERM_SMOOTH)
-from .layers import SSIM, get_scale_factor  # noqa: F401  (re-exported like the reference module does)
+from .layers import SSIM, PoseParameters, get_scale_factor  # noqa: F401  (re-exported like the reference module does)
 from .loss_utils import *  # noqa: F401,F403  (the reference does `from loss_utils import *`)
 from .loss_utils import create_coords as _create_coords
 from .loss_utils import _arith_flag, instance_mask_u8, instance_masks_u8
@@ -254,7 +254,18 @@ class Loss(nn.Module):
         lm = self._lm()
         ids = list(frame_id)
         poses = None
-        if self._cuda_arith and not self.pose_in:
+        params = all(isinstance(cam_T_cam[i], PoseParameters) for i in ids)
+        if params and not (self._cuda_arith and self.pose_in):
+            cam_T_cam = {i: cam_T_cam[i].matrix() for i in ids}      # the torch composition of networks/layers.py:16-98
+            params = False
+        if params:
+            # PoseNet's outputs as parameters: the kernels build the pose matrices and F, and return d/d(axisangle, translation)
+            F_all = None
+            aas = [_c(cam_T_cam[i].axisangle, "axisangle") for i in ids]
+            trs = [_c(cam_T_cam[i].translation, "translation") for i in ids]
+            inv_Ks = [_c(inputs[("inv_K", s)].detach(), "inv_K") for s in scales]
+            poses = ("params", aas, trs, inv_Ks)
+        elif self._cuda_arith and not self.pose_in:
             # one prologue launch (mdn_fundamental_fwd): F for every (scale, source frame, sample); autograd carries
             # d/dF back to the poses through mdn_fundamental_bwd.  Same arithmetic as the in-kernel path below.
             F_all = fundamental_matrices([inputs[("inv_K", s)] for s in scales], [cam_T_cam[i] for i in ids], self._library)
@@ -267,7 +278,7 @@ class Loss(nn.Module):
             for t in cams + inv_Ks:
                 if t.dim() != 3 or tuple(t.shape[1:]) != (4, 4):
                     raise ValueError("inv_K / cam_T_cam must be (B,4,4)")
-            poses = (cams, inv_Ks)
+            poses = ("cam", cams, inv_Ks)
         else:
             # arith="cpu": the reference's own three torch.matmul calls (loss_utils.py:61-62), batched over scales / frames
             R = torch.stack([cam_T_cam[i][:, :3, :3] for i in ids], 0).unsqueeze(0)      # (1,P,B,3,3)
@@ -323,13 +334,18 @@ class Loss(nn.Module):
         if self.photometric:
             flags |= TERM_PHOTO | (OPT_SSIM if self.ssim is not None else 0)
         data, F_all, poses = self._scale_data(inputs, ids, flow, mobile, instances_info, scales, cam_T_cam, post, bits)
-        cams, inv_Ks = poses if poses is not None else (None, None)
+        cams = inv_Ks = aas = trs = None
+        if poses is not None and poses[0] == "cam":
+            _, cams, inv_Ks = poses
+        elif poses is not None:
+            _, aas, trs, inv_Ks = poses
         b = data[0].tgt.shape[0]
         cfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=len(ids), post=post, mask_mode=MASK_OWN if o.disable_min else MASK_MIN,
                                 flags=flags, threshold=getattr(o, "threshold", None) if post != fused.POST_SN else None,
                                 alpha=o.alpha, w_d2_sim=o.w_d2_sim, w_e=o.w_e, w_s=o.w_s, w_c=o.w_c,
                                 w_p=getattr(o, "w_p", 1.0) if self.photometric else 0.0)
-        total, terms, _ = fused.fused_loss(cfg, data, self._library, fmat_all=F_all, cams=cams, inv_Ks=inv_Ks)
+        total, terms, _ = fused.fused_loss(cfg, data, self._library, fmat_all=F_all, cams=cams, inv_Ks=inv_Ks, axisangles=aas,
+                                           translations=trs)
         losses = {"consis": terms[OUT_CONSIS - 1] if not o.disable_consisloss else 0, "epip": terms[OUT_EPIP - 1],
                   "smooth": terms[OUT_SMOOTH - 1] if not o.disable_smoothloss else 0, "loss": total}
         if self.photometric:
@@ -353,7 +369,9 @@ class Loss(nn.Module):
                                          flags=flags & ~(TERM_SMOOTH | TERM_CONSIS), threshold=cfg.threshold,
                                          alpha=o.alpha, w_d2_sim=o.w_d2_sim, want_maps=want)
                 _, _, maps = fused.fused_loss(mcfg, [S], self._library, cams=None if cams is None else [c.detach() for c in cams],
-                                              inv_Ks=None if inv_Ks is None else inv_Ks[:1])
+                                              inv_Ks=None if inv_Ks is None else inv_Ks[:1],
+                                              axisangles=None if aas is None else [a.detach() for a in aas],
+                                              translations=None if trs is None else [t.detach() for t in trs])
                 h, w = S0.height, S0.width
                 sf = get_scale_factor(b, h, w).to(S0.tgt.device)
                 cache["epipolars"] = {(i, 0): maps["post_map"][p].expand(b, 3, h, w) for p, i in enumerate(ids)}

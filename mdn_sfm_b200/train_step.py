@@ -24,7 +24,7 @@ import torch.distributed as dist
 from torch import nn
 
 from . import distributed as D
-from .layers import transformation_from_parameters
+from .layers import PoseParameters, transformation_from_parameters
 
 
 def _conv(cin, cout, stride=1):
@@ -137,13 +137,23 @@ class TrainStep:
     """
 
     def __init__(self, opt, nets=None, loss_module=None, device="cuda", lr=1e-4, clip_grad=1.0,
-                 fine_tune_flow_motion=False, mode="TG", photometric=True):
+                 fine_tune_flow_motion=False, mode="TG", photometric=True, graph_loss=True, pose_params=True):
+        """graph_loss: run the CUDA loss path as one CUDA-graph replay per step (graphs.GraphedLoss; batches without
+        Detectron2 instances).  pose_params: hand PoseNet's (axisangle, translation) to the loss as parameters so that the
+        fused call also runs transformation_from_parameters and its adjoint (layers.PoseParameters).  Both apply to the
+        default CUDA loss only; a caller-supplied `loss_module` gets the reference's (B,4,4) matrices, eagerly."""
         self.opt, self.device = opt, torch.device(device)
         self.nets = (nets or StandInNets()).to(self.device)
         self.fine_tune = fine_tune_flow_motion
+        self.pose_params = False
+        self.eager_loss = None
         if loss_module is None:
             from .loss_functions import Loss
-            loss_module = Loss(opt, no_ssim=False, mode=mode, photometric=photometric)
+            loss_module = self.eager_loss = Loss(opt, no_ssim=False, mode=mode, photometric=photometric)
+            self.pose_params = pose_params
+            if graph_loss and self.device.type == "cuda":
+                from .graphs import GraphedLoss
+                loss_module = GraphedLoss(loss_module)
         self.loss = loss_module
         self.clip_grad = clip_grad
         trainable = [self.nets.mobile_decoder] + ([self.nets.flownet, self.nets.posenet] if fine_tune_flow_motion else [])
@@ -175,15 +185,23 @@ class TrainStep:
                 axisangle, translation = posenet(tgt, ref)
             flows.update(flow)
             mobiles.update(self.mobile_decoder(feats, axisangle, translation, frame_id=i))
-            cams[i] = transformation_from_parameters(axisangle, translation)
-        outputs, losses = self.loss(inputs, ids, flows, mobiles, instances, list(o.scales), cams)
+            cams[i] = PoseParameters(axisangle, translation) if self.pose_params else transformation_from_parameters(axisangle, translation)
+        loss = self.loss if (instances is None or self.eager_loss is None) else self.eager_loss     # (DS / DC batches: eager launches)
+        outputs, losses = loss(inputs, ids, flows, mobiles, instances, list(o.scales), cams)
         return flows, mobiles, cams, outputs, losses
 
     def step(self, inputs, instances=None):
         """process_batch -> zero_grad -> backward -> clip_grad_norm_ -> Adam (trainer.py:231-237).  Returns the losses dict."""
         _, _, _, _, losses = self.process_batch(inputs, instances)
         self.optimizer.zero_grad(set_to_none=True)
-        losses["loss"].backward()
+        graphed = hasattr(self.loss, "unit_upstream")
+        if graphed:
+            self.loss.unit_upstream = True       # loss.backward() below: the upstream gradient is 1
+        try:
+            losses["loss"].backward()
+        finally:
+            if graphed:
+                self.loss.unit_upstream = False
         torch.nn.utils.clip_grad_norm_(self.parameters_to_train, max_norm=self.clip_grad)
         self.optimizer.step()
         return losses

@@ -33,14 +33,18 @@ def rel_max(a, b):
 
 
 class tie_ruling:
-    """DS / DC only.  The reference resizes the integer instance mask with torchvision's antialiased bilinear `Resize` and
-    rounds; where the resized value is an EXACT 0.5 tie in exact arithmetic (rectangle edges of the synthetic Detectron2
-    masks land on such ties: ~17 pixels per 375x1242 -> 192x640 sample) its own CPU and CUDA kernels round to different
-    sides, and so may `mdn_instance_mask_resize`.  A flipped mask pixel changes that pixel's gradients by O(1).
+    """DS / DC only.  The reference resizes the integer instance mask with torchvision's antialiased bilinear `Resize` (fp32)
+    and rounds.  Where the resized value is a 0.5 tie -- exactly (rectangle edges of the synthetic Detectron2 masks land on
+    such ties: ~17 pixels per 375x1242 -> 192x640 sample) or to within the fp32 error of ATen's own filter (measured on
+    B200: its CPU and CUDA kernels return 0.5000051 and 0.4999982 for a float64 value of 0.4999940) -- the reference's own
+    CPU and CUDA kernels round to different sides.  `mdn_instance_mask_resize` replays the CPU kernel bit for bit
+    (scripts/diag_ties.py: `ours != cpu` is 0), so against the oracle run on CUDA a few pixels per batch differ, and a
+    flipped mask pixel changes that pixel's gradients by O(1).
 
     Inside this context `restate.resized_instance_mask` returns the reference's own mask with the PRODUCT's value
-    substituted at exactly those pixels where the two disagree -- after proving, in float64, that each of them is such a
-    tie (anything else fails the test).  Comparisons then run with no exempted pixel at all.  `.substituted` counts them."""
+    substituted at exactly those pixels where the two disagree -- after proving for each of them that it is such a tie:
+    |float64 value - 0.5| < 1e-6, or < 1e-4 AND the product equals the reference's own CPU kernel there.  Anything else
+    fails the test.  Comparisons then run with no exempted pixel at all.  `.substituted` counts the pixels."""
 
     def __init__(self, product_device, library=None):
         self.dev, self.library, self.substituted = product_device, library, 0
@@ -64,7 +68,11 @@ class tie_ruling:
             if bool(bad.any()):
                 full = restate.get_batch_instance_mask([{"instances": d["instances"].to("cpu")} for d in masks])[:, :1].double()
                 v64 = F.interpolate(full, size=size, mode="bilinear", align_corners=False, antialias=True)
-                assert float((v64[bad.cpu()] - 0.5).abs().max()) < 1e-6, ("instance masks differ away from an exact 0.5 tie", size, int(bad.sum()))
+                dist = (v64 - 0.5).abs()[:, 0]
+                cpu_ref = orig([{"instances": d["instances"].to("cpu")} for d in masks], size)[:, 0]
+                proven = (dist < 1e-6) | ((dist < 1e-4) & (got.cpu().long() == cpu_ref))
+                assert bool(proven[bad[:, 0].cpu()].all()), ("instance masks differ away from a 0.5 tie", size, int(bad.sum()),
+                                                             float(dist[bad[:, 0].cpu()].max()))
                 self.substituted += int(bad.sum())
                 ref = torch.where(bad.expand_as(ref), got.unsqueeze(1).expand_as(ref).to(ref.dtype), ref)
             cache[key] = ref

@@ -369,3 +369,37 @@ def test_uint8_frames_normalised_on_the_device_equal_the_dataset_transforms():
     with emulated() as lib:
         got = pyramid.frames_from_u8(u8, library=lib)
     assert torch.equal(got, ref.contiguous())
+
+
+@pytest.mark.parametrize("mode", ["T", "SN"])
+def test_pose_parameters_inside_the_call(mode):
+    """SURVEY 8f-N1, fused pose prologue: cam_T_cam[i] = PoseParameters(axisangle, translation) -- the kernels run
+    transformation_from_parameters (networks/layers.py:16-98) themselves and return d/d(axisangle), d/d(translation) --
+    against the oracle's torch composition + autograd.  (Epipolar terms only: the parameter path needs the CUDA-eager
+    arithmetic flag, whose warp rounding the CPU oracle does not share.)"""
+    from mdn_sfm_b200.layers import PoseParameters
+    from mdn_sfm_b200.loss_functions import Loss
+    B, H, W = 2, 32, 64
+    opt, batch = common.make(B, H, W, seed=23, flow_std=0.05)
+    inputs, flows, mobiles, _, _ = batch
+    g = torch.Generator().manual_seed(5)
+    aa = {i: torch.randn(B, 1, 1, 3, generator=g) * 0.05 for i in (-1, 1)}
+    tt = {i: torch.randn(B, 1, 1, 3, generator=g) * 0.2 for i in (-1, 1)}
+    aa[1][0] = 0.0      # a zero rotation: the 1e-7 guard and the norm's zero sub-gradient
+    ao, to = common.leaf(aa), common.leaf(tt)
+    fo, mo = common.leaf(flows), common.leaf(mobiles)
+    cams = {i: restate.transformation_from_parameters(ao[i], to[i]) for i in (-1, 1)}
+    _, lo = restate.loss_forward(opt, inputs, [-1, 1], fo, mo, None, [0, 1, 2, 3], cams, mode=mode)
+    lo["loss"].backward()
+    with emulated():
+        ag, tg = common.leaf(aa), common.leaf(tt)
+        fg, mg = common.leaf(flows), common.leaf(mobiles)
+        _, lg = Loss(opt, mode=mode, arith="cuda")(inputs, [-1, 1], fg, mg, None, [0, 1, 2, 3],
+                                                  {i: PoseParameters(ag[i], tg[i]) for i in (-1, 1)})
+        lg["loss"].backward()
+    assert float(lg["loss"]) == pytest.approx(float(lo["loss"]), rel=common.FWD_TOL)
+    for i in (-1, 1):
+        assert common.rel_max(ao[i].grad, ag[i].grad) <= common.GRAD_TOL, ("d/daxisangle", i)
+        assert common.rel_max(to[i].grad, tg[i].grad) <= common.GRAD_TOL, ("d/dtranslation", i)
+    for k in fo:
+        assert common.rel_max(fo[k].grad, fg[k].grad) <= common.GRAD_TOL, k

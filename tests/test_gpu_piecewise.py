@@ -269,3 +269,57 @@ def test_every_entry_point_on_a_non_current_device():
     w1, v1 = loss_utils.inverse_warp(img.to("cuda:1"), fl.to("cuda:1"), pix, "zeros")
     assert torch.equal(w0.cpu(), w1.cpu()) and torch.equal(v0.cpu(), v1.cpu())
     assert float(loss_utils.smooth_loss(img.to("cuda:0"), m.to("cuda:0"))) == float(loss_utils.smooth_loss(img.to("cuda:1"), m.to("cuda:1")))
+
+
+# ---- the train step around the loss
+def _train_steps(fine_tune):
+    from mdn_sfm_b200.train_step import StandInNets, TrainStep
+    B, H, W = 2, 64, 96
+    opt = synthetic.default_opt(B, H, W, threshold=0.8625)
+    inputs, _, _, _, _ = synthetic.make_batch(B, H, W, seed=1, with_instances=False)
+    inputs = _dev(inputs)
+    weights = [w.to(DEV) for w in restate.gauss_distance_weight(4, H, W)]
+
+    def oracle_loss(inp, ids, flows, mobiles, inst, scales, cams):
+        return restate.loss_forward(opt, inp, ids, flows, mobiles, inst, scales, cams, mode="TG", weights=weights,
+                                    photometric=True, ssim_on=True)
+
+    def build(**kw):
+        torch.manual_seed(0)
+        return TrainStep(opt, nets=StandInNets(width=8), device=DEV, lr=1e-3, fine_tune_flow_motion=fine_tune, **kw)
+
+    return inputs, build, oracle_loss
+
+
+@pytest.mark.parametrize("fine_tune", [False, True])
+def test_train_step_with_the_cuda_loss_equals_the_step_with_the_oracle_loss(fine_tune):
+    """One optimisation step (nets -> loss -> backward -> clip -> Adam, trainer.py:223-287) with the CUDA loss -- graph
+    replay, PoseNet's outputs handed over as parameters -- against the same step with the oracle as the loss (the
+    reference's transformation_from_parameters + ATen composition + autograd): loss 1e-5, every trainable gradient 1e-4.
+    fine_tune=True also trains the flow / pose nets, so d/dflow and d/d(axisangle, translation) reach their weights."""
+    inputs, build, oracle_loss = _train_steps(fine_tune)
+    ts_g = build(mode="TG", photometric=True)                      # graphed loss, pose parameters (the defaults)
+    ts_o = build(loss_module=oracle_loss)
+    lg, lo = ts_g.step(inputs), ts_o.step(inputs)
+    assert float(lg["loss"]) == pytest.approx(float(lo["loss"]), rel=common.FWD_TOL)
+    for (n, a), (_, b) in zip(ts_o.nets.named_parameters(), ts_g.nets.named_parameters()):
+        if a.grad is None:
+            assert b.grad is None, n
+            continue
+        assert common.rel_max(a.grad, b.grad) <= common.GRAD_TOL, (n, common.rel_max(a.grad, b.grad))
+    if fine_tune:
+        assert ts_g.nets.posenet.head.weight.grad is not None and float(ts_g.nets.posenet.head.weight.grad.abs().sum()) > 0
+
+
+def test_graphed_train_step_equals_the_eager_one_bit_for_bit():
+    """graphs.GraphedLoss inside TrainStep: three steps (capture, then two replays on new net outputs) leave the nets with
+    exactly the parameters of three steps through the eager Loss; so do pose parameters vs pose matrices built by torch."""
+    inputs, build, _ = _train_steps(True)
+    inputs2 = {k: (v.flip(0) if k[0] == "color" else v) for k, v in inputs.items()}
+    ts_a = build(mode="TG", photometric=True, graph_loss=True)
+    ts_b = build(mode="TG", photometric=True, graph_loss=False)
+    for batch in (inputs, inputs2, inputs):
+        la, lb = ts_a.step(batch), ts_b.step(batch)
+        assert torch.equal(la["loss"].detach(), lb["loss"].detach())
+    for (n, a), (_, b) in zip(ts_a.nets.named_parameters(), ts_b.nets.named_parameters()):
+        assert torch.equal(a, b), n
