@@ -389,7 +389,7 @@ class Workload:
                 data, _, poses = self.loss_mod._scale_data(inputs, self.ids, flows, mobiles, inst, list(self.scales), cams, post, bits)
             cfg = fz.FusedConfig(batch=B, n_pairs=2, post=post, mask_mode=_cabi.MASK_MIN, flags=flags,
                                  threshold=opt.threshold if post != 0 else None, alpha=opt.alpha, w_d2_sim=opt.w_d2_sim,
-                                 w_e=opt.w_e, w_s=opt.w_s, w_c=opt.w_c, w_p=opt.w_p)
+                                 w_e=opt.w_e, w_s=opt.w_s, w_c=opt.w_c, w_p=opt.w_p, inst_ready=self.loss_mod._inst_ready)
             need = [{"flow": [True, True], "mob": [True, True], "fmat": [False, False]} for _ in data]
             g_cams = [torch.empty_like(c) for c in poses[1]]
             loss_out, grads, _, call = fz.run_fused(cfg, data, need, lib, poses=([c.detach() for c in poses[1]], poses[2]), g_cams=g_cams)

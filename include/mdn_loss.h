@@ -135,6 +135,11 @@ typedef struct MdnLossDesc {
   const float* translation[MDN_MAX_PAIRS];
   float* g_axisangle[MDN_MAX_PAIRS];
   float* g_translation[MDN_MAX_PAIRS];
+  /* Optional (ABI 3): a cudaEvent_t recorded, on ANOTHER stream, after the work that produces scale[s].inst (the DS / DC
+   * instance masks: mdn_instance_mask_union / _resize).  The call launches its pre-pass (source repack, SN maxima) first
+   * and makes `stream` wait for the event only in front of the kernels that read the masks, so the mask preparation
+   * overlaps the pre-pass.  NULL: the masks are ready in stream order, as every other input. */
+  void* inst_ready;
 } MdnLossDesc;
 
 /* loss_out layout (MDN_OUT_COUNT = 8 device floats) written by mdn_loss_fused.  MDN_OUT_APPLIED is the upstream

@@ -39,7 +39,8 @@ class MdnLossDesc(C.Structure):
                 ("w_d2_sim", C.c_float), ("w_e", C.c_float), ("w_s", C.c_float), ("w_c", C.c_float),
                 ("w_p", C.c_float), ("scale", MdnScale * MAX_SCALES),
                 ("cam", _PAIR), ("g_cam", _PAIR), ("inv_K", _P * MAX_SCALES),
-                ("axisangle", _PAIR), ("translation", _PAIR), ("g_axisangle", _PAIR), ("g_translation", _PAIR)]
+                ("axisangle", _PAIR), ("translation", _PAIR), ("g_axisangle", _PAIR), ("g_translation", _PAIR),
+                ("inst_ready", _P)]
 
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmdn_loss.so")

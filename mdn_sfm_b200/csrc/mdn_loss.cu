@@ -1,8 +1,9 @@
 // mdn_loss.cu -- B200 (sm_100a) kernels + C ABI of the MDN_SfM loss path.  See include/mdn_loss.h.
 //
 // Kernel inventory
-//   sn_max_kernel        per-sample max / first arg-max of |e| (SN post-processing pre-pass, loss_utils.py:96)
-//   ref_pack_kernel      source images NCHW -> float4 per pixel for the warp gather (photometric term)
+//   ref_pack_kernel      the pre-pass of a call, one launch: source images NCHW -> float4 per pixel for the warp gather
+//                        (photometric term) and, in the same grid, the per-sample max / first arg-max of |e| (SN
+//                        post-processing, loss_utils.py:96)
 //   fused_tile_kernel    ONE launch over every (scale, sample, 64x16 tile): fundamental matrix from the pose, TMA-staged
 //                        input tiles, epipolar map + post-processing + masked reductions, bilinear flow warp, SSIM + L1,
 //                        smoothness, consistency, min mask, forward values AND gradients (upstream gradient 1),
@@ -288,15 +289,13 @@ MDN_DEV float post_process(const KParams& P, float e, float snmax, float wgt, fl
 }
 
 // ----------------------------------------------------------------------------------------------- SN pre-pass
-__global__ void __launch_bounds__(NTHREADS) sn_max_kernel(const KParams P, unsigned long long* keys, int chunks_per_img) {
-  // grid.x = chunk within image, grid.y = (scale * n_pairs + pair) * batch + b
-  int job = blockIdx.y;
+MDN_DEV void sn_max_block(const KParams& P, unsigned long long* keys, const int chunks_per_img, const int chunk, const int job) {
+  // chunk = chunk within image, job = (scale * n_pairs + pair) * batch + b
   int b = job % P.batch;
   int sp = job / P.batch;
   int pair = sp % P.n_pairs, s = sp / P.n_pairs;
   const KScale& S = P.sc[s];
   const int hw = S.h * S.w;
-  pdl_wait();
   float Fm[9];
   tile_fmat(P, s, pair, b, Fm);
   const float* fx = S.flow[pair] + (long long)b * 2 * hw;
@@ -317,7 +316,7 @@ __global__ void __launch_bounds__(NTHREADS) sn_max_kernel(const KParams P, unsig
     // in flight, not by its arithmetic
     const int quads = hw >> 2;
     const int per = (quads + chunks_per_img - 1) / chunks_per_img;
-    const int beg = blockIdx.x * per, end = min(quads, beg + per);
+    const int beg = chunk * per, end = min(quads, beg + per);
     const float4* fx4 = reinterpret_cast<const float4*>(fx);
     const float4* fy4 = reinterpret_cast<const float4*>(fy);
 #pragma unroll 2
@@ -329,7 +328,7 @@ __global__ void __launch_bounds__(NTHREADS) sn_max_kernel(const KParams P, unsig
     }
   } else {
     const int per = (hw + chunks_per_img - 1) / chunks_per_img;
-    const int beg = blockIdx.x * per, end = min(hw, beg + per);
+    const int beg = chunk * per, end = min(hw, beg + per);
     for (int i = beg + (int)threadIdx.x; i < end; i += blockDim.x) {
       const int y = i / S.w, x = i - y * S.w;
       consider(i, x, y, __ldg(fx + i), __ldg(fy + i));
@@ -349,15 +348,14 @@ __global__ void __launch_bounds__(NTHREADS) sn_max_kernel(const KParams P, unsig
 // NCHW planes -> one float4 (r, g, b, 0) per pixel, so that the flow-warp gather of the fused kernel fetches the
 // three channels of a bilinear corner with ONE 16-byte load (see gather_pair_packed).  Coalesced both ways: three
 // 128-byte reads and one 512-byte write per warp.  grid.y = (scale * n_pairs + pair) * batch + b.
-__global__ void __launch_bounds__(NTHREADS) ref_pack_kernel(const __grid_constant__ KParams P) {
-  pdl_wait();
-  // flat grid: scale s owns blocks [pack_begin[s], pack_begin[s + 1]), pack_blocks[s] per (pair, sample) image
+MDN_DEV void ref_pack_block(const KParams& P, const int bid) {
+  // flat list of blocks: scale s owns blocks [pack_begin[s], pack_begin[s + 1]), pack_blocks[s] per (pair, sample) image
   int s = 0;
 #pragma unroll
   for (int k = 1; k < MDN_MAX_SCALES; ++k)
-    if (k < P.n_scales && (int)blockIdx.x >= P.pack_begin[k]) s = k;
+    if (k < P.n_scales && bid >= P.pack_begin[k]) s = k;
   const KScale& S = P.sc[s];
-  const int rem = blockIdx.x - P.pack_begin[s];
+  const int rem = bid - P.pack_begin[s];
   const int job = rem / P.pack_blocks[s], blk = rem - job * P.pack_blocks[s];
   const int pair = job / P.batch, b = job - pair * P.batch;
   const int hw = S.h * S.w;
@@ -377,6 +375,20 @@ __global__ void __launch_bounds__(NTHREADS) ref_pack_kernel(const __grid_constan
   for (int q = 0; q < PACK_PX; ++q) {
     const int i = i0 + q * NTHREADS;
     if (i < hw) dst[i] = make_float4(r[q], g[q], bl[q], 0.f);
+  }
+}
+
+// The pre-pass of a call in ONE launch: blocks [0, n_pack) repack the source images, blocks [n_pack, n_pack + sn_chunks * n_keys)
+// scan for the per-sample SN maxima.  The two jobs are independent (one streams the source images, the other the flows), so
+// sharing a grid lets them overlap instead of running back to back (SN / DS / DC with the photometric term: -15 us per step).
+__global__ void __launch_bounds__(NTHREADS) ref_pack_kernel(const __grid_constant__ KParams P, unsigned long long* keys, const int n_pack,
+                                                            const int sn_chunks) {
+  pdl_wait();
+  const int bid = blockIdx.x;
+  if (bid < n_pack) ref_pack_block(P, bid);
+  else {
+    const int r = bid - n_pack;
+    sn_max_block(P, keys, sn_chunks, r % sn_chunks, r / sn_chunks);
   }
 }
 
@@ -988,25 +1000,27 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
       }
   }
   // the completion ticket is zeroed by the fused kernel itself; only the SN pre-pass needs a cleared buffer
-  if ((d->flags & MDN_TERM_EPIPOLAR) && d->post == MDN_POST_SN) {
-    size_t nkeys = (size_t)d->n_scales * d->n_pairs * d->batch;
-    if (cudaMemsetAsync(keys, 0, nkeys * sizeof(unsigned long long), stream) != cudaSuccess) return fail(MDN_ERR_CUDA, "memset failed");
-    const int chunks = 16;
-    dim3 grid(chunks, (unsigned)nkeys);
-    MDN_LAUNCH(sn_max_kernel, grid, dim3(NTHREADS), 0, stream, K, keys, chunks);
-  }
+  const bool sn_pass = (d->flags & MDN_TERM_EPIPOLAR) && d->post == MDN_POST_SN;
+  const int sn_chunks = 16;
+  const size_t nkeys = (size_t)d->n_scales * d->n_pairs * d->batch;
   const bool photo = (d->flags & MDN_TERM_PHOTO) != 0;
   if (ev) cudaEventRecord(ev[0], stream);
+  if (sn_pass && cudaMemsetAsync(keys, 0, nkeys * sizeof(unsigned long long), stream) != cudaSuccess) return fail(MDN_ERR_CUDA, "memset failed");
+  int n_pack = 0;
   if (photo && any_repack) {
-    int nblk = 0;
     for (int s = 0; s < d->n_scales; ++s) {
-      K.pack_begin[s] = nblk;
+      K.pack_begin[s] = n_pack;
       K.pack_blocks[s] = (K.sc[s].h * K.sc[s].w + NTHREADS * PACK_PX - 1) / (NTHREADS * PACK_PX);
-      nblk += K.pack_blocks[s] * d->n_pairs * d->batch;
+      n_pack += K.pack_blocks[s] * d->n_pairs * d->batch;
     }
-    K.pack_begin[d->n_scales] = nblk;
-    MDN_LAUNCH_PDL(1, ref_pack_kernel, dim3(nblk), dim3(NTHREADS), 0, stream, K);
+    K.pack_begin[d->n_scales] = n_pack;
   }
+  // one pre-pass launch: source repack blocks, then SN-maximum blocks (either part may be empty)
+  const int n_pre = n_pack + (sn_pass ? sn_chunks * (int)nkeys : 0);
+  if (n_pre > 0) MDN_LAUNCH_PDL(1, ref_pack_kernel, dim3(n_pre), dim3(NTHREADS), 0, stream, K, keys, n_pack, sn_chunks);
+  // DS / DC: the instance masks may still be in flight on another stream (their preparation overlaps the pre-pass above);
+  // the launches that read them wait for the caller's event here
+  if (d->inst_ready && cudaStreamWaitEvent(stream, (cudaEvent_t)d->inst_ready, 0) != cudaSuccess) return fail(MDN_ERR_CUDA, "cudaStreamWaitEvent failed");
   const size_t smem = fused_smem_floats(photo) * sizeof(float);
   static_assert(fused_smem_floats(true) * sizeof(float) <= 113 * 1024, "two CTAs per SM");
   bool maps = false;

@@ -65,6 +65,7 @@ class FusedConfig:
     w_p: float = 1.0
     cuda_arith: bool = True   # replay the reference's CUDA-eager rounding (MDN_OPT_CUDA_ARITH); False = its CPU rounding
     want_maps: tuple = ()   # subset of ("post_map", "ori_map", "warped", "diff", "valid", "ssim_map"), scale 0 only
+    inst_ready: object = None   # torch.cuda.Event recorded on another stream after the instance-mask preparation (MdnLossDesc.inst_ready)
 
 
 _workspaces = {}
@@ -143,6 +144,9 @@ def run_fused(cfg: FusedConfig, scales: List[ScaleData], need_grad, library=None
     if pose_params is not None:
         gp = g_pose_params or (None, None)
         call.set_pose_params(pose_params[0], pose_params[1], pose_params[2], gp[0], gp[1])
+    if cfg.inst_ready is not None:
+        call.desc.inst_ready = cfg.inst_ready.cuda_event
+        call.keep.append(cfg.inst_ready)
     loss_out = torch.empty(OUT_COUNT, dtype=torch.float32, device=dev)
     ws = _workspace(dev, call.workspace_bytes(library))
     call.run(library, loss_out, ws, _cabi.stream_ptr(loss_out))

@@ -43,6 +43,17 @@ def _c(t, what):
     return _cabi.check_tensor(t, what=what).contiguous()
 
 
+_side_streams = {}
+
+
+def _side_stream(device):
+    """One extra stream per device for work that may overlap the loss call's pre-pass (the DS / DC instance masks)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device)
+    return _side_streams[key]
+
+
 def _mode_bits(mode, ds_base):
     if mode not in MODES:
         raise ValueError("mode must be one of %s (got %r)" % (MODES, mode))
@@ -313,9 +324,23 @@ class Loss(nn.Module):
                 S.mob[1] = _c(mobile[("mobile", 1, s)], "mobile mask")
             S.weight, _ = lm._epi_extras(post, 0, h, w, tgt.device, None)
             data.append(S)
-        if bits & (OPT_INST_MASK | OPT_CROSS_ENT):   # DS / DC: the masks of every pyramid level from one pass (two launches)
-            insts = instance_masks_u8(instances_info, [(S.height, S.width) for S in data], data[0].tgt.device, self._library,
-                                      data[0].tgt.shape[0])
+        self._inst_ready = None
+        if bits & (OPT_INST_MASK | OPT_CROSS_ENT):   # DS / DC: the masks of every pyramid level from one pass (four launches)
+            dev = data[0].tgt.device
+            sizes = [(S.height, S.width) for S in data]
+            if dev.type == "cuda":
+                # on a side stream: the fused call launches its pre-pass (source repack, SN maxima) first and waits for the
+                # masks only in front of the kernels that read them (MdnLossDesc.inst_ready), so the two overlap
+                cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    insts = instance_masks_u8(instances_info, sizes, dev, self._library, data[0].tgt.shape[0])
+                    self._inst_ready = torch.cuda.Event()
+                    self._inst_ready.record(side)
+                for m in insts:
+                    m.record_stream(cur)
+            else:
+                insts = instance_masks_u8(instances_info, sizes, dev, self._library, data[0].tgt.shape[0])
             for S, m in zip(data, insts):
                 S.inst = m
         return data, F_all, poses
@@ -343,7 +368,7 @@ class Loss(nn.Module):
         cfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=len(ids), post=post, mask_mode=MASK_OWN if o.disable_min else MASK_MIN,
                                 flags=flags, threshold=getattr(o, "threshold", None) if post != fused.POST_SN else None,
                                 alpha=o.alpha, w_d2_sim=o.w_d2_sim, w_e=o.w_e, w_s=o.w_s, w_c=o.w_c,
-                                w_p=getattr(o, "w_p", 1.0) if self.photometric else 0.0)
+                                w_p=getattr(o, "w_p", 1.0) if self.photometric else 0.0, inst_ready=self._inst_ready)
         total, terms, _ = fused.fused_loss(cfg, data, self._library, fmat_all=F_all, cams=cams, inv_Ks=inv_Ks, axisangles=aas,
                                            translations=trs)
         losses = {"consis": terms[OUT_CONSIS - 1] if not o.disable_consisloss else 0, "epip": terms[OUT_EPIP - 1],

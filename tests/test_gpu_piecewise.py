@@ -286,7 +286,11 @@ def _train_steps(fine_tune):
 
     def build(**kw):
         torch.manual_seed(0)
-        return TrainStep(opt, nets=StandInNets(width=8), device=DEV, lr=1e-3, fine_tune_flow_motion=fine_tune, **kw)
+        nets = StandInNets(width=8)
+        with torch.no_grad():      # a random-init pose head emits |t| ~ 1e-3: scaled to KITTI-like magnitudes (|t| ~ 0.1), where the
+            nets.posenet.head.weight.mul_(40.0)     # epipolar geometry is not degenerate and fp32 gradients are meaningful
+            nets.posenet.head.bias.add_(torch.tensor([0.3, -0.2, 0.5, 4.0, -6.0, 9.0]))
+        return TrainStep(opt, nets=nets, device=DEV, lr=1e-3, fine_tune_flow_motion=fine_tune, **kw)
 
     return inputs, build, oracle_loss
 
@@ -306,20 +310,52 @@ def test_train_step_with_the_cuda_loss_equals_the_step_with_the_oracle_loss(fine
         if a.grad is None:
             assert b.grad is None, n
             continue
-        assert common.rel_max(a.grad, b.grad) <= common.GRAD_TOL, (n, common.rel_max(a.grad, b.grad))
+        # PoseNet's weights see the loss through a six-number bottleneck per sample: the 1e-4 the loss is held to on
+        # d/d(axisangle, translation) (checked directly below) reaches them amplified by the net's own Jacobian
+        tol = 10 * common.GRAD_TOL if n.startswith("posenet") else common.GRAD_TOL
+        assert common.rel_max(a.grad, b.grad) <= tol, (n, common.rel_max(a.grad, b.grad))
     if fine_tune:
         assert ts_g.nets.posenet.head.weight.grad is not None and float(ts_g.nets.posenet.head.weight.grad.abs().sum()) > 0
+        # the loss itself on the nets' outputs: d/d(axisangle), d/d(translation), d/dflow, d/dmobile at the plain tolerance
+        from mdn_sfm_b200.layers import PoseParameters
+        with torch.no_grad():
+            flows, mobiles, cams, _, _ = ts_g.process_batch(inputs)
+        res = []
+        for product in (False, True):
+            fl = {k: v.detach().clone().requires_grad_(True) for k, v in flows.items()}
+            mo = {k: v.detach().clone().requires_grad_(True) for k, v in mobiles.items()}
+            aa = {k: c.axisangle.detach().clone().requires_grad_(True) for k, c in cams.items()}
+            tt = {k: c.translation.detach().clone().requires_grad_(True) for k, c in cams.items()}
+            if product:
+                _, losses = ts_g.eager_loss(inputs, [-1, 1], fl, mo, None, [0, 1, 2, 3], {k: PoseParameters(aa[k], tt[k]) for k in aa})
+            else:
+                _, losses = oracle_loss(inputs, [-1, 1], fl, mo, None, [0, 1, 2, 3],
+                                        {k: restate.transformation_from_parameters(aa[k], tt[k]) for k in aa})
+            losses["loss"].backward()
+            res.append((fl, mo, aa, tt))
+        for do, dg, what in zip(res[0], res[1], ("d/dflow", "d/dmobile", "d/daxisangle", "d/dtranslation")):
+            for k in do:
+                assert common.rel_max(do[k].grad, dg[k].grad) <= common.GRAD_TOL, (what, k, common.rel_max(do[k].grad, dg[k].grad))
 
 
 def test_graphed_train_step_equals_the_eager_one_bit_for_bit():
     """graphs.GraphedLoss inside TrainStep: three steps (capture, then two replays on new net outputs) leave the nets with
     exactly the parameters of three steps through the eager Loss; so do pose parameters vs pose matrices built by torch."""
+    det, bench_ = torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False     # (the nets' cuDNN kernels, not ours)
+    try:
+        _graphed_vs_eager()
+    finally:
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = det, bench_
+
+
+def _graphed_vs_eager():
     inputs, build, _ = _train_steps(True)
     inputs2 = {k: (v.flip(0) if k[0] == "color" else v) for k, v in inputs.items()}
     ts_a = build(mode="TG", photometric=True, graph_loss=True)
     ts_b = build(mode="TG", photometric=True, graph_loss=False)
-    for batch in (inputs, inputs2, inputs):
+    for n, batch in enumerate((inputs, inputs2, inputs)):
         la, lb = ts_a.step(batch), ts_b.step(batch)
-        assert torch.equal(la["loss"].detach(), lb["loss"].detach())
+        assert torch.equal(la["loss"].detach(), lb["loss"].detach()), (n, float(la["loss"]), float(lb["loss"]))
     for (n, a), (_, b) in zip(ts_a.nets.named_parameters(), ts_b.nets.named_parameters()):
         assert torch.equal(a, b), n
