@@ -382,14 +382,17 @@ MDN_DEV void ref_pack_block(const KParams& P, const int bid) {
 // scan for the per-sample SN maxima.  The two jobs are independent (one streams the source images, the other the flows), so
 // sharing a grid lets them overlap instead of running back to back (SN / DS / DC with the photometric term: -15 us per step).
 __global__ void __launch_bounds__(NTHREADS) ref_pack_kernel(const __grid_constant__ KParams P, unsigned long long* keys, const int n_pack,
-                                                            const int sn_chunks) {
+                                                            const int n_sn, const int ratio, const int sn_chunks) {
   pdl_wait();
   const int bid = blockIdx.x;
-  if (bid < n_pack) ref_pack_block(P, bid);
-  else {
-    const int r = bid - n_pack;
-    sn_max_block(P, keys, sn_chunks, r % sn_chunks, r / sn_chunks);
-  }
+  if (n_sn == 0) { ref_pack_block(P, bid); return; }
+  // the two kinds of blocks INTERLEAVED (`ratio` repack blocks, then one SN block, ...): blocks are dispatched in index
+  // order, so a grid that lists one job after the other would run them one after the other
+  const int grp = bid / (ratio + 1), rem = bid - grp * (ratio + 1);
+  if (rem < ratio) {
+    const int k = grp * ratio + rem;
+    if (k < n_pack) ref_pack_block(P, k);
+  } else if (grp < n_sn) sn_max_block(P, keys, sn_chunks, grp % sn_chunks, grp / sn_chunks);
 }
 
 #include "mdn_fused.cuh"
@@ -1016,8 +1019,10 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
     K.pack_begin[d->n_scales] = n_pack;
   }
   // one pre-pass launch: source repack blocks, then SN-maximum blocks (either part may be empty)
-  const int n_pre = n_pack + (sn_pass ? sn_chunks * (int)nkeys : 0);
-  if (n_pre > 0) MDN_LAUNCH_PDL(1, ref_pack_kernel, dim3(n_pre), dim3(NTHREADS), 0, stream, K, keys, n_pack, sn_chunks);
+  const int n_sn = sn_pass ? sn_chunks * (int)nkeys : 0;
+  const int ratio = n_sn ? (n_pack + n_sn - 1) / n_sn : 0;            // repack blocks per SN block (0: SN blocks only)
+  const int n_pre = n_sn ? std::max(n_sn, ratio ? (n_pack + ratio - 1) / ratio : 0) * (ratio + 1) : n_pack;
+  if (n_pre > 0) MDN_LAUNCH_PDL(1, ref_pack_kernel, dim3(n_pre), dim3(NTHREADS), 0, stream, K, keys, n_pack, n_sn, ratio, sn_chunks);
   // DS / DC: the instance masks may still be in flight on another stream (their preparation overlaps the pre-pass above);
   // the launches that read them wait for the caller's event here
   if (d->inst_ready && cudaStreamWaitEvent(stream, (cudaEvent_t)d->inst_ready, 0) != cudaSuccess) return fail(MDN_ERR_CUDA, "cudaStreamWaitEvent failed");

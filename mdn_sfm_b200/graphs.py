@@ -42,8 +42,10 @@ class GraphedLossStep:
     def _step(self):
         for t in self.leaves:
             t.grad = None
-        self.outputs, losses = self.loss_module(*self.args)
-        losses["loss"].backward()
+        with torch.enable_grad():
+            self.outputs, losses = self.loss_module(*self.args)
+            if losses["loss"].requires_grad:       # (a forward-only capture when nothing is differentiable)
+                losses["loss"].backward()
         return {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}
 
     def replay(self):

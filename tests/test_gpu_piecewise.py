@@ -318,8 +318,7 @@ def test_train_step_with_the_cuda_loss_equals_the_step_with_the_oracle_loss(fine
         assert ts_g.nets.posenet.head.weight.grad is not None and float(ts_g.nets.posenet.head.weight.grad.abs().sum()) > 0
         # the loss itself on the nets' outputs: d/d(axisangle), d/d(translation), d/dflow, d/dmobile at the plain tolerance
         from mdn_sfm_b200.layers import PoseParameters
-        with torch.no_grad():
-            flows, mobiles, cams, _, _ = ts_g.process_batch(inputs)
+        flows, mobiles, cams, _, _ = ts_g.process_batch(inputs)
         res = []
         for product in (False, True):
             fl = {k: v.detach().clone().requires_grad_(True) for k, v in flows.items()}
