@@ -45,6 +45,37 @@ def test_struct_layout_matches_header():
     assert c_ == _cabi.MdnScale.g_flow.offset and d_ == _cabi.MdnLossDesc.scale.offset
 
 
+def test_integration_stub_matches_the_header():
+    """The ctypes structures printed in INTEGRATION.md (what a maintainer would copy) are EXECUTED and every field's offset
+    and both sizes are held to the C compiler's view of include/mdn_loss.h; the block must also be what
+    scripts/gen_integration_stub.py generates from the product's own binding."""
+    import subprocess
+    import sys
+    import tempfile
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index("<!-- stub:begin -->"):doc.index("<!-- stub:end -->")]
+    code = block[block.index("```python") + len("```python"):block.rindex("```")]
+    ns = {}
+    exec(code, ns)
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import gen_integration_stub
+    assert gen_integration_stub.stub().strip() in doc, "INTEGRATION.md stub is stale: run scripts/gen_integration_stub.py"
+    items = []
+    for cls in ("MdnScale", "MdnLossDesc"):
+        items.append(("sizeof(%s)" % cls, ctypes.sizeof(ns[cls])))
+        for name, _ in ns[cls]._fields_:
+            items.append(("offsetof(%s,%s)" % (cls, name), getattr(ns[cls], name).offset))
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "off.c")
+        body = "".join('printf("%%zu\\n", (size_t)%s);' % expr for expr, _ in items)
+        open(c, "w").write('#include <stdio.h>\n#include <stddef.h>\n#include "mdn_loss.h"\nint main(){%s return 0;}' % body)
+        exe = os.path.join(d, "off")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        got = [int(v) for v in subprocess.check_output([exe]).split()]
+    for (expr, mine), theirs in zip(items, got):
+        assert mine == theirs, (expr, mine, theirs)
+
+
 def test_product_refuses_cpu_tensors():
     import torch
     from mdn_sfm_b200 import synthetic
