@@ -28,7 +28,21 @@ __global__ void __launch_bounds__(NTHREADS) instance_union_kernel(const __grid_c
   const bool pair = (hw & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 1) == 0;
   if (pair) {   // two pixels per thread (375 x 1242 is even, not a multiple of 4)
     const long long n2 = hw >> 1;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const long long step = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // four independent pixel pairs in flight per thread (the pass waits on load latency, not on arithmetic)
+    for (; i + 3 * step < n2; i += 4 * step) {
+      unsigned v[4] = {0, 0, 0, 0};
+      for (int k = 0; k < n; ++k) {
+        const unsigned short* p = reinterpret_cast<const unsigned short*>(src + (long long)k * hw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] |= __ldg(p + i + q * step);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        reinterpret_cast<unsigned short*>(dst)[i + q * step] = (unsigned short)(((v[q] & 0xffu) ? 1u : 0u) | ((v[q] & 0xff00u) ? 0x100u : 0u));
+    }
+    for (; i < n2; i += step) {
       unsigned v = 0;
       for (int k = 0; k < n; ++k) v |= __ldg(reinterpret_cast<const unsigned short*>(src + (long long)k * hw) + i);
       reinterpret_cast<unsigned short*>(dst)[i] = (unsigned short)(((v & 0xffu) ? 1u : 0u) | ((v & 0xff00u) ? 0x100u : 0u));

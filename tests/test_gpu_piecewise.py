@@ -319,22 +319,31 @@ def test_train_step_with_the_cuda_loss_equals_the_step_with_the_oracle_loss(fine
         # the loss itself on the nets' outputs: d/d(axisangle), d/d(translation), d/dflow, d/dmobile at the plain tolerance
         from mdn_sfm_b200.layers import PoseParameters
         flows, mobiles, cams, _, _ = ts_g.process_batch(inputs)
-        res = []
-        for product in (False, True):
-            fl = {k: v.detach().clone().requires_grad_(True) for k, v in flows.items()}
-            mo = {k: v.detach().clone().requires_grad_(True) for k, v in mobiles.items()}
-            aa = {k: c.axisangle.detach().clone().requires_grad_(True) for k, c in cams.items()}
-            tt = {k: c.translation.detach().clone().requires_grad_(True) for k, c in cams.items()}
-            if product:
+        res = {}
+        for which in ("oracle64", "oracle", "product"):
+            dt = torch.float64 if which == "oracle64" else torch.float32
+            own = lambda v: v.detach().to(dt).clone().requires_grad_(True)
+            fl, mo = {k: own(v) for k, v in flows.items()}, {k: own(v) for k, v in mobiles.items()}
+            aa, tt = {k: own(c.axisangle) for k, c in cams.items()}, {k: own(c.translation) for k, c in cams.items()}
+            if which == "product":
                 _, losses = ts_g.eager_loss(inputs, [-1, 1], fl, mo, None, [0, 1, 2, 3], {k: PoseParameters(aa[k], tt[k]) for k in aa})
             else:
-                _, losses = oracle_loss(inputs, [-1, 1], fl, mo, None, [0, 1, 2, 3],
+                inp = {k: v.to(dt) for k, v in inputs.items()}
+                _, losses = oracle_loss(inp, [-1, 1], fl, mo, None, [0, 1, 2, 3],
                                         {k: restate.transformation_from_parameters(aa[k], tt[k]) for k in aa})
             losses["loss"].backward()
-            res.append((fl, mo, aa, tt))
-        for do, dg, what in zip(res[0], res[1], ("d/dflow", "d/dmobile", "d/daxisangle", "d/dtranslation")):
+            res[which] = (fl, mo, aa, tt)
+        for d64, do, dg, what in zip(res["oracle64"], res["oracle"], res["product"], ("d/dflow", "d/dmobile", "d/daxisangle", "d/dtranslation")):
             for k in do:
-                assert common.rel_max(do[k].grad, dg[k].grad) <= common.GRAD_TOL, (what, k, common.rel_max(do[k].grad, dg[k].grad))
+                if what in ("d/dflow", "d/dmobile"):       # per-pixel gradients: against the reference's own fp32 arithmetic
+                    assert common.rel_max(do[k].grad, dg[k].grad) <= common.GRAD_TOL, (what, k, common.rel_max(do[k].grad, dg[k].grad))
+                else:
+                    # the six pose gradients are sums over every pixel of terms of both signs: in fp32 the REFERENCE's own
+                    # result is only good to a few 1e-4 of the float64 value here.  The product is held to the float64 truth,
+                    # to the plain tolerance or twice the reference's own fp32 error, whichever is larger.
+                    floor = common.rel_max(d64[k].grad, do[k].grad)
+                    err = common.rel_max(d64[k].grad, dg[k].grad)
+                    assert err <= max(common.GRAD_TOL, 2 * floor), (what, k, err, floor)
 
 
 def test_graphed_train_step_equals_the_eager_one_bit_for_bit():
