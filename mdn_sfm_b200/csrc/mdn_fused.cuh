@@ -735,7 +735,10 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
           } else { R.fx = load_pair(flx, y); R.fy = load_pair(fly, y); }
           R.m0 = ld2s(mq0 + k * S2);
           R.m1 = minmode ? ld2s(sM1 + o2own + k * S2) : R.m0;
-          if (use_wgt) R.wgt = load_pair(S.weight, y);
+          if (use_wgt) {
+            R.wgt = load_pair(S.weight, y);
+            if (!in1) R.wgt.y = 1.f;     // (odd widths: the column past the image must not turn 1 / weight into inf, inf * 0 = NaN)
+          }
           if (use_inst & (y < h) & in0) {
             const uint8_t* ip = S.inst + (size_t)b * hw + (unsigned)(y * w + px0);
             R.kin = make_float2((float)__ldg(ip), in1 ? (float)__ldg(ip + 1) : 0.f);

@@ -244,7 +244,7 @@ def test_image_pyramid_on_gpu_matches_torchvision():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(2, 6, 8), (1, 17, 20), (2, 16, 64), (1, 40, 132), (3, 21, 76), (1, 2, 4)])
+@pytest.mark.parametrize("shape", [(2, 6, 8), (1, 17, 20), (2, 16, 64), (1, 40, 132), (3, 21, 76), (1, 2, 4), (2, 19, 45), (1, 8, 9)])
 def test_tma_staging_on_images_smaller_than_the_box(shape):
     """The TMA box (72 x 20) is larger than these images / their edge tiles: out-of-tensor elements must arrive as zeros and
     the reflected ring must be patched from inside the tile -- every mode family against the oracle on the same GPU."""
