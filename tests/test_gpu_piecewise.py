@@ -329,8 +329,13 @@ def test_train_step_with_the_cuda_loss_equals_the_step_with_the_oracle_loss(fine
                 _, losses = ts_g.eager_loss(inputs, [-1, 1], fl, mo, None, [0, 1, 2, 3], {k: PoseParameters(aa[k], tt[k]) for k in aa})
             else:
                 inp = {k: v.to(dt) for k, v in inputs.items()}
-                _, losses = oracle_loss(inp, [-1, 1], fl, mo, None, [0, 1, 2, 3],
-                                        {k: restate.transformation_from_parameters(aa[k], tt[k]) for k in aa})
+                # (the reference allocates its pose matrices with torch.zeros: the default dtype decides their precision)
+                torch.set_default_dtype(dt)
+                try:
+                    _, losses = oracle_loss(inp, [-1, 1], fl, mo, None, [0, 1, 2, 3],
+                                            {k: restate.transformation_from_parameters(aa[k], tt[k]) for k in aa})
+                finally:
+                    torch.set_default_dtype(torch.float32)
             losses["loss"].backward()
             res[which] = (fl, mo, aa, tt)
         for d64, do, dg, what in zip(res["oracle64"], res["oracle"], res["product"], ("d/dflow", "d/dmobile", "d/daxisangle", "d/dtranslation")):
