@@ -205,29 +205,41 @@ MDN_DEV void fundamental_from_pose(const float* cam, const float* kp, float* F) 
   fundamental_from_m1(M1, kp, F);
 }
 
+// One scale's term of dL/dM1 = sum_s K gF K^T (K = K^-1 of scale s, kp its (4,4) row-major matrix of the sample)
+MDN_DEV void fundamental_bwd_scale_term(const float* kp, const float* gF, float* T2) {
+  float K[9], KT[9], T1[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { K[r * 3 + c] = kp[r * 4 + c]; KT[c * 3 + r] = kp[r * 4 + c]; }
+  mat3_mul(K, gF, T1);
+  mat3_mul(T1, KT, T2);
+}
+
+MDN_DEV void fundamental_bwd_finish(const FundArgs& A, const float* G1, int p, int b);
+
 // d(loss)/d(cam[p][b]) from d(loss)/dF of every scale; g_fmat is [n_scales][n_pairs][batch][9]
 MDN_DEV void fundamental_bwd_one(const FundArgs& A, const float* g_fmat, int p, int b) {
-  float R[9], tx[9], G1[9], cam[16];
-  load_cam(A, p, b, cam);
-  load_pose(cam, R, tx);
+  float G1[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) G1[k] = 0.f;
-  for (int s = 0; s < A.n_scales; ++s) {                // dL/dM1 = sum_s K gF K^T   (K = K^-1 of scale s)
-    float K[9], KT[9], T1[9], T2[9];
-    const float* kp = A.inv_K[s] + b * 16;
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { K[r * 3 + c] = kp[r * 4 + c]; KT[c * 3 + r] = kp[r * 4 + c]; }
+  for (int s = 0; s < A.n_scales; ++s) {
+    float T2[9], gF[9];
     const float* g = g_fmat + ((size_t)(s * A.n_pairs + p) * A.batch + b) * 9;
-    float gF[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) gF[k] = __ldcg(g + k);
-    mat3_mul(K, gF, T1);
-    mat3_mul(T1, KT, T2);
+    fundamental_bwd_scale_term(A.inv_K[s] + b * 16, gF, T2);
 #pragma unroll
     for (int k = 0; k < 9; ++k) G1[k] += T2[k];
   }
+  fundamental_bwd_finish(A, G1, p, b);
+}
+
+// ... from G1 = dL/dM1 (the scale terms added in scale order)
+MDN_DEV void fundamental_bwd_finish(const FundArgs& A, const float* G1, int p, int b) {
+  float R[9], tx[9], cam[16];
+  load_cam(A, p, b, cam);
+  load_pose(cam, R, tx);
   float txT[9], RT[9], gR[9], gTx[9];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
@@ -422,6 +434,7 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
   const KParams& P = Q.K;
   __shared__ float part4[MDN_MAX_SCALES][FIN_ROWS][NSLOT];
   __shared__ float tots4[MDN_MAX_SCALES][NSLOT];
+  __shared__ float pose_terms[MDN_MAX_SCALES][MDN_MAX_PAIRS][9];
   __shared__ bool is_last;
   pdl_wait();
   const int b = blockIdx.x;
@@ -437,14 +450,29 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
     float t[MDN_MAX_SCALES];
 #pragma unroll
     for (int s = 0; s < MDN_MAX_SCALES; ++s) t[s] = 0.f;
-    for (int item = row; item < cum[MDN_MAX_SCALES]; item += FIN_ROWS) {
-      int s = 0;
+    // first tile of the sample at each scale, minus the scale's offset in the sample's list
+    int first[MDN_MAX_SCALES];
 #pragma unroll
-      for (int q = 1; q < MDN_MAX_SCALES; ++q) s += (item >= cum[q]) ? 1 : 0;
-      const KScale& Z = P.sc[s];
-      const float v = __ldcg(P.partials + ((long long)Z.tile_begin + (long long)b * (Z.tiles_x * Z.tiles_y) + (item - cum[s])) * NSLOT + slot);
+    for (int s = 0; s < MDN_MAX_SCALES; ++s) first[s] = (s < P.n_scales ? P.sc[s].tile_begin + b * (cum[s + 1] - cum[s]) : 0) - cum[s];
+    // four loads in flight per thread (the pass is a chain of L2 round trips otherwise); added in list order, as before
+    constexpr int FU = 4;
+    for (int item0 = row; item0 < cum[MDN_MAX_SCALES]; item0 += FU * FIN_ROWS) {
+      float v[FU];
+      int sc[FU];
 #pragma unroll
-      for (int q = 0; q < MDN_MAX_SCALES; ++q) t[q] += (q == s) ? v : 0.f;
+      for (int u = 0; u < FU; ++u) {
+        const int item = item0 + u * FIN_ROWS;
+        int s = 0, f = first[0];
+#pragma unroll
+        for (int q = 1; q < MDN_MAX_SCALES; ++q)
+          if (item >= cum[q]) { s = q; f = first[q]; }
+        sc[u] = s;
+        v[u] = (item < cum[MDN_MAX_SCALES]) ? __ldcg(P.partials + (unsigned)((f + item) * NSLOT + slot)) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < FU; ++u)
+#pragma unroll
+        for (int q = 0; q < MDN_MAX_SCALES; ++q) t[q] += (q == sc[u]) ? v[u] : 0.f;
     }
 #pragma unroll
     for (int s = 0; s < MDN_MAX_SCALES; ++s) part4[s][row][slot] = t[s];
@@ -465,6 +493,7 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
     const float (*part)[NSLOT] = &tots4[s];     // part[0][k] = this scale's sums
 
     float gF[9];
+#pragma unroll
     for (int k = 0; k < 9; ++k) gF[k] = part[0][pair * PAIR_SLOTS + SL_GF + k];
     if (P.post == MDN_POST_SN) {
       // d/d(max): -(2/M) * c_epi * sum(bg*post), routed to the first arg-max pixel (loss_utils.py:96-98 backward)
@@ -477,6 +506,7 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
         const float* flx = S.flow[pair] + (long long)b * 2 * hw;
         float Fm[9];
         const float* Fsrc = has_pose(P, pair) ? P.fmat_ws + ((size_t)(s * P.n_pairs + pair) * P.batch + b) * 9 : S.fmat[pair] + b * 9;
+#pragma unroll
         for (int k = 0; k < 9; ++k) Fm[k] = Fsrc[k];
         float u = __fadd_rn((float)x, __fmul_rn(S.sx, flx[idx]));
         float v = __fadd_rn((float)y, __fmul_rn(S.sy, flx[hw + idx]));
@@ -495,13 +525,23 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
         gF[6] += g2 * xf; gF[7] += g2 * yf; gF[8] += g2;
       }
     }
-    if (Q.g_fmat[s][pair])
+    if (Q.g_fmat[s][pair]) {
+#pragma unroll
       for (int k = 0; k < 9; ++k) Q.g_fmat[s][pair][b * 9 + k] = gF[k];
-    if (Q.gf_ws)
+    }
+    if (Q.gf_ws) {
+#pragma unroll
       for (int k = 0; k < 9; ++k) Q.gf_ws[((size_t)(s * P.n_pairs + pair) * P.batch + b) * 9 + k] = gF[k];
+      // the pose adjoint's term of this (scale, pair), K gF K^T, while the matrix is in registers
+      float T2[9];
+      fundamental_bwd_scale_term(P.inv_K[s] + b * 16, gF, T2);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) pose_terms[s][pair][k] = T2[k];
+    }
   }
   __syncthreads();
-  // pose adjoint of this sample (what mdn_fundamental_bwd computes) from the d/dF written above by this block
+  // pose adjoint of this sample (what mdn_fundamental_bwd computes): the scale terms added in scale order, then the
+  // adjoint of M1 = [t]x R and of the pose parameters
   if (Q.gf_ws && threadIdx.x < (unsigned)P.n_pairs && (Q.g_cam[threadIdx.x] || Q.g_aa[threadIdx.x] || Q.g_tr[threadIdx.x])) {
     FundArgs A;
     for (int k = 0; k < MDN_MAX_SCALES; ++k) A.inv_K[k] = P.inv_K[k];
@@ -510,7 +550,14 @@ __global__ void __launch_bounds__(FIN_ROWS * NSLOT) finish_kernel(const __grid_c
       A.g_cam[k] = Q.g_cam[k]; A.g_aa[k] = Q.g_aa[k]; A.g_tr[k] = Q.g_tr[k];
     }
     A.n_scales = P.n_scales; A.n_pairs = P.n_pairs; A.batch = P.batch;
-    fundamental_bwd_one(A, Q.gf_ws, threadIdx.x, b);
+    float G1[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) G1[k] = 0.f;
+    for (int s = 0; s < P.n_scales; ++s) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) G1[k] += pose_terms[s][threadIdx.x][k];
+    }
+    fundamental_bwd_finish(A, G1, threadIdx.x, b);
   }
   // last block to arrive folds the per-sample sums into the loss scalars, in a fixed order
   __threadfence();
@@ -1357,8 +1404,37 @@ static int launch_resize(const TIn* src, int32_t batch, int32_t in_h, int32_t in
   A.row_begin[n_out] = hrows; A.vrow_begin[n_out] = vrows;
   cudaStream_t st = (cudaStream_t)stream;
   MDN_LAUNCH(instance_resize_weights_kernel, dim3((n_idx + NTHREADS / 32 - 1) / (NTHREADS / 32)), dim3(NTHREADS), 0, st, A, n_idx);
-  { auto kfn = instance_resize_h_kernel<TIn>; MDN_LAUNCH(kfn, dim3(hrows), dim3(128), 0, st, A, src); }
-  { auto kfn = instance_resize_v_kernel<TOut>; MDN_LAUNCH(kfn, dim3(vrows), dim3(128), 0, st, A); }
+  // {0,1} masks: one fused pass out of bit-packed rows when every level's source window fits a block's shared memory
+  // (down-scaling factors up to ~15 at these widths); otherwise, and for fp32 images, the two separable passes
+  bool fused = sizeof(TIn) == 1 && sizeof(TOut) == 1 && !getenv("MDN_RESIZE_TWO_PASS");
+  int frows = 0;
+  for (int k = 0; k < n_out && fused; ++k) {
+    const double sy = std::max(1.0, (double)in_h / out_h[k]), sx = std::max(1.0, (double)in_w / out_w[k]);
+    const int ty = aa_taps(in_h, out_h[k]), tx = aa_taps(in_w, out_w[k]);
+    const int cols = std::min(128, (int)out_w[k]);
+    // source columns a 128-column chunk can span (+ alignment to a 32-pixel word + the funnel shift's slack word)
+    const int words = (int)std::ceil((cols * sx + tx + 2) / 32.0) + 2;
+    // R output rows need at most (R - 1) sy + 1 + ty source rows
+    if (words > AF_W || ty + 1 > AF_NR) { fused = false; break; }
+    const int R = std::min((int)std::floor((AF_NR - ty - 1) / sy) + 1, 16);
+    A.frows[k] = R;
+    A.frow_begin[k] = frows;
+    frows += batch * ((out_h[k] + R - 1) / R) * ((out_w[k] + 127) / 128);
+  }
+  A.frow_begin[n_out] = frows;
+  const int nwg = (in_w + 31) / 32 + 1;      // packed row pitch in words (one zero word of slack)
+  if (fused && (size_t)batch * in_h * nwg * sizeof(unsigned) > (size_t)batch * in_h * out_w[0] * sizeof(float)) fused = false;
+  if (fused) {
+    unsigned* gbits = reinterpret_cast<unsigned*>(A.tmp[0]);     // (the two-pass temporary of level 0 is free on this path)
+    const long long n_words = (long long)batch * in_h * nwg;
+    (void)n_words;
+    MDN_LAUNCH(mask_bitpack_kernel, dim3(std::min(batch * in_h, 148 * 16)), dim3(NTHREADS), 0, st,
+               reinterpret_cast<const uint8_t*>(src), gbits, batch * in_h, (int)in_w, nwg);
+    MDN_LAUNCH(instance_mask_resize_fused_kernel, dim3(frows), dim3(128), 0, st, A, (const unsigned*)gbits, nwg);
+  } else {
+    { auto kfn = instance_resize_h_kernel<TIn>; MDN_LAUNCH(kfn, dim3(hrows), dim3(128), 0, st, A, src); }
+    { auto kfn = instance_resize_v_kernel<TOut>; MDN_LAUNCH(kfn, dim3(vrows), dim3(128), 0, st, A); }
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }

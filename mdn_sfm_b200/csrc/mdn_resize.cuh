@@ -73,6 +73,8 @@ struct ResizeArgs {
   int vrow_begin[MDN_MAX_SCALES + 1];  // ... vertical pass (output rows)
   int n_out, batch, ih, iw;
   int packed;                          // fp32 outputs as one (r, g, b, 0) float4 per pixel (planes = images x 3)
+  int frows[MDN_MAX_SCALES];           // fused mask pass: output rows per block
+  int frow_begin[MDN_MAX_SCALES + 1];  // ... first blockIdx.x of each output size
 };
 
 MDN_DEV float aa_tri(float x) { x = x < 0.f ? -x : x; return x < 1.f ? __fsub_rn(1.f, x) : 0.f; }
@@ -269,6 +271,137 @@ __global__ void __launch_bounds__(128) instance_resize_v_kernel(const __grid_con
     TOut* dst = reinterpret_cast<TOut*>(A.dst[k]) + ((long long)b * oh + oy0 + r) * ow + ox;
     if (sizeof(TOut) == 1) *dst = (TOut)rintf(out[r]);      // torch.round, then the cast back to integers
     else *dst = (TOut)out[r];
+  }
+}
+
+// The {0,1} MASK path: the mask is bit-packed once (mask_bitpack_kernel, 1 bit per pixel), then ONE launch does both
+// passes: a block owns 128 output columns x frows[k] output rows of one (size k, sample).  It (1) fetches the packed
+// source rows its outputs need, (2) runs the horizontal pass out of those bits -- a tap is `if (bit) t += w`, exactly the
+// library's `t += byte * w` for a {0,1} byte, in tap order -- keeping the fp32 intermediate in shared memory instead
+// of the (B, in_h, out_w) global temporary, and (3) the vertical pass + round-half-even.  Same arithmetic, same order,
+// bit-identical to the two-pass kernels above; a source row is read as 1 bit per tap instead of 1 byte load per tap, and
+// the 2 x 21 MB round trip of the temporary (B = 12, 375 x 1242 -> 4 levels) is gone.
+constexpr int AF_NR = 48;      // source rows a block can hold
+constexpr int AF_W = 56;       // 32-pixel words per packed row (incl. one word of slack for the funnel shift)
+static_assert(AF_W <= 64, "the fill loop maps 64 threads to a packed row");
+
+// {0,1} bytes -> bits: word j of row r holds pixels 32 j .. 32 j + 31 (a warp reads 32 consecutive bytes, __ballot_sync
+// makes them one word); rows are `nwg` words apart, zero past the image
+__global__ void __launch_bounds__(NTHREADS) mask_bitpack_kernel(const uint8_t* __restrict__ src, unsigned* __restrict__ bits, const int rows,
+                                                                const int iw, const int nwg) {
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {          // a block packs whole rows: uniform trip counts
+    const uint8_t* sr = src + (long long)r * iw;
+    unsigned* br = bits + (long long)r * nwg;
+#pragma unroll 2
+    for (int j0 = 0; j0 < nwg; j0 += NTHREADS / 32) {
+      const int j = j0 + wrp, x = 32 * j + lane;
+      const unsigned v = (j < nwg && x < iw) ? (unsigned)__ldg(sr + x) : 0u;
+      const unsigned m = __ballot_sync(0xffffffffu, v != 0u);
+      if (j < nwg && lane == 0) br[j] = m;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) instance_mask_resize_fused_kernel(const __grid_constant__ ResizeArgs A, const unsigned* __restrict__ gbits, const int nwg) {
+  __shared__ unsigned bits[AF_NR][AF_W];
+  __shared__ float tmpS[AF_NR][128];
+  // blocks are numbered from the LAST output size backwards: in a pyramid that is the smallest level, whose blocks walk the
+  // most source rows per output row -- the longest blocks start first
+  const int bid = (int)(gridDim.x - 1 - blockIdx.x);
+  int k = 0;
+#pragma unroll
+  for (int q = 1; q < MDN_MAX_SCALES; ++q)
+    if (q < A.n_out && bid >= A.frow_begin[q]) k = q;
+  const int oh = A.oh[k], ow = A.ow[k], R = A.frows[k];
+  const int chunks = (ow + 127) / 128;
+  int rem = bid - A.frow_begin[k];
+  const int cx = rem % chunks;
+  rem /= chunks;
+  const int groups = (oh + R - 1) / R;
+  const int b = rem / groups, oy0 = (rem - b * groups) * R;
+  const int tid = threadIdx.x;
+  const int ox = cx * 128 + tid;
+  const bool live = ox < ow;
+  // source window of the block: spans are monotone in the output index
+  const int2 xf = __ldg(A.xspan[k] + cx * 128), xl = __ldg(A.xspan[k] + min(ow, cx * 128 + 128) - 1);
+  const int w_lo = xf.x & ~31;
+  const int nw = min(((xl.x + xl.y - w_lo + 31) >> 5) + 1, AF_W);
+  const int oy1 = min(oy0 + R, oh) - 1;
+  const int2 yf = __ldg(A.yspan[k] + oy0), yl = __ldg(A.yspan[k] + oy1);
+  const int y_lo = yf.x, nr = min(yl.x + yl.y - yf.x, AF_NR);
+  // (1) the packed rows [y_lo, y_lo + nr) x words [w_lo / 32, w_lo / 32 + nw) of the sample
+  {
+    const unsigned* gb = gbits + ((long long)b * A.ih + y_lo) * nwg + (w_lo >> 5);
+    const int jmax = nwg - (w_lo >> 5);
+    const int j = tid & 63;               // (AF_W <= 64: two rows per trip, no division)
+    if (j < nw)
+      for (int r = tid >> 6; r < nr; r += 2) bits[r][j] = (j < jmax) ? __ldg(gb + (unsigned)(r * nwg + j)) : 0u;
+  }
+  __syncthreads();
+  // (2) horizontal pass: column ox of every packed row, eight rows share a weight load
+  if (live) {
+    const int2 sp = __ldg(A.xspan[k] + ox);
+    const int o = sp.x - w_lo;
+    const float* wcol = A.wxt[k] + ox;
+    for (int r0 = 0; r0 < nr; r0 += 8) {
+      float t[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t[q] = 0.f;       // (0 + w == w: the library's `t = src[0] * w[0]` start)
+      for (int jc = 0; jc < sp.y; jc += 32) {
+        const int idx = (o + jc) >> 5, sh = (o + jc) & 31;
+        unsigned win[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          win[q] = (r0 + q < nr) ? __funnelshift_r(bits[r0 + q][idx], bits[r0 + q][min(idx + 1, AF_W - 1)], sh) : 0u;
+        const int nj = min(32, sp.y - jc);
+        const float* wp = wcol + (size_t)jc * ow;
+        for (int j = 0; j < nj; ++j, wp += ow) {
+          const float wj = __ldg(wp);
+          const unsigned m = 1u << j;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (win[q] & m) t[q] = __fadd_rn(t[q], wj);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (r0 + q < nr) tmpS[r0 + q][tid] = t[q];
+    }
+  }
+  __syncthreads();
+  // (3) vertical pass, round half to even, store.  The y weights of the block's rows are the same for every column:
+  // staged in shared memory (over the packed bits, which are dead now), read back as broadcasts
+  float* wyS = reinterpret_cast<float*>(&bits[0][0]);
+  const int ty = A.ty[k], nrow = oy1 - oy0 + 1;
+  const bool w_fit = nrow * ty <= AF_NR * AF_W;
+  if (w_fit) {
+    const float* wsrc = A.wyt[k] + (unsigned)(oy0 * ty);
+    for (int i = tid; i < nrow * ty; i += 128) wyS[i] = __ldg(wsrc + i);
+  }
+  __syncthreads();
+  if (live) {
+    uint8_t* dcol = reinterpret_cast<uint8_t*>(A.dst[k]) + ((long long)b * oh + oy0) * ow + ox;
+    for (int r = 0; r < nrow; ++r) {
+      const int2 sp = __ldg(A.yspan[k] + oy0 + r);
+      const float* col = &tmpS[sp.x - y_lo][tid];
+      float out = 0.f;
+      if (w_fit) {
+        const float* wrow = wyS + r * ty;
+        if (sp.y > 0) out = __fmul_rn(col[0], wrow[0]);
+        int y = 1;
+        for (; y + 4 <= sp.y; y += 4) {
+          const float v0 = col[y * 128], v1 = col[(y + 1) * 128], v2 = col[(y + 2) * 128], v3 = col[(y + 3) * 128];
+          out = __fmaf_rn(v3, wrow[y + 3], __fmaf_rn(v2, wrow[y + 2], __fmaf_rn(v1, wrow[y + 1], __fmaf_rn(v0, wrow[y], out))));
+        }
+        for (; y < sp.y; ++y) out = __fmaf_rn(col[y * 128], wrow[y], out);
+      } else {
+        const float* wrow = A.wyt[k] + (long long)(oy0 + r) * ty;
+        if (sp.y > 0) out = __fmul_rn(col[0], __ldg(wrow));
+        for (int y = 1; y < sp.y; ++y) out = __fmaf_rn(col[y * 128], __ldg(wrow + y), out);
+      }
+      dcol[(unsigned)(r * ow)] = (uint8_t)rintf(out);
+    }
   }
 }
 

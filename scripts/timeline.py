@@ -1,5 +1,5 @@
 """GPU timeline of one graph replay of the bench step (kernels, memcpys, memsets with start offsets and gaps), from
-torch.profiler / CUPTI.  Experiment tooling: python scripts/timeline.py [--bwd 0|1] [--steps-per-graph N]"""
+torch.profiler / CUPTI.  Experiment tooling: python scripts/timeline.py [--bwd 0|1] [--steps-per-graph N] [--mode T|DC|...]"""
 import os
 import sys
 
@@ -17,22 +17,24 @@ def arg(name, default):
 
 bwd = int(arg("--bwd", "1"))
 n_per = int(arg("--steps-per-graph", "4"))
+mode = arg("--mode", "T")
+with_inst = mode in ("DS", "DC")
 B, H, W, scales = 12, 192, 640, (0, 1, 2, 3)
 opt = synthetic.default_opt(B, H, W)
 sets = []
 for i in range(4):
-    inputs, flows, mobiles, cams, inst = synthetic.make_batch(B, H, W, scales=scales, seed=42 + i, flow_std=0.05, device="cuda", with_instances=False)
+    inputs, flows, mobiles, cams, inst = synthetic.make_batch(B, H, W, scales=scales, seed=42 + i, flow_std=0.05, device="cuda", with_instances=with_inst)
     g = lambda d: {k: v.requires_grad_(True) for k, v in d.items()}
-    sets.append((inputs, g(flows), g(mobiles), g(cams)))
-loss = Loss(opt, no_ssim=False, mode="T", photometric=True)
+    sets.append((inputs, g(flows), g(mobiles), g(cams), inst))
+loss = Loss(opt, no_ssim=False, mode=mode, photometric=True)
 
 
 def step(i):
-    inputs, flows, mobiles, cams = sets[i % 4]
+    inputs, flows, mobiles, cams, inst = sets[i % 4]
     for d in (flows, mobiles, cams):
         for v in d.values():
             v.grad = None
-    _, losses = loss(inputs, [-1, 1], flows, mobiles, None, list(scales), cams)
+    _, losses = loss(inputs, [-1, 1], flows, mobiles, inst, list(scales), cams)
     if bwd:
         losses["loss"].backward()
 
@@ -64,6 +66,6 @@ t0 = evs[0].time_range.start
 prev_end = None
 for e in evs:
     gap = (e.time_range.start - prev_end) if prev_end is not None else 0.0
-    print("%9.1f us  +%6.1f gap  %7.1f us  %s" % (e.time_range.start - t0, gap, e.time_range.end - e.time_range.start, e.name[:70]))
+    print("%9.1f us  +%6.1f gap  %7.1f us  [stream %s] %s" % (e.time_range.start - t0, gap, e.time_range.end - e.time_range.start, getattr(e, "device_resource_id", "?"), e.name[:60]))
     prev_end = e.time_range.end
 print("total %.1f us for %d steps" % (evs[-1].time_range.end - t0, 3 * n_per))

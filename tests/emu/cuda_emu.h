@@ -187,6 +187,15 @@ static inline int __all_sync(unsigned, int pred) {
   for (int m = 16; m >= 1; m >>= 1) v &= mdn_emu::exchange(v, mdn_emu::st().cur ^ m);
   return (int)v;
 }
+// one bit per lane of the caller's warp (all 32 lanes call it): OR-butterfly over the shuffle rendezvous
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  unsigned v = pred ? (1u << (mdn_emu::st().cur & 31)) : 0u;
+  for (int m = 16; m >= 1; m >>= 1) v |= mdn_emu::exchange(v, mdn_emu::st().cur ^ m);
+  return v;
+}
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+  return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (shift & 31));
+}
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }

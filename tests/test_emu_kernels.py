@@ -3,6 +3,8 @@
 This is what catches tile / halo / reflection / adjoint bugs without a GPU.  It says nothing about speed and
 the product never takes this route (see tests/emu/cuda_emu.h).
 """
+import os
+
 import pytest
 import torch
 
@@ -265,6 +267,15 @@ def test_instance_mask_union_and_resize_match_torchvision(src_hw, sizes):
         bare = loss_utils.instance_masks_u8(inst[0]["instances"], sizes[:1], "cpu", lib)
     assert assert_masks_equal_up_to_exact_ties(got, inst, sizes) == 0      # (this seed has no tie)
     assert_masks_equal_up_to_exact_ties(bare, inst[0]["instances"], sizes[:1])
+    # the fused pass over bit-packed rows (the default where a block's source window fits) and the two separable passes
+    # through the global temporary perform the same fp32 operations in the same order
+    os.environ["MDN_RESIZE_TWO_PASS"] = "1"
+    try:
+        with emulated() as lib:
+            two = loss_utils.instance_masks_u8(inst, sizes, "cpu", lib)
+    finally:
+        del os.environ["MDN_RESIZE_TWO_PASS"]
+    assert all(torch.equal(a, b) for a, b in zip(got, two))
 
 
 def test_image_pyramid_matches_torchvision_resize():

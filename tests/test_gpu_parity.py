@@ -200,6 +200,17 @@ def test_instance_mask_prep_on_gpu_matches_torchvision():
     got = loss_utils.instance_masks_u8([{"instances": d["instances"].to(DEV)} for d in inst], sizes, DEV)
     assert all(m.is_cuda for m in got)
     assert_masks_equal_up_to_exact_ties(got, inst, sizes)
+    # fused pass (bit-packed rows, no global temporary) == the two separable passes, bit for bit; so does a shape whose
+    # smallest level falls back to the two passes (factor 47 > a block's 64 source rows)
+    import os
+    for szs in (sizes, [(192, 640), (8, 12)]):
+        one = loss_utils.instance_masks_u8([{"instances": d["instances"].to(DEV)} for d in inst], szs, DEV)
+        os.environ["MDN_RESIZE_TWO_PASS"] = "1"
+        try:
+            two = loss_utils.instance_masks_u8([{"instances": d["instances"].to(DEV)} for d in inst], szs, DEV)
+        finally:
+            del os.environ["MDN_RESIZE_TWO_PASS"]
+        assert all(torch.equal(a, b) for a, b in zip(one, two))
 
 
 @pytest.mark.gpu
