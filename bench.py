@@ -457,19 +457,21 @@ class Workload:
         return roof
 
 
-def host_copy_ceiling(dev, world, nbytes=64 << 20, reps=8):
-    """Pinned host -> device bandwidth of plain `reps` x 64 MB cudaMemcpyAsync on every rank AT THE SAME TIME (GB/s of this
-    rank, min over ranks): what the host's PCIe / memory system gives the e2e upload when all ranks pull together."""
+def host_copy_ceiling(dev, world, nbytes=256 << 20, reps=4):
+    """Pinned host -> device bandwidth of plain `reps` x 256 MB cudaMemcpyAsync on every rank AT THE SAME TIME (GB/s of this
+    rank, min over ranks): what the host's PCIe / memory system gives the e2e upload when all ranks pull together.
+    (Measured on this pool, scratch runs of round 2: the same copy lands anywhere between 14 and 55 GB/s from one pinned
+    allocation to the next -- NUMA placement of the pinned pages on a shared host -- and small copies scatter most; large
+    copies, the best of five rounds, give the stable upper figure.)"""
     import torch.distributed as dist
-    h = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+    from mdn_sfm_b200.staging import pinned_empty
+    h = pinned_empty(nbytes, dev)          # on the GPU's own NUMA node, like BatchStager's slabs
     d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    # the link and the pinned pages are cold after the kernel-only measurements (round 2's first version timed 8 copies after
-    # one warm-up copy and reported 24 GB/s where the step itself moved 55): 1 GB of warm-up, then the best of three rounds
-    for _ in range(16):
+    for _ in range(4):
         d.copy_(h, non_blocking=True)
     torch.cuda.synchronize()
     gbs = 0.0
-    for _ in range(3):
+    for _ in range(5):
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -620,7 +622,7 @@ def run_ours(args):
            "ms_per_step": e2e_ms, "runs_ms_per_step_sorted": runs8, "statistic": "median of 5 runs of %d steps (max over ranks per run)" % n_e2e,
            "h2d_gbs_achieved": h2d_bytes / (e2e_ms * 1e-3) / 1e9, "host_copy_ceiling_gbs": ceiling,
            "frac_of_host_copy_ceiling": h2d_bytes / (e2e_ms * 1e-3) / 1e9 / ceiling,
-           "host_copy_ceiling": "8 x 64 MB pinned cudaMemcpyAsync on every rank at the same time after 1 GB of warm-up copies, best of 3 rounds, min over ranks",
+           "host_copy_ceiling": "4 x 256 MB pinned cudaMemcpyAsync on every rank at the same time, best of 5 rounds, min over ranks",
            "path": "mdn_sfm_b200.staging.BatchStager (one pinned slab -> one H2D copy per step on a copy stream, %d buffers: three "
                    "full-resolution frames as (B,H,W,3) uint8, flows, mobile maps, poses, intrinsics) + pyramid.frames_from_u8 "
                    "(ArrayToTensor + Normalize on the device) + pyramid.add_pyramid_levels(packed_sources=True) + "

@@ -8,7 +8,57 @@ The tensors handed to the loss are views of the device slab, 256-byte aligned, c
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
+
+
+def gpu_local_cpus(device):
+    """The CPUs NVML lists as local to `device` (its NUMA node), or None when that cannot be determined."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(props.uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)).encode())
+        n_cpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return cpus or None
+    except Exception:
+        return None
+
+
+@contextlib.contextmanager
+def numa_local(device):
+    """Runs the block with the calling thread bound to the CPUs local to `device`: pinned host memory allocated inside is
+    placed on the GPU's own NUMA node (the kernel's default policy is local allocation).  On a two-socket host an unbound
+    process gets its pinned slab from either node, and a remote slab uploads at half the rate or less (measured on this
+    pool: 14 ... 55 GB/s for the same cudaMemcpyAsync from one allocation to the next); with one rank per GPU, local slabs
+    are also what lets eight uploads run at once.  No-op when NVML or the affinity calls are unavailable."""
+    cpus = gpu_local_cpus(device) if hasattr(os, "sched_setaffinity") else None
+    if not cpus:
+        yield False
+        return
+    before = os.sched_getaffinity(0)
+    try:
+        os.sched_setaffinity(0, cpus)
+        yield True
+    finally:
+        os.sched_setaffinity(0, before)
+
+
+def pinned_empty(nbytes, device):
+    """nbytes of pinned host memory on the NUMA node of `device`, touched by a local CPU before it is handed out."""
+    with numa_local(device):
+        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        t.zero_()
+    return t
 
 
 def _layout(template):
@@ -37,7 +87,7 @@ class BatchStager:
         self.n_dicts = len(template)
         self.n_buffers = n_buffers
         self.copy_stream = torch.cuda.Stream(self.device)
-        self.host = [torch.empty(self.nbytes, dtype=torch.uint8).pin_memory() for _ in range(n_buffers)]
+        self.host = [pinned_empty(self.nbytes, self.device) for _ in range(n_buffers)]     # on the GPU's own NUMA node
         self.dev = [torch.empty(self.nbytes, dtype=torch.uint8, device=self.device) for _ in range(n_buffers)]
         self.ready = [torch.cuda.Event() for _ in range(n_buffers)]     # copy of buffer k has landed
         self.free = [torch.cuda.Event() for _ in range(n_buffers)]      # consumers of buffer k have finished
