@@ -47,7 +47,10 @@ constexpr int W2 = TW + 4, S2 = TW + 8, R2H = TH + 4, OFF2 = 2, R2P = S2 * R2H;
 static_assert((R2P * 4) % 128 == 0 && S2 >= OFF2 + W2, "TMA box geometry");
 // halo-1 planes (SSIM adjoint coefficients): window rows y0-1 .. y0+TH, columns x0-1 .. x0+TW
 constexpr int S1 = TW + 4, R1H = TH + 2, R1P = S1 * R1H;
-constexpr int WPR = 3;                                // window rows per SSIM patch (2 columns x WPR rows)
+#ifndef MDN_WPR
+#define MDN_WPR 3
+#endif
+constexpr int WPR = MDN_WPR;                                // window rows per SSIM patch (2 columns x WPR rows)
 static_assert((TH + 2) % WPR == 0, "SSIM patches tile the halo-1 region exactly");
 constexpr int NCP = (TW + 2) / 2, NPATCH = NCP * ((TH + 2) / WPR);
 constexpr int RING = W2 * R2H - TW * TH;              // halo slots of the halo-2 region
@@ -1081,7 +1084,10 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
       const MdnScale& S = d->scale[s];
       maps |= S.post_map[p] || S.ori_map[p] || S.warped[p] || S.diff[p] || S.valid[p] || S.ssim_map[p];
     }
-  K.prefetch_distance = MDN_FUSED_MIN_CTAS * 148;   // one wave of resident CTAs (148 SMs on B200)
+#ifndef MDN_PREFETCH_WAVES_X2
+#define MDN_PREFETCH_WAVES_X2 2      // prefetch distance in half waves (tuning macro; 2 = one wave)
+#endif
+  K.prefetch_distance = MDN_FUSED_MIN_CTAS * 148 * MDN_PREFETCH_WAVES_X2 / 2;   // one wave of resident CTAs (148 SMs on B200)
 #ifndef MDN_EMU
   {
     // TMA descriptors for the input tiles (target image, mobile maps): one box copy per plane instead of ~400 cp.async
@@ -1118,6 +1124,11 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
       }
       K.tma_ok[s] = ok ? 1 : 0;
     }
+    // every input tile arrives by TMA: the L2 prefetch of the next wave (flows only, then) no longer pays for its
+    // instructions (measured round 2: 218.7 vs 219.5 / 201.1 vs 202.9 us per step without it); kept for cp.async staging
+    bool all_tma = true;
+    for (int s = 0; s < d->n_scales; ++s) all_tma = all_tma && K.tma_ok[s];
+    if (all_tma) K.prefetch_distance = 1 << 30;
   }
 #endif
   if (ev) cudaEventRecord(ev[1], stream);
