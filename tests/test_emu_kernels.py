@@ -278,6 +278,29 @@ def test_instance_mask_union_and_resize_match_torchvision(src_hw, sizes):
     assert all(torch.equal(a, b) for a, b in zip(got, two))
 
 
+def test_fused_mask_resize_equals_the_two_passes_on_random_shapes():
+    """The bit-packed fused resize against the two separable passes (same fp32 operations, same order) over random source /
+    output sizes, batch sizes, level counts and mask densities: up- and down-scaling, factors on both sides of the fused
+    path's limits (a block's 48 source rows / 56 packed words), sizes that are not multiples of anything."""
+    import random
+    from mdn_sfm_b200 import loss_utils, synthetic
+    rnd = random.Random(11)
+    g = torch.Generator().manual_seed(3)
+    with emulated() as lib:
+        for _ in range(12):
+            H, W = rnd.randint(3, 120), rnd.randint(3, 260)
+            sizes = [(rnd.randint(1, 130), rnd.randint(1, 290)) for _ in range(rnd.randint(1, 4))]
+            inst = [{"instances": synthetic.SyntheticInstances(torch.rand(rnd.randint(1, 3), H, W, generator=g) > rnd.choice([0.5, 0.9, 0.99]))}
+                    for _ in range(rnd.randint(1, 2))]
+            one = loss_utils.instance_masks_u8(inst, sizes, "cpu", lib)
+            os.environ["MDN_RESIZE_TWO_PASS"] = "1"
+            try:
+                two = loss_utils.instance_masks_u8(inst, sizes, "cpu", lib)
+            finally:
+                del os.environ["MDN_RESIZE_TWO_PASS"]
+            assert all(torch.equal(a, b) for a, b in zip(one, two)), ((H, W), sizes)
+
+
 def test_image_pyramid_matches_torchvision_resize():
     """mdn_image_pyramid == torchvision Resize((H/2**s, W/2**s)) of an fp32 image (bilinear + antialias),
     the three lower pyramid levels in one call; fp32 round-off only (the separable sums run in the library's order)."""
