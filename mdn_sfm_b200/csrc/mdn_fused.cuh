@@ -101,10 +101,10 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
   sm.FL = sm.D + 6 * PR * FT * 2;
 
   // ---- which tile
-  int s = 0;
+  int s = 0;      // (tile_begin decreases with the scale index: the last scale owns the first tiles, see plan_tiles)
 #pragma unroll
   for (int k = 1; k < MDN_MAX_SCALES; ++k)
-    if (k < P.n_scales && (int)blockIdx.x >= P.sc[k].tile_begin) s = k;
+    if (k < P.n_scales && (int)blockIdx.x < P.sc[k - 1].tile_begin) s = k;
   const KScale& S = P.sc[s];
   int rem = blockIdx.x - S.tile_begin;
   const int tiles_per_img = S.tiles_x * S.tiles_y;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
       int s2 = 0;
 #pragma unroll
       for (int k = 1; k < MDN_MAX_SCALES; ++k)
-        if (k < P.n_scales && nt >= P.sc[k].tile_begin) s2 = k;
+        if (k < P.n_scales && nt < P.sc[k - 1].tile_begin) s2 = k;
       const KScale& Z = P.sc[s2];
       int r2 = nt - Z.tile_begin;
       const int tpi = Z.tiles_x * Z.tiles_y;

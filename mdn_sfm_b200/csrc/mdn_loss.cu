@@ -871,9 +871,12 @@ extern "C" MDN_API const char* mdn_last_error_string(void) { return g_err; }
 
 struct WsLayout { size_t partials, sample_sums, refpack, snkeys, ticket, fmat, gfmat, total; int n_tiles; };
 
+// Tile numbering: the LAST scale's tiles come first (tile_begin decreases with the scale index).  In a pyramid those are
+// the small levels, whose tiles are mostly ragged (the slower generic paths) -- they start first and the full tiles of
+// level 0 fill the grid's tail (measured round 2: 214.1 vs 216.5 us per step).
 static int plan_tiles(const MdnLossDesc* d, KParams& K) {
   int t = 0;
-  for (int s = 0; s < d->n_scales; ++s) {
+  for (int s = d->n_scales - 1; s >= 0; --s) {
     KScale& Z = K.sc[s];
     Z.h = d->scale[s].height; Z.w = d->scale[s].width;
     Z.tiles_x = (Z.w + TW - 1) / TW; Z.tiles_y = (Z.h + TH - 1) / TH;
