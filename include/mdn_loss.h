@@ -66,11 +66,14 @@ enum MdnFlags {
   MDN_OPT_INST_MASK   = 1 << 5,  /* DS: post *= instance mask         loss_utils.py:127-138                  */
   MDN_OPT_CROSS_ENT   = 1 << 6,  /* DC: + w_d2_sim * cross entropy    loss_utils.py:72-78, loss_functions.py:132-133 */
   MDN_OPT_GRADS       = 1 << 7,  /* also write d(loss)/d(flow, mob, fmat) for an upstream gradient of 1      */
-  MDN_OPT_CUDA_ARITH  = 1 << 8   /* replay the rounding of the reference's CUDA-EAGER path where it differs from its
+  MDN_OPT_CUDA_ARITH  = 1 << 8,  /* replay the rounding of the reference's CUDA-EAGER path where it differs from its
                                     CPU path: `tensor /= python_scalar` is a multiplication by the fp32-rounded
                                     reciprocal on CUDA (ATen BinaryDivTrueKernel.cu) but a true division on the CPU.
                                     Affects grid /= (w-1), (h-1) (loss_utils.py:29-30, utils.py:309-310) and
                                     post /= threshold (loss_utils.py:86).  Without the flag: CPU rounding.          */
+  MDN_OPT_PAD_BORDER     = 1 << 9,  /* padding_mode of the flow warp's grid_sample (loss_utils.py:33; the `padding_mode`   */
+  MDN_OPT_PAD_REFLECTION = 1 << 10  /* argument of Loss / LossModule, loss_functions.py:12,161): "border" / "reflection"
+                                       instead of "zeros" (neither flag; what every caller upstream passes).  At most one. */
 };
 
 /* One pyramid level.  h = height, w = width of THIS level. */
@@ -217,8 +220,8 @@ MDN_API int mdn_epipolar_points_bwd(const float* p1, const float* p2, const floa
 MDN_API size_t mdn_epipolar_points_workspace_bytes(int32_t batch, int64_t n);
 
 /*
- * inverse_warp (loss_utils.py:12-36) / FlowWarp (utils.py:289-315): bilinear flow warp, zeros padding,
- * align_corners=True.  flow is in pixels.  warped (B,C,h,w) may be NULL (FlowWarp: grid + validity only);
+ * inverse_warp (loss_utils.py:12-36) / FlowWarp (utils.py:289-315): bilinear flow warp, align_corners=True,
+ * zeros padding (bits 2-3 of `warp_flags`: 1 = border, 2 = reflection -- grid_sample's other padding modes).  flow is in pixels.  warped (B,C,h,w) may be NULL (FlowWarp: grid + validity only);
  * grid_out (B,h,w,2) normalised grid or NULL; valid (B,h,w) uint8 or NULL.  `warp_flags` bit 0 selects the
  * (g-0.5)*2 normalisation of utils.py:311 instead of 2*g-1 (loss_utils.py:31) -- same value, other rounding;
  * bit 1 selects the CUDA-eager rounding of `/= (w-1)` (see MDN_OPT_CUDA_ARITH).

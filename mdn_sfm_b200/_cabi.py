@@ -14,7 +14,10 @@ POST_SN, POST_T, POST_TG = 0, 1, 2
 MASK_MIN, MASK_OWN, MASK_SHARED = 0, 1, 2
 TERM_EPIPOLAR, TERM_PHOTO, TERM_SMOOTH, TERM_CONSIS = 1, 2, 4, 8
 OPT_SSIM, OPT_INST_MASK, OPT_CROSS_ENT, OPT_GRADS, OPT_CUDA_ARITH = 16, 32, 64, 128, 256
+OPT_PAD_BORDER, OPT_PAD_REFLECTION = 512, 1024
+PAD_FLAG = {"zeros": 0, "border": OPT_PAD_BORDER, "reflection": OPT_PAD_REFLECTION}      # grid_sample padding_mode -> MdnFlags
 WARP_FLOWWARP_NORM, WARP_CUDA_ARITH = 1, 2
+WARP_PAD = {"zeros": 0, "border": 4, "reflection": 8}      # bits 2-3 of warp_flags
 OUT_LOSS, OUT_EPIP, OUT_SMOOTH, OUT_CONSIS, OUT_PHOTO, OUT_APPLIED, OUT_COUNT = 0, 1, 2, 3, 4, 5, 8
 
 ABI_VERSION = 3

@@ -81,7 +81,8 @@ MDN_DEV Epi epipolar_distance(const float* F, float x, float y, float u, float v
 // (align_corners=True): every op rounded on its own, exactly as the separate ATen kernels do.
 struct WarpCoord {
   float gx, gy;    // normalised grid in [-1,1]
-  float ix, iy;    // un-normalised source coordinates
+  float ix, iy;    // un-normalised source coordinates (after the padding mode's clip / reflection)
+  float mx, my;    // d(ix) / d(un-padded ix), likewise y: 1 for zeros padding
   bool valid;      // max(|gx|,|gy|) <= 1
 };
 
@@ -90,7 +91,35 @@ struct WarpGeom {
   float inv_wm1, inv_hm1;  // (float)(1.0 / (double)(w-1)): what ATen's CUDA `tensor /= scalar` multiplies by
   bool cuda_arith;         // MDN_OPT_CUDA_ARITH
   bool flowwarp_norm;      // utils.py:311 normalisation
+  int pad;                 // grid_sample padding_mode: 0 zeros, 1 border, 2 reflection (standalone warp kernels)
 };
+
+// grid_sample's padding modes on the un-normalised coordinate (ATen GridSampler.h / GridSampler.cuh, align_corners=True:
+// clip_coordinates_set_grad, reflect_coordinates_set_grad with twice_low = 0, twice_high = 2 (size - 1)).  size_m1 = size - 1
+// >= 1.  mult = d(out) / d(in): 0 where the coordinate was clipped, -1 on a reflected branch.
+constexpr int PAD_ZEROS = 0, PAD_BORDER = 1, PAD_REFLECTION = 2;
+MDN_DEV float pad_clip(float in, float size_m1, float& mult) {
+  if (in <= 0.f) { mult = 0.f; return 0.f; }
+  if (in >= size_m1) { mult = 0.f; return size_m1; }
+  mult = 1.f;
+  return in;
+}
+MDN_DEV float pad_coordinate(float in, float size_m1, int pad, float& mult) {
+  mult = 1.f;
+  if (pad == PAD_ZEROS) return in;
+  float m_refl = 1.f;
+  if (pad == PAD_REFLECTION) {
+    if (in < 0.f) { m_refl = -1.f; in = -in; }
+    const float extra = fmodf(in, size_m1);
+    const int flips = (int)floorf(__fdiv_rn(in, size_m1));
+    if (flips % 2 == 0) in = extra;
+    else { m_refl = -m_refl; in = __fsub_rn(size_m1, extra); }
+  }
+  float m_clip;
+  in = pad_clip(in, size_m1, m_clip);
+  mult = m_refl * m_clip;
+  return in;
+}
 
 MDN_DEV WarpCoord warp_coord(float x, float y, float fx, float fy, const WarpGeom& G) {
   WarpCoord c;
@@ -109,8 +138,8 @@ MDN_DEV WarpCoord warp_coord(float x, float y, float fx, float fy, const WarpGeo
   }
   c.gx = gx; c.gy = gy;
   c.valid = (fabsf(gx) <= 1.f) && (fabsf(gy) <= 1.f);
-  c.ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), wm1);
-  c.iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), hm1);
+  c.ix = pad_coordinate(__fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), wm1), wm1, G.pad, c.mx);
+  c.iy = pad_coordinate(__fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), hm1), hm1, G.pad, c.my);
   return c;
 }
 
@@ -327,7 +356,7 @@ struct GatherPx {
 
 MDN_DEV float4 ldg4(const float4* p) { return __ldg(p); }
 
-template <bool DERIV>
+template <bool DERIV, int PAD = PAD_ZEROS>
 MDN_DEV void gather_pair_packed(const float4* __restrict__ pk, int h, int w, float2 xs, float2 ys, float2 fx, float2 fy,
                                 const WarpGeom& G, GatherPx* out, bool& valid_a, bool& valid_b) {
   const float2 one = splat2(1.f), neg1 = splat2(-1.f), two = splat2(2.f);
@@ -342,8 +371,13 @@ MDN_DEV void gather_pair_packed(const float4* __restrict__ pk, int h, int w, flo
   gy = fma2(two, gy, neg1);
   valid_a = (fabsf(gx.x) <= 1.f) & (fabsf(gy.x) <= 1.f);
   valid_b = (fabsf(gx.y) <= 1.f) & (fabsf(gy.y) <= 1.f);
-  const float2 ix = mul2(add2(gx, one), splat2(0.5f * G.wm1));   // grid_sample un-normalisation, align_corners=True
-  const float2 iy = mul2(add2(gy, one), splat2(0.5f * G.hm1));
+  float2 ix = mul2(add2(gx, one), splat2(0.5f * G.wm1));   // grid_sample un-normalisation, align_corners=True
+  float2 iy = mul2(add2(gy, one), splat2(0.5f * G.hm1));
+  float2 gmx = one, gmy = one;     // border / reflection padding: the coordinate is clipped / folded back, its gradient scaled
+  if (PAD != PAD_ZEROS) {
+    ix.x = pad_coordinate(ix.x, G.wm1, PAD, gmx.x); ix.y = pad_coordinate(ix.y, G.wm1, PAD, gmx.y);
+    iy.x = pad_coordinate(iy.x, G.hm1, PAD, gmy.x); iy.y = pad_coordinate(iy.y, G.hm1, PAD, gmy.y);
+  }
   const float2 x0f = make_float2(floorf(ix.x), floorf(ix.y)), y0f = make_float2(floorf(iy.x), floorf(iy.y));
   float2 ax1 = fma2(x0f, neg1, ix), ax0 = fma2(ix, neg1, add2(x0f, one));
   float2 ay1 = fma2(y0f, neg1, iy), ay0 = fma2(iy, neg1, add2(y0f, one));
@@ -393,6 +427,11 @@ MDN_DEV void gather_pair_packed(const float4* __restrict__ pk, int h, int w, flo
                           fma2(make_float2(v01[e].x, v01[e].y), splat2(c01), mul2(make_float2(v00[e].x, v00[e].y), splat2(c00)))));
       out[e].dy[0] = dyrg.x; out[e].dy[1] = dyrg.y;
       out[e].dy[2] = fmaf(v11[e].z, c11, fmaf(v10[e].z, c10, fmaf(v01[e].z, c01, v00[e].z * c00)));
+      if (PAD != PAD_ZEROS) {
+        const float mxe = e ? gmx.y : gmx.x, mye = e ? gmy.y : gmy.x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { out[e].dx[c] *= mxe; out[e].dy[c] *= mye; }
+      }
     }
   }
 }

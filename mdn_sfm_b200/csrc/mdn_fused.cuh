@@ -72,7 +72,8 @@ MDN_DEV float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2
 
 template <bool B> struct BoolTag { static constexpr bool value = B; };
 
-template <bool PHOTO, bool MAPS>
+// PAD: grid_sample padding mode of the flow warp (0 zeros = what the reference's callers pass, 1 border, 2 reflection)
+template <bool PHOTO, bool MAPS, int PAD = 0>
 __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(const __grid_constant__ KParams P) {
   MDN_DYN_SMEM(smem_raw);
   pdl_wait();
@@ -542,7 +543,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
           const float2 fyp = make_float2(__fmul_rn(sy, fyc.x), __fmul_rn(sy, fyc.y));
           GatherPx G2[2];
           bool va, vb;
-          gather_pair_packed<true>(rfp, h, w, xs, splat2((float)(py0 + k)), fxp, fyp, geom, G2, va, vb);
+          gather_pair_packed<true, PAD>(rfp, h, w, xs, splat2((float)(py0 + k)), fxp, fyp, geom, G2, va, vb);
           put(G2, va, vb, PR * g + 2 + k, 2 * t + 2, true, true, k, fxc, fyc);
         }
       }
@@ -564,7 +565,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
         const float2 fyp = make_float2(__fmul_rn(sy, cur.fy.x), __fmul_rn(sy, cur.fy.y));
         GatherPx G2[2];
         bool va, vb;
-        gather_pair_packed<true>(rfp, h, w, make_float2((float)cur.xa, (float)cur.xb), splat2((float)cur.ya), fxp, fyp, geom, G2, va, vb);
+        gather_pair_packed<true, PAD>(rfp, h, w, make_float2((float)cur.xa, (float)cur.xb), splat2((float)cur.ya), fxp, fyp, geom, G2, va, vb);
         put(G2, va, vb, cur.r, cur.j, oka, okb, it < PR ? it : -1, cur.fx, cur.fy);
         cur = nxt;
       }

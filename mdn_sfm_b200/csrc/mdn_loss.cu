@@ -781,6 +781,7 @@ __global__ void __launch_bounds__(NTHREADS) flow_warp_bwd_kernel(const float* __
       float g = g_warped[((long long)b * C + c) * hw + i];
       gix += g * ddx; giy += g * ddy;
     }
+    gix *= wc.mx; giy *= wc.my;      // (1 with zeros padding)
     // grid_sample: * (size-1)/2 ; "2*g-1": * 2 ; "/= (size-1)": / (size-1)
     float tx = __fmul_rn(__fmul_rn(gix, __fmul_rn(wm1, 0.5f)), 2.f), ty = __fmul_rn(__fmul_rn(giy, __fmul_rn(hm1, 0.5f)), 2.f);
     g_flow[(long long)b * 2 * hw + i] = G.cuda_arith ? __fmul_rn(tx, G.inv_wm1) : __fdiv_rn(tx, wm1);
@@ -893,6 +894,7 @@ static int check_desc(const MdnLossDesc* d) {
     return fail(MDN_ERR_BAD_SHAPE, "batch / n_scales / n_pairs out of range");
   if (d->post < MDN_POST_SN || d->post > MDN_POST_TG) return fail(MDN_ERR_UNSUPPORTED, "unknown post-processing mode");
   if (d->mask_mode < MDN_MASK_MIN || d->mask_mode > MDN_MASK_SHARED) return fail(MDN_ERR_UNSUPPORTED, "unknown mask mode");
+  if ((d->flags & MDN_OPT_PAD_BORDER) && (d->flags & MDN_OPT_PAD_REFLECTION)) return fail(MDN_ERR_UNSUPPORTED, "two padding modes");
   if ((d->flags & MDN_TERM_CONSIS) && d->mask_mode == MDN_MASK_SHARED)
     return fail(MDN_ERR_UNSUPPORTED, "consistency term needs two mobile maps (not MDN_MASK_SHARED)");
   const int f = d->flags;
@@ -939,8 +941,9 @@ static int check_desc(const MdnLossDesc* d) {
   return MDN_OK;
 }
 
-static WarpGeom make_geom(int h, int w, bool cuda_arith, bool flowwarp_norm) {
+static WarpGeom make_geom(int h, int w, bool cuda_arith, bool flowwarp_norm, int pad = 0) {
   WarpGeom G;
+  G.pad = pad;
   G.wm1 = (float)(w - 1); G.hm1 = (float)(h - 1);
   G.inv_wm1 = (float)(1.0 / (double)(w - 1)); G.inv_hm1 = (float)(1.0 / (double)(h - 1));
   G.cuda_arith = cuda_arith; G.flowwarp_norm = flowwarp_norm;
@@ -1151,6 +1154,10 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
     if (a == cudaSuccess) a = cudaFuncSetAttribute(fused_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (a == cudaSuccess) a = cudaFuncSetAttribute(fused_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (a == cudaSuccess) a = cudaFuncSetAttribute(fused_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (a == cudaSuccess) a = cudaFuncSetAttribute(fused_tile_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (a == cudaSuccess) a = cudaFuncSetAttribute(fused_tile_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (a == cudaSuccess) a = cudaFuncSetAttribute(fused_tile_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (a == cudaSuccess) a = cudaFuncSetAttribute(fused_tile_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (a != cudaSuccess) {
       cudaGetLastError();
       snprintf(g_err, sizeof(g_err), "the fused kernel needs %d bytes of opt-in shared memory per block on device %d: %s", bytes, dev_index,
@@ -1159,7 +1166,13 @@ static int launch_fused(const MdnLossDesc* d, float* loss_out, void* workspace, 
     }
     smem_opt_in_devices.fetch_or(dev_bit, std::memory_order_release);
   }
-  if (photo && maps) { auto kfn = fused_tile_kernel<true, true>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
+  // padding_mode of the flow warp other than zeros: its own instantiations (the zeros-padding kernels are untouched)
+  const int pad = (d->flags & MDN_OPT_PAD_BORDER) ? 1 : ((d->flags & MDN_OPT_PAD_REFLECTION) ? 2 : 0);
+  if (photo && pad == 1 && maps) { auto kfn = fused_tile_kernel<true, true, 1>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
+  else if (photo && pad == 1) { auto kfn = fused_tile_kernel<true, false, 1>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
+  else if (photo && pad == 2 && maps) { auto kfn = fused_tile_kernel<true, true, 2>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
+  else if (photo && pad == 2) { auto kfn = fused_tile_kernel<true, false, 2>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
+  else if (photo && maps) { auto kfn = fused_tile_kernel<true, true>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
   else if (photo) { auto kfn = fused_tile_kernel<true, false>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
   else if (maps) { auto kfn = fused_tile_kernel<false, true>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
   else { auto kfn = fused_tile_kernel<false, false>; MDN_LAUNCH_PDL(2, kfn, grid, block, smem, stream, K); }
@@ -1297,7 +1310,7 @@ extern "C" MDN_API int mdn_flow_warp_fwd(const float* ref, const float* flow, fl
   if (!flow || (warped && !ref)) return fail(MDN_ERR_NULL_POINTER, "flow / ref is NULL");
   if (batch < 1 || channels < 0 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad warp shape (h,w >= 2)");
   MDN_LAUNCH(flow_warp_fwd_kernel, dim3(blocks_for((long long)height * width), batch), dim3(NTHREADS), 0, (cudaStream_t)stream, ref, flow, warped,
-             grid_out, valid, (int)channels, (int)height, (int)width, make_geom(height, width, (warp_flags & 2) != 0, (warp_flags & 1) != 0));
+             grid_out, valid, (int)channels, (int)height, (int)width, make_geom(height, width, (warp_flags & 2) != 0, (warp_flags & 1) != 0, (warp_flags >> 2) & 3));
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }
@@ -1307,7 +1320,7 @@ extern "C" MDN_API int mdn_flow_warp_bwd(const float* ref, const float* flow, co
   if (!ref || !flow || !g_warped || !g_flow) return fail(MDN_ERR_NULL_POINTER, "ref / flow / g_warped / g_flow is NULL");
   if (batch < 1 || channels < 1 || height < 2 || width < 2) return fail(MDN_ERR_BAD_SHAPE, "bad warp shape (h,w >= 2)");
   MDN_LAUNCH(flow_warp_bwd_kernel, dim3(blocks_for((long long)height * width), batch), dim3(NTHREADS), 0, (cudaStream_t)stream, ref, flow, g_warped,
-             g_flow, (int)channels, (int)height, (int)width, make_geom(height, width, (warp_flags & 2) != 0, false));
+             g_flow, (int)channels, (int)height, (int)width, make_geom(height, width, (warp_flags & 2) != 0, false, (warp_flags >> 2) & 3));
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MDN_OK : fail(MDN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }

@@ -14,7 +14,7 @@ Same constructor / method signatures, same returned structures and the same numb
 * Only ``losses["loss"]`` carries a grad_fn; the per-term entries are detached values (the reference's are
   differentiable, nobody differentiates them).  The per-pixel ``outputs`` maps are computed lazily on first
   access (they are read every 50 batches for TensorBoard, trainer.py:248-250), and are not differentiable.
-* ``padding_mode`` other than "zeros" is rejected (the reference only ever passes "zeros").
+* ``padding_mode``: "zeros" (what every upstream caller passes), "border" and "reflection" as in ``F.grid_sample``.
 * ``arith="cuda"`` (default) replays the rounding of the reference's CUDA-eager path, ``arith="cpu"`` that of its
   CPU path; they differ where ATen divides a tensor by a Python scalar (a reciprocal multiply on CUDA), which
   moves warp coordinates by an ulp and can flip a bilinear cell (MDN_OPT_CUDA_ARITH in include/mdn_loss.h).
@@ -92,8 +92,8 @@ class LossModule(nn.Module):
     def __init__(self, opt, batch=None, ssim=None, padding_mode="zeros", cuda=True, *, mode=None, weights=None,
                  ds_base="SN", library=None, arith="cuda"):
         super().__init__()
-        if padding_mode != "zeros":
-            raise NotImplementedError("mdn_sfm_b200: only padding_mode='zeros' is implemented")
+        if padding_mode not in _cabi.PAD_FLAG:
+            raise ValueError("padding_mode must be 'zeros', 'border' or 'reflection' (torch.nn.functional.grid_sample)")
         if not cuda:
             raise RuntimeError("mdn_sfm_b200.LossModule has no CPU path (cuda=False is not supported)")
         self.options = opt
@@ -198,7 +198,7 @@ class LossModule(nn.Module):
         S = fused.ScaleData(h, w, 1.0, 1.0, 1.0, tgt=target)
         S.ref[0], S.flow[0] = reference, flow_map
         cfg = fused.FusedConfig(cuda_arith=self._cuda_arith, batch=b, n_pairs=1, post=fused.POST_T, mask_mode=MASK_SHARED,
-                                flags=TERM_PHOTO | (OPT_SSIM if self.ssim is not None else 0),
+                                flags=TERM_PHOTO | (OPT_SSIM if self.ssim is not None else 0) | _cabi.PAD_FLAG[self.padding_mode],
                                 want_maps=("warped", "diff", "valid"))
         total, _, maps = fused.fused_loss(cfg, [S], self._library)
         valid = maps["valid"][0].bool().expand(b, 3, h, w)
@@ -237,8 +237,8 @@ class Loss(nn.Module):
     def __init__(self, opt, no_ssim=True, padding_mode="zeros", alpha=1, *, mode=None, photometric=None, weights=None,
                  ds_base="SN", library=None, arith="cuda"):
         super().__init__()
-        if padding_mode != "zeros":
-            raise NotImplementedError("mdn_sfm_b200: only padding_mode='zeros' is implemented")
+        if padding_mode not in _cabi.PAD_FLAG:
+            raise ValueError("padding_mode must be 'zeros', 'border' or 'reflection' (torch.nn.functional.grid_sample)")
         self.ssim = None if no_ssim else SSIM()
         self.opt = opt
         self.alpha = alpha   # stored but unused, as upstream (LossModule reads opt.alpha, loss_functions.py:16)
@@ -357,7 +357,7 @@ class Loss(nn.Module):
         if not o.disable_consisloss:
             flags |= TERM_CONSIS
         if self.photometric:
-            flags |= TERM_PHOTO | (OPT_SSIM if self.ssim is not None else 0)
+            flags |= TERM_PHOTO | (OPT_SSIM if self.ssim is not None else 0) | _cabi.PAD_FLAG[self.padding_mode]
         data, F_all, poses = self._scale_data(inputs, ids, flow, mobile, instances_info, scales, cam_T_cam, post, bits)
         cams = inv_Ks = aas = trs = None
         if poses is not None and poses[0] == "cam":

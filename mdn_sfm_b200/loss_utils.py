@@ -30,10 +30,11 @@ def inverse_warp(ref_img, flow_map, pix_coords, padding_mode, library=None, arit
     (it must be the regular pixel grid, which is what every caller passes).  `arith` picks which of the
     reference's two roundings of `grid /= (w-1)` is replayed: its CUDA-eager one (default) or its CPU one.
     """
-    if padding_mode != "zeros":
-        raise NotImplementedError("mdn_sfm_b200: only padding_mode='zeros' is implemented")
+    if padding_mode not in _cabi.WARP_PAD:
+        raise ValueError("padding_mode must be 'zeros', 'border' or 'reflection' (torch.nn.functional.grid_sample)")
     ref_img, flow_map = _c(ref_img, "ref_img"), _c(flow_map, "flow_map")
-    warped, _, valid = FlowWarpFn.apply(ref_img, flow_map, _cabi.WARP_CUDA_ARITH if _arith_flag(arith) else 0, True, library)
+    warped, _, valid = FlowWarpFn.apply(ref_img, flow_map, (_cabi.WARP_CUDA_ARITH if _arith_flag(arith) else 0) | _cabi.WARP_PAD[padding_mode],
+                                        True, library)
     return warped, valid.bool().unsqueeze(1).expand(-1, ref_img.shape[1], -1, -1)
 
 

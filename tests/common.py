@@ -87,17 +87,17 @@ class tie_ruling:
 
 
 def oracle_run(opt, batch, mode, photo, ssim_on, device="cpu", pose_grad=False, product_device=None, library=None,
-               rule_ties=True):
+               rule_ties=True, padding_mode="zeros"):
     """product_device / library: where (and with which build) the product's instance masks are made for the DS / DC tie
     ruling (see tie_ruling); default = the oracle's own device.  rule_ties=False: the oracle exactly as it is (comparisons
     against the reference's golden fixtures, where no product is involved)."""
     if rule_ties and mode in ("DS", "DC") and batch[4] is not None:
         with tie_ruling(product_device or device, library):
-            return _oracle_run(opt, batch, mode, photo, ssim_on, device, pose_grad)
-    return _oracle_run(opt, batch, mode, photo, ssim_on, device, pose_grad)
+            return _oracle_run(opt, batch, mode, photo, ssim_on, device, pose_grad, padding_mode)
+    return _oracle_run(opt, batch, mode, photo, ssim_on, device, pose_grad, padding_mode)
 
 
-def _oracle_run(opt, batch, mode, photo, ssim_on, device="cpu", pose_grad=False):
+def _oracle_run(opt, batch, mode, photo, ssim_on, device="cpu", pose_grad=False, padding_mode="zeros"):
     inputs, flows, mobiles, cams, inst = batch
     mv = lambda d: {k: v.to(device) for k, v in d.items()}
     inputs, cams = mv(inputs), mv(cams)
@@ -110,12 +110,13 @@ def _oracle_run(opt, batch, mode, photo, ssim_on, device="cpu", pose_grad=False)
     scales = sorted({k[2] for k in flows})
     weights = restate.gauss_distance_weight(4, H, W) if mode == "TG" else None
     out, losses = restate.loss_forward(opt, inputs, [-1, 1], f, m, inst, scales, cams, mode=mode, weights=weights,
-                                       photometric=photo, ssim_on=ssim_on)
+                                       photometric=photo, ssim_on=ssim_on, padding_mode=padding_mode)
     losses["loss"].backward()
     return out, losses, f, m, cams
 
 
-def product_run(opt, batch, mode, photo, ssim_on, device, pose_grad=False, library=None, arith=None, pose_in=True):
+def product_run(opt, batch, mode, photo, ssim_on, device, pose_grad=False, library=None, arith=None, pose_in=True,
+                padding_mode="zeros"):
     arith = arith or ("cuda" if str(device).startswith("cuda") else "cpu")
     from mdn_sfm_b200.loss_functions import Loss
     inputs, flows, mobiles, cams, inst = batch
@@ -127,7 +128,7 @@ def product_run(opt, batch, mode, photo, ssim_on, device, pose_grad=False, libra
     if pose_grad:
         cams = leaf(cams)
     scales = sorted({k[2] for k in flows})
-    loss = Loss(opt, no_ssim=not ssim_on, mode=mode, photometric=photo, library=library, arith=arith)
+    loss = Loss(opt, no_ssim=not ssim_on, padding_mode=padding_mode, mode=mode, photometric=photo, library=library, arith=arith)
     loss.pose_in = pose_in
     out, losses = loss(inputs, [-1, 1], f, m, inst, scales, cams)
     losses["loss"].backward()

@@ -109,6 +109,34 @@ def test_loss_module_methods():
             assert float(lm.losses[k]) == pytest.approx(float(olm.losses[k]), rel=1e-5), k
 
 
+@pytest.mark.parametrize("padding_mode", ["border", "reflection"])
+def test_padding_modes_of_the_flow_warp(padding_mode):
+    """Loss(padding_mode=...) / inverse_warp(..., padding_mode): grid_sample's border and reflection modes (the ctor argument of
+    loss_functions.py:12,161; upstream callers pass "zeros").  Large flows, so that many samples leave the image and are
+    clipped / folded back -- values, validity and the gradient through the clipped coordinate against the oracle."""
+    from mdn_sfm_b200 import loss_utils
+    opt, batch = common.make(2, 24, 72, scales=(0, 1), seed=17, flow_std=0.4)
+    ref = common.oracle_run(opt, batch, "T", True, True, padding_mode=padding_mode)
+    with emulated():
+        got = common.product_run(opt, batch, "T", True, True, "cpu", padding_mode=padding_mode)
+        common.compare(ref, got, True)
+        g = torch.Generator().manual_seed(22)
+        B, h, w = 2, 19, 37
+        img, x = torch.rand(B, 3, h, w, generator=g), torch.rand(B, 3, h, w, generator=g)
+        flow = torch.randn(B, 2, h, w, generator=g) * 25
+        pix = restate.create_coords(B, h, w)
+        fo = flow.clone().requires_grad_(True)
+        wo, vo = restate.inverse_warp(img, fo, pix, padding_mode)
+        (wo * x).sum().backward()
+        fg = flow.clone().requires_grad_(True)
+        wg, vg = loss_utils.inverse_warp(img, fg, pix, padding_mode, arith="cpu")
+        (wg * x).sum().backward()
+        assert common.rel_max(wo, wg) < 1e-5 and torch.equal(vo, vg)
+        assert common.rel_max(fo.grad, fg.grad) < 1e-4
+    with pytest.raises(ValueError):
+        loss_utils.inverse_warp(img, flow, pix, "circular")
+
+
 def test_free_functions():
     from mdn_sfm_b200 import layers, loss_utils, utils
     g = torch.Generator().manual_seed(21)

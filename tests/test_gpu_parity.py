@@ -188,6 +188,17 @@ def test_batch_stager_uploads_what_the_loader_wrote():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("padding_mode", ["border", "reflection"])
+def test_padding_modes_on_gpu(padding_mode):
+    """grid_sample's other padding modes through Loss(padding_mode=...) (loss_functions.py:12,161) against the oracle run
+    eagerly on the same GPU, flows large enough that a fifth of the samples leave the image; multi-tile shape, 4 scales."""
+    opt, batch = common.make(2, 64, 192, seed=23, flow_std=0.3)
+    ref = common.oracle_run(opt, batch, "TG", True, True, DEV, padding_mode=padding_mode)
+    got = common.product_run(opt, batch, "TG", True, True, DEV, padding_mode=padding_mode)
+    common.compare(ref, got, True)
+
+
+@pytest.mark.gpu
 def test_instance_mask_prep_on_gpu_matches_torchvision():
     """mdn_instance_mask_union + mdn_instance_mask_resize on the GPU == the reference's
     Resize(size)(get_batch_instance_mask(.)) (torchvision on the CPU, int64), all four pyramid levels from one pass,
