@@ -15,16 +15,16 @@ CFG = dict(max_examples=10, deadline=None, derandomize=True, suppress_health_che
 @settings(**CFG)
 @given(B=st.integers(1, 2), H=st.integers(3, 21), W=st.integers(3, 70), mode=st.sampled_from(["SN", "T", "TG"]),
        photo=st.booleans(), ssim=st.booleans(), dmin=st.booleans(), dsm=st.booleans(), dcs=st.booleans(),
-       fstd=st.sampled_from([0.02, 0.1, 0.5]), seed=st.integers(0, 10 ** 6))
-def test_random_shapes_modes_and_switches_match_the_oracle(B, H, W, mode, photo, ssim, dmin, dsm, dcs, fstd, seed):
+       fstd=st.sampled_from([0.02, 0.1, 0.5]), seed=st.integers(0, 10 ** 6), pad=st.sampled_from(["zeros", "zeros", "border", "reflection"]))
+def test_random_shapes_modes_and_switches_match_the_oracle(B, H, W, mode, photo, ssim, dmin, dsm, dcs, fstd, seed, pad):
     if mode == "TG" and (H < 8 or W < 8):
         mode = "T"         # (the reference's Gaussian weight table needs 8 pixels over its pyramid)
     opt, batch = common.make(B, H, W, scales=(0,), seed=seed, flow_std=fstd, disable_min=dmin, disable_smoothloss=dsm,
                              disable_consisloss=dcs)
     batch = batch[:4] + (None,)
-    ref = common.oracle_run(opt, batch, mode, photo, ssim, pose_grad=True)
+    ref = common.oracle_run(opt, batch, mode, photo, ssim, pose_grad=True, padding_mode=pad)
     with emulated():
-        got = common.product_run(opt, batch, mode, photo, ssim, "cpu", pose_grad=True)
+        got = common.product_run(opt, batch, mode, photo, ssim, "cpu", pose_grad=True, padding_mode=pad)
         common.compare(ref, got, photo)      # (inside: the lazily computed per-pixel outputs launch on first access)
 
 
