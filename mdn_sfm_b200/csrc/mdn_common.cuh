@@ -579,6 +579,11 @@ MDN_DEV void cp_async_wait_all() {
 
 MDN_DEV float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 MDN_DEV float signf_(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+// signf_(x) * v, bit for bit (v finite), in three instructions instead of five: the sign bit of x flips v; zero / NaN x give 0
+MDN_DEV float signmul(float x, float v) {
+  const float r = __uint_as_float(__float_as_uint(v) ^ (__float_as_uint(x) & 0x80000000u));
+  return (x < 0.f || x > 0.f) ? r : 0.f;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Transposing butterfly: reduces NV per-lane values over the 32 lanes of a warp with NV-ish shuffles
@@ -586,11 +591,8 @@ MDN_DEV float signf_(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f
 template <int NV>
 MDN_DEV void warp_reduce_transpose(float* v) {
   const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int m = 16; m >= NV && m >= 1; m >>= 1) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], m);
-  }
+  // the halving (transposing) steps first: they leave ONE value per lane, so the full-width steps that fold the 32 / NV
+  // groups of lanes cost one shuffle each instead of NV
 #pragma unroll
   for (int half = NV / 2; half >= 1; half >>= 1) {
     const bool up = (lane & half) != 0;
@@ -601,6 +603,8 @@ MDN_DEV void warp_reduce_transpose(float* v) {
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
     }
   }
+#pragma unroll
+  for (int m = NV; m <= 16; m <<= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
 }
 
 }  // namespace mdn

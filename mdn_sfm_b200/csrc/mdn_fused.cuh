@@ -393,11 +393,11 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
         // d0 = m(x-1) - m(x), d1 = m(x) - m(x+1), d2 = m(x+1) - m(x+2); each pixel counts its right / lower edge
         const float d0 = ml[k] - mc.x, d1 = mc.x - mc.y, d2 = mc.y - mr[k];
         acc[SL_SMX + 2 * q] += fabsf(d1) * eh[k][1] + fabsf(d2) * eh[k][2];
-        const float s0 = signf_(d0) * eh[k][0], s1 = signf_(d1) * eh[k][1], s2 = signf_(d2) * eh[k][2];
+        const float s0 = signmul(d0, eh[k][0]), s1 = signmul(d1, eh[k][1]), s2 = signmul(d2, eh[k][2]);
         const float2 du = fma2(mc, splat2(-1.f), mu), dn = fma2(mn, splat2(-1.f), mc);   // m(y-1) - m(y), m(y) - m(y+1)
         acc[SL_SMY + 2 * q] += fabsf(dn.x) * ev[k + 1].x + fabsf(dn.y) * ev[k + 1].y;
-        gm.x += cx * (s1 - s0) + cy * (signf_(dn.x) * ev[k + 1].x - signf_(du.x) * ev[k].x);
-        gm.y += cx * (s2 - s1) + cy * (signf_(dn.y) * ev[k + 1].y - signf_(du.y) * ev[k].y);
+        gm.x += cx * (s1 - s0) + cy * (signmul(dn.x, ev[k + 1].x) - signmul(du.x, ev[k].x));
+        gm.y += cx * (s2 - s1) + cy * (signmul(dn.y, ev[k + 1].y) - signmul(du.y, ev[k].y));
       }
       float2 g0, g1;
       if (own) { g0 = q ? make_float2(0.f, 0.f) : gm; g1 = q ? gm : make_float2(0.f, 0.f); }
@@ -557,7 +557,8 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
 #pragma unroll 1
       for (int it = it0; it < N_IT; ++it) {
         Slot nxt;
-        prep(it + 1, nxt);
+        if (it + 1 < N_IT) prep(it + 1, nxt);      // (block-uniform: nothing to prepare behind the last slot)
+        else { nxt = cur; nxt.live = false; }
         if (!cur.live) break;
         const bool oka = (cur.ya | cur.xa) >= 0, okb = (cur.ya | cur.xb) >= 0;
         // flow -> pixels with SCALAR multiplies (see gather_pair)
@@ -638,8 +639,8 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
             if ((y < h) & in1) S.diff[pair][((size_t)b * 3 + c) * hw + (size_t)y * w + px1] = a1;
           }
           if (grads) {
-            wbar[k].x -= c_l1 * signf_(d0) * vmask[k].x;
-            wbar[k].y -= c_l1 * signf_(d1) * vmask[k].y;
+            wbar[k].x -= signmul(d0, c_l1 * vmask[k].x);      // == c_l1 * sign(d0) * valid: every factor but one is 0 / +-1
+            wbar[k].y -= signmul(d1, c_l1 * vmask[k].y);
             const float* Dd = sm.D + (k * FT + tid) * 2 + (2 * c) * PR * FT * 2;
             gix[k] = fma2(wbar[k], ld2s(Dd), gix[k]);
             giy[k] = fma2(wbar[k], ld2s(Dd + PR * FT * 2), giy[k]);
@@ -825,7 +826,7 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
               const float2 rb = make_float2(rcp_fast(bge.x), rcp_fast(bge.y));
               const float2 tnt = fma2(mul2(m, rb), splat2(-1.f), lg);            // lg - m / (bg + 1e-5)
               mb = fma2(post, splat2(-c_epi), mb);
-              mb.x += c_nt * signf_(ml.x) * tnt.x; mb.y += c_nt * signf_(ml.y) * tnt.y;
+              mb.x += signmul(ml.x, c_nt * tnt.x); mb.y += signmul(ml.y, c_nt * tnt.y);
               // d(loss)/dd = c_epi bg kmask 2 (d k) k
               const float2 dbar = mul2(mul2(mul2(bg, kmask), splat2(2.f * c_epi)), mul2(rs, kw));
               const float2 g2 = mul2(mul2(dbar, rden), live);

@@ -48,6 +48,7 @@ def main():
     by_line = collections.Counter()
     by_op = collections.Counter()
     text = {}
+    seen_addr = set()
     for r in src:
         if len(r) >= 2 and r[0] == "File Path":
             cur = r[1].split("/")[-1]
@@ -61,6 +62,9 @@ def main():
             except ValueError:
                 pass
         elif r[0] == "" and r[2].startswith("0x"):
+            if r[2] in seen_addr:      # an inlined instruction is listed under every source line of its call chain: count it once
+                continue
+            seen_addr.add(r[2])
             try:
                 n = int(r[7])
             except ValueError:
@@ -71,7 +75,7 @@ def main():
             if parts:
                 by_op[parts[0].split(".")[0]] += n
     tot = sum(by_line.values())
-    print("total executed warp-instructions (source page):", tot)
+    print("executed warp-instructions summed over source lines (inlined code counts once per line of its call chain):", tot)
     print("top source lines:")
     for (f, ln), n in by_line.most_common(nlines):
         print(f"  {100 * n / tot:5.2f}% {n:>10d} {f}:{ln}  {text[(f, ln)]}")
