@@ -40,7 +40,10 @@ def _worker(rank, world, port, mode, q):
     slow = D.max_over_ranks(1.0 + rank)
     if rank == 0:
         _, gl, gf, _, _ = common.oracle_run(opt_g, batch, mode, True, True)
-        q.put((mean, {k: float(gl[k].detach()) for k in mean}, torch.cat(gathered, 0), gf[("flow", 1, 0)].grad, slow))
+        # numpy arrays travel BY VALUE: a torch tensor on a Queue is a shared-memory handle that the parent can only open
+        # while this process is alive, and the worker may exit first (seen as FileNotFoundError in the parent's q.get)
+        q.put(({k: float(v) for k, v in mean.items()}, {k: float(gl[k].detach()) for k in mean}, torch.cat(gathered, 0).numpy().copy(),
+               gf[("flow", 1, 0)].grad.numpy().copy(), float(slow)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -54,6 +57,7 @@ def test_rank_mean_equals_global_batch(mode):
     for p in procs:
         p.start()
     mean, glob, g_sharded, g_global, slow = q.get(timeout=300)
+    g_sharded, g_global = torch.from_numpy(g_sharded), torch.from_numpy(g_global)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
