@@ -527,6 +527,15 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
       // pixels -- no reflection / slot arithmetic, one LDG.64 per flow plane, next row's flow loaded a row ahead
       const bool tile_full = weven & (x0 + TW <= w) & (y0 + TH <= h);
 #ifdef MDN_ABLATE_P1
+      const int it0 = N_IT;
+#else
+      const int it0 = tile_full ? PR : 0;
+#endif
+      Slot cur;
+      // the first slot of the rolled loop (on a full tile: this thread's halo-ring slot) is prepared BEFORE the own rows, so that its
+      // flow loads fly while the own rows are gathered (-1 % per step; the slot's geometry costs ten registers across the own rows)
+      prep(it0, cur);
+#ifdef MDN_ABLATE_P1
       if (false) {
 #else
       if (tile_full) {
@@ -547,13 +556,6 @@ __global__ void __launch_bounds__(FT, MDN_FUSED_MIN_CTAS) fused_tile_kernel(cons
           put(G2, va, vb, PR * g + 2 + k, 2 * t + 2, true, true, k, fxc, fyc);
         }
       }
-#ifdef MDN_ABLATE_P1
-      const int it0 = N_IT;
-#else
-      const int it0 = tile_full ? PR : 0;
-#endif
-      Slot cur;
-      prep(it0, cur);
 #pragma unroll 1
       for (int it = it0; it < N_IT; ++it) {
         Slot nxt;
