@@ -10,6 +10,10 @@ import torch
 
 from mdn_sfm_b200 import loss_utils, synthetic
 
+if "--lib" in sys.argv:   # a tuning build instead of the in-tree library
+    from mdn_sfm_b200 import _cabi
+    _cabi._lib = _cabi.Library(os.path.abspath(sys.argv[sys.argv.index("--lib") + 1]))
+
 g = torch.Generator().manual_seed(5)
 inst = [{"instances": d["instances"].to("cuda")} for d in synthetic.make_instances(12, g)]
 sizes = [(192, 640), (96, 320), (48, 160), (24, 80)]
